@@ -1,0 +1,101 @@
+"""ctypes binding of the C ABI declared in include/cagc_b200.h.
+
+This is the only place the native library is loaded.  There is no fallback: if
+`lib/libcagc_b200.so` is missing or its ABI version differs, importing this
+module raises, and every op of the package is unusable ("no CPU
+fallback in product code").  Build it with `python __graft_entry__.py` (or
+`python -m b200gan.build`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), 'lib', 'libcagc_b200.so')
+ABI_VERSION = 5
+
+_p = C.c_void_p
+_i = C.c_int
+_l = C.c_int64
+_f = C.c_float
+
+# name -> (restype, argtypes); mirrors include/cagc_b200.h one to one
+SIGNATURES = {
+    'cagc_abi_version': (_i, []),
+    'cagc_last_error': (C.c_char_p, []),
+    'cagc_launch_count': (_l, []),
+    'cagc_upfirdn2d': (_i, [_p, _p, _p, _p, _l, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i]),
+    'cagc_fused_bias_act': (_i, [_p, _p, _p, _p, _p, _l, _l, _i, _i, _i, _f, _f]),
+    'cagc_bias_grad_chunks': (_i, [_l]),
+    'cagc_fused_bias_act_bwd': (_i, [_p, _p, _p, _p, _p, _l, _i, _l, _f, _f]),
+    'cagc_conv_same': (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _l, _i, _i]),
+    'cagc_conv_up': (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i]),
+    'cagc_conv_up_dgrad': (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i]),
+    'cagc_conv_wgrad_splits': (_i, [_i, _i, _i, _i, _i, _i]),
+    'cagc_conv_wgrad': (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i]),
+    'cagc_fir_nhwc': (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _l, _i]),
+    'cagc_act_bwd_chunks': (_i, [_i, _i]),
+    'cagc_act_bwd': (_i, [_p, _p, _l, _l, _l, _l, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _l, _i]),
+    'cagc_mod_bwd': (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i]),
+    'cagc_torgb_fwd': (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _i, _i, _i, _i]),
+    'cagc_torgb_bwd': (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f]),
+    'cagc_to_nhwc': (_i, [_p, _p, _l, _l, _l, _l, _p, _i, _i, _i, _i, _i]),
+    'cagc_adam_step': (_i, [_p, _p, _p, _p, _p, _l, _f, _f, _f, _f, _f, _f, _f]),
+}
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f'native library {LIB_PATH} not found: build it with `python __graft_entry__.py` '
+            '(nvcc -gencode arch=compute_100a,code=sm_100a); there is no fallback path')
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    got = lib.cagc_abi_version()
+    if got != ABI_VERSION:
+        raise ImportError(f'{LIB_PATH}: ABI version {got}, expected {ABI_VERSION}; rebuild the library')
+    return lib
+
+
+lib = _load()
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str = ''):
+    """Turn a non-zero return code into a Python exception (the reference raises RuntimeError
+    through TORCH_CHECK, op/fused_bias_act.cpp:7-15)."""
+    if rc != 0:
+        msg = lib.cagc_last_error().decode('utf-8', 'replace')
+        raise NativeError(f'{what or "cagc"} failed (code {rc}): {msg}')
+
+
+def ptr(t):
+    """Device pointer of a tensor or NULL for None."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_of(t: torch.Tensor):
+    """Current CUDA stream of the tensor's device (the reference launches on the current stream
+    without a device guard, op/upfirdn2d_kernel.cu:213-215; callers here hold a device guard)."""
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise RuntimeError(f'{what}: this implementation is CUDA-only (sm_100a); got a {t.device.type} tensor. '
+                           'The CPU restatement lives in oracle/ and is test infrastructure.')
+    if t.dtype != torch.float32:
+        raise RuntimeError(f'{what}: only float32 tensors are supported, got {t.dtype}')
+
+
+def launch_count() -> int:
+    return int(lib.cagc_launch_count())

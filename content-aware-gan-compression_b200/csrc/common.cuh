@@ -1,0 +1,62 @@
+// Shared helpers for the cagc_b200 native library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <atomic>
+
+#include "cagc_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "cagc_b200 is written for sm_100a (B200) only"
+#endif
+
+namespace cagc {
+
+extern thread_local char g_err[512];
+extern std::atomic<int64_t> g_launches;
+
+inline int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+// call right after a kernel launch
+inline int launched(const char* what) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail((int)e, "%s: launch failed: %s", what, cudaGetErrorString(e));
+    return 0;
+}
+
+#define CAGC_REQUIRE(cond, ...)                                   \
+    do {                                                          \
+        if (!(cond)) return ::cagc::fail(CAGC_E_INVALID, __VA_ARGS__); \
+    } while (0)
+
+#define CAGC_TRY(expr)            \
+    do {                          \
+        int _rc = (expr);         \
+        if (_rc != 0) return _rc; \
+    } while (0)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+template <typename T>
+__host__ __device__ inline T ceil_div(T a, T b) { return (a + b - 1) / b; }
+
+constexpr float kSqrt2 = 1.41421356237309504880f;
+constexpr float kLreluSlope = 0.2f;
+constexpr int kNumSMs = 148;  // B200
+
+__device__ __forceinline__ float lrelu_sqrt2(float v) { return (v > 0.f ? v : v * kLreluSlope) * kSqrt2; }
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+}  // namespace cagc

@@ -1,0 +1,36 @@
+// Parameter block shared by the SIMT and tcgen05 convolution kernels.
+#pragma once
+#include "common.cuh"
+
+namespace cagc {
+
+constexpr int kMaxTaps = 25;
+
+struct Tap {
+    int dy, dx, slab;
+};
+
+struct ConvP {
+    const float* in;
+    const float* w;
+    const float* in_scale;
+    const float* out_scale;
+    const float* noise;
+    const float* noise_w;
+    const float* bias;
+    float* out;
+    int B, Hin, Win, in_pitch;
+    int Ho, Wo, in_stride;
+    int n_cols;  // weight slab leading dimension == out pitch
+    int out_valid;
+    int Hout, Wout, out_stride, out_oy, out_ox;
+    int64_t noise_bstride;
+    int act;
+    int ntaps;
+    Tap taps[kMaxTaps];
+};
+
+}  // namespace cagc
+
+// tcgen05 / TMA implicit-GEMM path (conv_tc.cu)
+int cagc_tc_conv(cudaStream_t stream, const cagc::ConvP& p, const char* what);

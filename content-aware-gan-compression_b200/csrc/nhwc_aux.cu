@@ -1,0 +1,477 @@
+// Bandwidth kernels around the modulated convolution on NHWC-p tensors:
+//   * fir_nhwc      : Blur after the transposed conv (model.py:270) + demod/noise/bias/lrelu epilogue
+//   * act_bwd       : backward of the StyledConv epilogue with the bias / noise-weight / demod
+//                     reductions folded into the same pass (SURVEY.md App. B "Backward")
+//   * mod_bwd       : gs reduction + gx = s*gx~ (style-modulation backward)
+//   * torgb fwd/bwd : 1x1 modulated conv to RGB + bias + upsampled skip (model.py:380-395)
+// All of them are HBM-bound: one 128-bit access per thread per tensor element, threads contiguous
+// along (pixel, channel), per-thread channel ownership so that the per-channel reductions live in
+// registers, fixed-order (deterministic) partial sums.
+#include "common.cuh"
+
+namespace cagc {
+
+// ------------------------------------------------------------------------------------------------
+// FIR on NHWC-p (up = down = 1) with fused epilogue
+// thread = one float4 of the flattened output row (x, c4); a strip of TR output rows is produced
+// from a ring of KH input rows kept in registers.
+// ------------------------------------------------------------------------------------------------
+template <int KH, int KW, int TR>
+__global__ void __launch_bounds__(256) fir_nhwc_kernel(const float* __restrict__ in, const float* __restrict__ fir,
+                                                       const float* __restrict__ out_scale,
+                                                       const float* __restrict__ noise,
+                                                       const float* __restrict__ noise_w,
+                                                       const float* __restrict__ bias, float* __restrict__ out,
+                                                       int in_h, int in_w, int out_h, int out_w, int pitch, int valid,
+                                                       int pad_x0, int pad_y0, int64_t noise_bstride, int act) {
+    __shared__ float skf[KH * KW];
+    if (threadIdx.x < KH * KW) {
+        int ky = threadIdx.x / KW, kx = threadIdx.x % KW;
+        skf[threadIdx.x] = fir[(KH - 1 - ky) * KW + (KW - 1 - kx)];
+    }
+    __syncthreads();
+    const int c4n = pitch >> 2;
+    const int pos = blockIdx.x * 256 + threadIdx.x;
+    if (pos >= out_w * c4n) return;
+    const int ox = pos / c4n, c = (pos - ox * c4n) * 4;
+    const int b = blockIdx.z;
+    const int oy0 = blockIdx.y * TR;
+
+    float kf[KH * KW];
+#pragma unroll
+    for (int i = 0; i < KH * KW; ++i) kf[i] = skf[i];
+
+    float4 scale4 = make_float4(1.f, 1.f, 1.f, 1.f), bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (out_scale) scale4 = ldg4(out_scale + (int64_t)b * pitch + c);
+    if (bias) bias4 = ldg4(bias + c);
+    const float nw = noise ? __ldg(noise_w) : 0.f;
+
+    const float* src = in + (int64_t)b * in_h * in_w * pitch + c;
+    const int ix0 = ox - pad_x0;
+    float4 ring[KH][KW];
+#pragma unroll
+    for (int r = 0; r < TR + KH - 1; ++r) {
+        const int iy = oy0 + r - pad_y0;
+        const bool rowok = iy >= 0 && iy < in_h && (oy0 + r - (KH - 1) < out_h);
+#pragma unroll
+        for (int j = 0; j < KW; ++j) {
+            const int ix = ix0 + j;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (rowok && ix >= 0 && ix < in_w) v = ldg4(src + ((int64_t)iy * in_w + ix) * pitch);
+            ring[r % KH][j] = v;
+        }
+        if (r >= KH - 1) {
+            const int q = r - (KH - 1);
+            const int oy = oy0 + q;
+            if (oy < out_h) {
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int i = 0; i < KH; ++i)
+#pragma unroll
+                    for (int j = 0; j < KW; ++j) {
+                        const float k = kf[i * KW + j];
+                        const float4 v = ring[(q + i) % KH][j];
+                        acc.x = fmaf(k, v.x, acc.x);
+                        acc.y = fmaf(k, v.y, acc.y);
+                        acc.z = fmaf(k, v.z, acc.z);
+                        acc.w = fmaf(k, v.w, acc.w);
+                    }
+                float v[4] = {acc.x * scale4.x, acc.y * scale4.y, acc.z * scale4.z, acc.w * scale4.w};
+                if (noise) {
+                    const float nz = nw * __ldg(noise + (int64_t)b * noise_bstride + (int64_t)oy * out_w + ox);
+                    v[0] += nz; v[1] += nz; v[2] += nz; v[3] += nz;
+                }
+                v[0] += bias4.x; v[1] += bias4.y; v[2] += bias4.z; v[3] += bias4.w;
+                if (act) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) v[j] = lrelu_sqrt2(v[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (c + j >= valid) v[j] = 0.f;
+                st4(out + (((int64_t)b * out_h + oy) * out_w + ox) * pitch + c, make_float4(v[0], v[1], v[2], v[3]));
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// epilogue backward.  block = (c4n, PY) threads: x = channel quad (fixed per thread), y = pixel lane
+// ------------------------------------------------------------------------------------------------
+constexpr int kChunkPixels = 1024;
+
+__global__ void __launch_bounds__(256) act_bwd_kernel(const float* __restrict__ ga, int64_t sb, int64_t sc, int64_t sh,
+                                                      int64_t sw, int ga_vec, const float* __restrict__ a,
+                                                      const float* __restrict__ d, const float* __restrict__ noise,
+                                                      const float* __restrict__ noise_w,
+                                                      const float* __restrict__ bias, float* __restrict__ gu,
+                                                      float* __restrict__ partial, int H, int W, int pitch, int valid,
+                                                      int64_t noise_bstride, int act, int chunks) {
+    extern __shared__ float4 red[];  // [PY][3][c4n]
+    const int c4n = blockDim.x, PY = blockDim.y;
+    const int cx = threadIdx.x, py = threadIdx.y;
+    const int c = cx * 4;
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const int HW = H * W;
+    const int per = ceil_div(HW, chunks);
+    const int p_lo = chunk * per, p_hi = min(HW, p_lo + per);
+
+    float4 d4 = make_float4(1.f, 1.f, 1.f, 1.f), bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (d) d4 = ldg4(d + (int64_t)b * pitch + c);
+    if (bias) bias4 = ldg4(bias + c);
+    const float nw = noise ? __ldg(noise_w) : 0.f;
+    // guard the division for padding channels (d == 0 there)
+    const float4 rd4 = make_float4(d4.x != 0.f ? 1.f / d4.x : 0.f, d4.y != 0.f ? 1.f / d4.y : 0.f,
+                                   d4.z != 0.f ? 1.f / d4.z : 0.f, d4.w != 0.f ? 1.f / d4.w : 0.f);
+    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f}, s3[4] = {0.f, 0.f, 0.f, 0.f};
+    const float dv[4] = {d4.x, d4.y, d4.z, d4.w}, rdv[4] = {rd4.x, rd4.y, rd4.z, rd4.w};
+    const float bv[4] = {bias4.x, bias4.y, bias4.z, bias4.w};
+    constexpr float kInvPos = 0.70710678118654752440f;            // 1/sqrt2
+    constexpr float kInvNeg = 0.70710678118654752440f / 0.2f;     // 1/(0.2*sqrt2)
+
+    for (int p = p_lo + py; p < p_hi; p += PY) {
+        const int y = p / W, x = p - y * W;
+        const int64_t off = ((int64_t)b * HW + p) * pitch + c;
+        const float4 a4 = ld4(a + off);
+        float gav[4];
+        const float* gp = ga + b * sb + y * sh + x * sw + (int64_t)c * sc;
+        if (ga_vec) {
+            const float4 t = ld4(gp);
+            gav[0] = t.x; gav[1] = t.y; gav[2] = t.z; gav[3] = t.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) gav[j] = (c + j < valid) ? gp[j * sc] : 0.f;
+        }
+        const float nz = noise ? nw * __ldg(noise + (int64_t)b * noise_bstride + p) : 0.f;
+        const float nraw = noise ? __ldg(noise + (int64_t)b * noise_bstride + p) : 0.f;
+        const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+        float guv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float gz, yv;
+            if (act) {
+                const bool pos = av[j] > 0.f;
+                gz = gav[j] * (pos ? kSqrt2 : kSqrt2 * kLreluSlope);
+                yv = av[j] * (pos ? kInvPos : kInvNeg) - nz - bv[j];
+            } else {
+                gz = gav[j];
+                yv = av[j] - nz - bv[j];
+            }
+            if (c + j >= valid) gz = 0.f;
+            guv[j] = gz * dv[j];
+            s1[j] += gz;
+            s2[j] = fmaf(gz * yv, rdv[j], s2[j]);
+            s3[j] = fmaf(gz, nraw, s3[j]);
+        }
+        st4(gu + off, make_float4(guv[0], guv[1], guv[2], guv[3]));
+    }
+    red[(py * 3 + 0) * c4n + cx] = make_float4(s1[0], s1[1], s1[2], s1[3]);
+    red[(py * 3 + 1) * c4n + cx] = make_float4(s2[0], s2[1], s2[2], s2[3]);
+    red[(py * 3 + 2) * c4n + cx] = make_float4(s3[0], s3[1], s3[2], s3[3]);
+    __syncthreads();
+    for (int q = py; q < 3; q += PY) {  // thread (cx, q) reduces quantity q over the pixel lanes in a fixed order
+        float4 t = red[(0 * 3 + q) * c4n + cx];
+        for (int k = 1; k < PY; ++k) {
+            const float4 v = red[(k * 3 + q) * c4n + cx];
+            t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+        }
+        st4(partial + ((((int64_t)b * chunks + chunk) * 3 + q) * pitch) + c, t);
+    }
+}
+
+__global__ void __launch_bounds__(256) mod_bwd_kernel(float* __restrict__ gxt, const float* __restrict__ x,
+                                                      const float* __restrict__ s, float* __restrict__ partial,
+                                                      int HW, int pitch, int chunks) {
+    extern __shared__ float4 red[];  // [PY][c4n]
+    const int c4n = blockDim.x, PY = blockDim.y;
+    const int cx = threadIdx.x, py = threadIdx.y, c = cx * 4;
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const int per = ceil_div(HW, chunks);
+    const int p_lo = chunk * per, p_hi = min(HW, p_lo + per);
+    const float4 s4 = ldg4(s + (int64_t)b * pitch + c);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int p = p_lo + py; p < p_hi; p += PY) {
+        const int64_t off = ((int64_t)b * HW + p) * pitch + c;
+        float4 g = ld4(gxt + off);
+        const float4 xv = ld4(x + off);
+        acc.x = fmaf(g.x, xv.x, acc.x);
+        acc.y = fmaf(g.y, xv.y, acc.y);
+        acc.z = fmaf(g.z, xv.z, acc.z);
+        acc.w = fmaf(g.w, xv.w, acc.w);
+        g.x *= s4.x; g.y *= s4.y; g.z *= s4.z; g.w *= s4.w;
+        st4(gxt + off, g);
+    }
+    red[py * c4n + cx] = acc;
+    __syncthreads();
+    if (py == 0) {
+        float4 t = red[cx];
+        for (int k = 1; k < PY; ++k) {
+            const float4 v = red[k * c4n + cx];
+            t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+        }
+        st4(partial + ((int64_t)b * chunks + chunk) * pitch + c, t);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// ToRGB forward: 8 lanes per pixel, 4 pixels per warp step, effective weights in shared memory
+// ------------------------------------------------------------------------------------------------
+constexpr int kRgbMaxOut = 4;
+constexpr int kRgbChunk = 256;  // pixels per CTA
+
+__global__ void __launch_bounds__(256) torgb_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                        const float* __restrict__ s, const float* __restrict__ bias,
+                                                        const float* __restrict__ skip, const float* __restrict__ fir,
+                                                        float* __restrict__ out, int H, int W, int pitch, int cin,
+                                                        int nout, float wscale, int fh, int fw, int pad0) {
+    extern __shared__ __align__(16) float weff[];  // [nout][pitch]
+    __shared__ float sfir[64];
+    const int b = blockIdx.y;
+    const int HW = H * W;
+    for (int i = threadIdx.x; i < nout * pitch; i += 256) {
+        const int o = i / pitch, c = i - o * pitch;
+        weff[i] = (c < cin) ? wscale * __ldg(w + o * cin + c) * __ldg(s + (int64_t)b * pitch + c) : 0.f;
+    }
+    if (skip)
+        for (int i = threadIdx.x; i < fh * fw; i += 256) {
+            const int ky = i / fw, kx = i - ky * fw;
+            sfir[i] = fir[(fh - 1 - ky) * fw + (fw - 1 - kx)];
+        }
+    __syncthreads();
+    const int lane8 = threadIdx.x & 7;
+    const int grp = threadIdx.x >> 3;  // 32 pixel groups per CTA
+    const int c4n = pitch >> 2;
+    const int p_lo = blockIdx.x * kRgbChunk;
+    const int p_hi = min(HW, p_lo + kRgbChunk);
+    const int Hs = H >> 1, Ws = W >> 1;
+    for (int pbase = p_lo; pbase < p_hi; pbase += 32) {  // warp-uniform trip count (shuffles below)
+        const int p = pbase + grp;
+        const bool pvalid = p < p_hi;
+        const float* xp = x + ((int64_t)b * HW + (pvalid ? p : p_lo)) * pitch;
+        float acc[kRgbMaxOut] = {0.f, 0.f, 0.f, 0.f};
+        for (int c4 = lane8; c4 < c4n; c4 += 8) {
+            const float4 xv = ldg4(xp + c4 * 4);
+#pragma unroll
+            for (int o = 0; o < kRgbMaxOut; ++o) {
+                if (o < nout) {
+                    const float4 wv = ld4(&weff[o * pitch + c4 * 4]);
+                    acc[o] = fmaf(xv.x, wv.x, acc[o]);
+                    acc[o] = fmaf(xv.y, wv.y, acc[o]);
+                    acc[o] = fmaf(xv.z, wv.z, acc[o]);
+                    acc[o] = fmaf(xv.w, wv.w, acc[o]);
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 0; o < kRgbMaxOut; ++o) {
+            acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], 4);
+            acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], 2);
+            acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], 1);
+        }
+        if (pvalid && lane8 < nout) {
+            const int o = lane8;
+            float v = acc[0];
+#pragma unroll
+            for (int q = 1; q < kRgbMaxOut; ++q)
+                if (o == q) v = acc[q];
+            if (bias) v += __ldg(bias + o);
+            const int y = p / W, xx = p - y * W;
+            if (skip) {
+                // Upsample(skip): zero-insert x2, pad (pad0, .), true convolution with fir (model.py:38-56)
+                const float* sp = skip + ((int64_t)b * nout + o) * Hs * Ws;
+                float u = 0.f;
+                for (int i = 0; i < fh; ++i) {
+                    const int ay = y + i - pad0;
+                    if (ay < 0 || (ay & 1)) continue;
+                    const int sy = ay >> 1;
+                    if (sy >= Hs) break;
+                    for (int j = 0; j < fw; ++j) {
+                        const int ax = xx + j - pad0;
+                        if (ax < 0 || (ax & 1)) continue;
+                        const int sx = ax >> 1;
+                        if (sx >= Ws) break;
+                        u = fmaf(sfir[i * fw + j], __ldg(sp + sy * Ws + sx), u);
+                    }
+                }
+                v += u;
+            }
+            out[((int64_t)b * nout + o) * HW + p] = v;
+        }
+    }
+}
+
+// ToRGB backward: block = (c4n, PY); gx written, per-sample T[o][c] partials
+__global__ void __launch_bounds__(256) torgb_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x,
+                                                        const float* __restrict__ w, const float* __restrict__ s,
+                                                        float* __restrict__ gx, float* __restrict__ partial, int HW,
+                                                        int pitch, int cin, int nout, float wscale, int chunks) {
+    extern __shared__ float4 red[];  // [PY][nout][c4n]
+    const int c4n = blockDim.x, PY = blockDim.y;
+    const int cx = threadIdx.x, py = threadIdx.y, c = cx * 4;
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const int per = ceil_div(HW, chunks);
+    const int p_lo = chunk * per, p_hi = min(HW, p_lo + per);
+    float4 we[kRgbMaxOut], T[kRgbMaxOut];
+    const float4 s4 = ldg4(s + (int64_t)b * pitch + c);
+    const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+    for (int o = 0; o < kRgbMaxOut; ++o) {
+        float t[4] = {0.f, 0.f, 0.f, 0.f};
+        if (o < nout) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (c + j < cin) t[j] = wscale * __ldg(w + o * cin + c + j) * sv[j];
+        }
+        we[o] = make_float4(t[0], t[1], t[2], t[3]);
+        T[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int p = p_lo + py; p < p_hi; p += PY) {
+        const int64_t off = ((int64_t)b * HW + p) * pitch + c;
+        const float4 xv = ld4(x + off);
+        float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int o = 0; o < kRgbMaxOut; ++o) {
+            if (o < nout) {
+                const float gv = __ldg(g + ((int64_t)b * nout + o) * HW + p);
+                o4.x = fmaf(we[o].x, gv, o4.x);
+                o4.y = fmaf(we[o].y, gv, o4.y);
+                o4.z = fmaf(we[o].z, gv, o4.z);
+                o4.w = fmaf(we[o].w, gv, o4.w);
+                T[o].x = fmaf(gv, xv.x, T[o].x);
+                T[o].y = fmaf(gv, xv.y, T[o].y);
+                T[o].z = fmaf(gv, xv.z, T[o].z);
+                T[o].w = fmaf(gv, xv.w, T[o].w);
+            }
+        }
+        st4(gx + off, o4);
+    }
+#pragma unroll
+    for (int o = 0; o < kRgbMaxOut; ++o)
+        if (o < nout) red[(py * nout + o) * c4n + cx] = T[o];
+    __syncthreads();
+    for (int o = py; o < nout; o += PY) {
+        float4 t = red[o * c4n + cx];
+        for (int k = 1; k < PY; ++k) {
+            const float4 v = red[(k * nout + o) * c4n + cx];
+            t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+        }
+        st4(partial + (((int64_t)b * chunks + chunk) * nout + o) * pitch + c, t);
+    }
+}
+
+static inline int pixel_chunks(int HW) {
+    int c = ceil_div(HW, kChunkPixels);
+    if (c < 1) c = 1;
+    if (c > 128) c = 128;
+    return c;
+}
+
+// (c4n, PY) block shape shared by the reduction kernels; PY >= need_py
+static inline int block_shape(int pitch, int need_py, dim3* blk) {
+    const int c4n = pitch / 4;
+    if (c4n < 1 || c4n > 256) return -1;
+    int PY = 256 / c4n;
+    if (PY < need_py) return -1;
+    if (PY > 64) PY = 64;
+    *blk = dim3(c4n, PY);
+    return 0;
+}
+
+}  // namespace cagc
+
+using namespace cagc;
+
+extern "C" {
+
+int cagc_fir_nhwc(cagc_stream_t stream_, const float* in, const float* fir, const float* out_scale, const float* noise,
+                  const float* noise_w, const float* bias, float* out, int B, int in_h, int in_w, int pitch, int valid,
+                  int kh, int kw, int pad_x0, int pad_x1, int pad_y0, int pad_y1, int64_t noise_bstride, int act) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CAGC_REQUIRE(in && fir && out, "fir_nhwc: null pointer");
+    CAGC_REQUIRE(pitch > 0 && pitch % 4 == 0, "fir_nhwc: pitch must be a positive multiple of 4");
+    CAGC_REQUIRE(!noise || noise_w, "fir_nhwc: noise without noise weight");
+    CAGC_REQUIRE(aligned16(in) && aligned16(out), "fir_nhwc: pointers must be 16-byte aligned");
+    if (kh != 4 || kw != 4) return fail(CAGC_E_UNSUPPORTED, "fir_nhwc: only 4x4 FIR kernels are implemented (got %dx%d)", kh, kw);
+    const int out_h = in_h + pad_y0 + pad_y1 - kh + 1, out_w = in_w + pad_x0 + pad_x1 - kw + 1;
+    if (B == 0 || out_h <= 0 || out_w <= 0) return 0;
+    CAGC_REQUIRE(B <= 65535, "fir_nhwc: batch too large");
+    constexpr int TR = 8;
+    dim3 grid(ceil_div(out_w * (pitch / 4), 256), ceil_div(out_h, TR), B);
+    fir_nhwc_kernel<4, 4, TR><<<grid, 256, 0, stream>>>(in, fir, out_scale, noise, noise_w, bias, out, in_h, in_w, out_h,
+                                                       out_w, pitch, valid, pad_x0, pad_y0, noise_bstride, act);
+    return launched("fir_nhwc_kernel");
+}
+
+int cagc_act_bwd_chunks(int H, int W) { return pixel_chunks(H * W); }
+
+int cagc_act_bwd(cagc_stream_t stream_, const float* ga, int64_t sb, int64_t sc, int64_t sh, int64_t sw, const float* a,
+                 const float* d, const float* noise, const float* noise_w, const float* bias, float* gu, float* partial,
+                 int B, int H, int W, int pitch, int valid, int64_t noise_bstride, int act) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CAGC_REQUIRE(ga && a && gu && partial, "act_bwd: null pointer");
+    CAGC_REQUIRE(pitch > 0 && pitch % 4 == 0, "act_bwd: pitch must be a positive multiple of 4");
+    CAGC_REQUIRE(!noise || noise_w, "act_bwd: noise without noise weight");
+    if (B == 0 || H * W == 0) return 0;
+    dim3 blk;
+    CAGC_REQUIRE(block_shape(pitch, 1, &blk) == 0, "act_bwd: pitch %d unsupported (max 1024)", pitch);
+    const int chunks = pixel_chunks(H * W);
+    // a float4 read may touch channels >= valid; that is only in bounds when the source pixel pitch
+    // covers our pitch (an NHWC-p buffer, or dense NHWC with C a multiple of 4)
+    const int vec = (sc == 1) && (sb % 4 == 0) && (sh % 4 == 0) && (sw % 4 == 0) && aligned16(ga) && (sw >= pitch);
+    dim3 grid(chunks, B);
+    const size_t smem = sizeof(float4) * blk.y * 3 * blk.x;
+    act_bwd_kernel<<<grid, blk, smem, stream>>>(ga, sb, sc, sh, sw, vec, a, d, noise, noise_w, bias, gu, partial, H, W,
+                                                pitch, valid, noise_bstride, act, chunks);
+    return launched("act_bwd_kernel");
+}
+
+int cagc_mod_bwd(cagc_stream_t stream_, float* gxt, const float* x, const float* s, float* partial, int B, int H, int W,
+                 int pitch) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CAGC_REQUIRE(gxt && x && s && partial, "mod_bwd: null pointer");
+    CAGC_REQUIRE(pitch > 0 && pitch % 4 == 0, "mod_bwd: pitch must be a positive multiple of 4");
+    if (B == 0 || H * W == 0) return 0;
+    dim3 blk;
+    CAGC_REQUIRE(block_shape(pitch, 1, &blk) == 0, "mod_bwd: pitch %d unsupported (max 1024)", pitch);
+    const int chunks = pixel_chunks(H * W);
+    dim3 grid(chunks, B);
+    mod_bwd_kernel<<<grid, blk, sizeof(float4) * blk.x * blk.y, stream>>>(gxt, x, s, partial, H * W, pitch, chunks);
+    return launched("mod_bwd_kernel");
+}
+
+int cagc_torgb_fwd(cagc_stream_t stream_, const float* x, const float* w, const float* s, const float* bias,
+                   const float* skip, const float* fir, float* out, int B, int H, int W, int pitch, int cin, int nout,
+                   float wscale, int fh, int fw, int pad0, int pad1) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    (void)pad1;
+    CAGC_REQUIRE(x && w && s && out, "torgb_fwd: null pointer");
+    CAGC_REQUIRE(pitch > 0 && pitch % 4 == 0 && cin <= pitch, "torgb_fwd: bad pitch");
+    CAGC_REQUIRE(nout >= 1 && nout <= kRgbMaxOut, "torgb_fwd: nout must be 1..4");
+    CAGC_REQUIRE(!skip || (fir && fh * fw <= 64 && H % 2 == 0 && W % 2 == 0), "torgb_fwd: bad skip/fir");
+    if (B == 0 || H * W == 0) return 0;
+    CAGC_REQUIRE(B <= 65535, "torgb_fwd: batch too large");
+    const size_t smem = sizeof(float) * nout * pitch;
+    CAGC_REQUIRE(smem <= 48 * 1024, "torgb_fwd: pitch too large");
+    dim3 grid(ceil_div(H * W, kRgbChunk), B);
+    torgb_fwd_kernel<<<grid, 256, smem, stream>>>(x, w, s, bias, skip, fir, out, H, W, pitch, cin, nout, wscale, fh, fw,
+                                                  pad0);
+    return launched("torgb_fwd_kernel");
+}
+
+int cagc_torgb_bwd(cagc_stream_t stream_, const float* g, const float* x, const float* w, const float* s, float* gx,
+                   float* partial, int B, int H, int W, int pitch, int cin, int nout, float wscale) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CAGC_REQUIRE(g && x && w && s && gx && partial, "torgb_bwd: null pointer");
+    CAGC_REQUIRE(pitch > 0 && pitch % 4 == 0 && cin <= pitch, "torgb_bwd: bad pitch");
+    CAGC_REQUIRE(nout >= 1 && nout <= kRgbMaxOut, "torgb_bwd: nout must be 1..4");
+    if (B == 0 || H * W == 0) return 0;
+    dim3 blk;
+    CAGC_REQUIRE(block_shape(pitch, 1, &blk) == 0, "torgb_bwd: pitch %d unsupported (max 1024)", pitch);
+    const int chunks = pixel_chunks(H * W);
+    dim3 grid(chunks, B);
+    const size_t smem = sizeof(float4) * blk.y * nout * blk.x;
+    torgb_bwd_kernel<<<grid, blk, smem, stream>>>(g, x, w, s, gx, partial, H * W, pitch, cin, nout, wscale, chunks);
+    return launched("torgb_bwd_kernel");
+}
+
+}  // extern "C"

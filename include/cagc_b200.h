@@ -1,0 +1,179 @@
+/*
+ * cagc_b200.h -- C ABI of the B200-native StyleGAN2 generator hot path.
+ *
+ * This is the drop-in boundary.  The reference binds two
+ * pybind11 modules at this level:
+ *
+ *   fused.fused_bias_act(input, bias, refer, act, grad, alpha, scale)   op/fused_bias_act.cpp:11-21
+ *   upfirdn2d.upfirdn2d(input, kernel, up_x, up_y, down_x, down_y,
+ *                       pad_x0, pad_x1, pad_y0, pad_y1)                  op/upfirdn2d.cpp:4-22
+ *
+ * and calls cuDNN/ATen for the modulated convolution (model.py:241-289).  Here
+ * every one of those is a plain `extern "C"` entry point taking device
+ * pointers, sizes and a CUDA stream: no torch types cross the boundary.  The
+ * caller owns all memory (inputs, outputs, workspaces); nothing is retained;
+ * every call is an asynchronous launch on `stream` and is re-entrant.
+ *
+ * Return value: 0 on success; a positive cudaError_t if a launch failed; a
+ * negative CAGC_E_* code for rejected arguments.  `cagc_last_error()` returns
+ * a thread-local human-readable message for the last non-zero return.
+ *
+ * Activation layout ("NHWC-p"): fp32, [B, H, W, pitch] with the channel pitch
+ * a multiple of 4 floats (16 B; the host side uses multiples of 8).  Channels
+ * >= the logical count are padding and are always written as zero.
+ */
+#ifndef CAGC_B200_H_
+#define CAGC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* cagc_stream_t; /* cudaStream_t */
+
+#define CAGC_E_INVALID   (-1)  /* bad argument (null pointer, bad size, misaligned pitch) */
+#define CAGC_E_UNSUPPORTED (-2) /* shape outside what the kernels implement */
+
+/* bump when a signature changes; the Python loader checks it */
+#define CAGC_ABI_VERSION 5
+
+int cagc_abi_version(void);
+const char* cagc_last_error(void);
+/* number of kernel launches issued through this library by the calling process (all threads) */
+int64_t cagc_launch_count(void);
+
+/* ------------------------------------------------------------------------
+ * upfirdn2d -- replaces upfirdn2d.upfirdn2d (op/upfirdn2d.cpp:4-22,
+ * op/upfirdn2d_kernel.cu:209-369).  Same tensor contract: input
+ * [major, in_h, in_w, minor], kernel [kh, kw], output
+ * [major, out_h, out_w, minor] with
+ *   out_h = (in_h*up_y + pad_y0 + pad_y1 - kh) / down_y + 1   (op/upfirdn2d.py:103-104)
+ * zero-insertion upsample -> pad/crop (negative pads crop) -> true 2-D
+ * convolution -> decimation.  fp32 only.
+ * ---------------------------------------------------------------------- */
+int cagc_upfirdn2d(cagc_stream_t stream, const float* input, const float* kernel, float* output,
+                   int64_t major, int in_h, int in_w, int minor, int kh, int kw,
+                   int up_x, int up_y, int down_x, int down_y,
+                   int pad_x0, int pad_x1, int pad_y0, int pad_y1);
+
+/* ------------------------------------------------------------------------
+ * fused_bias_act -- replaces fused.fused_bias_act (op/fused_bias_act.cpp:11-21,
+ * op/fused_bias_act_kernel.cu:19-99).  x = in[i] (+ bias[(i / step_b) % size_b]
+ * when bias != NULL); (act, grad) switch as in the reference: act 1 = linear,
+ * 3 = leaky ReLU; grad 0: y = x>0 ? x : alpha*x; grad 1: y = refer>0 ? x :
+ * alpha*x (refer = forward output); grad 2: y = 0.  out = y * scale.
+ * ---------------------------------------------------------------------- */
+int cagc_fused_bias_act(cagc_stream_t stream, const float* input, const float* bias, const float* refer,
+                        float* output, int64_t n, int64_t step_b, int size_b,
+                        int act, int grad, float alpha, float scale);
+
+/* Backward of fused leaky ReLU with the bias gradient reduced in the same pass
+ * (the reference runs a separate `grad_input.sum(dim)`, op/fused_act.py:33-39).
+ * Layout [outer, size_b, step_b]; grad_in = (refer>0 ? g : alpha*g)*scale;
+ * bias_partial is [outer * size_b * chunks] with chunks = cagc_bias_grad_chunks(step_b);
+ * the caller sums it over (outer, chunks). */
+int cagc_bias_grad_chunks(int64_t step_b);
+int cagc_fused_bias_act_bwd(cagc_stream_t stream, const float* grad_out, const float* refer, float* grad_in,
+                            float* bias_partial, int64_t outer, int size_b, int64_t step_b,
+                            float alpha, float scale);
+
+/* ------------------------------------------------------------------------
+ * Modulated convolution (model.py:241-289), fused form of SURVEY.md App. B.
+ *
+ * cagc_conv_same: k x k stride-1 "same" convolution over NHWC-p input with
+ * shared weights, optional per-(sample, in-channel) scale applied on load
+ * (style modulation), and a fused epilogue
+ *     y = out_scale[b,o] * u  (+ noise_w[0]*noise[b,y,x]) (+ bias[o]);  act: lrelu(0.2)*sqrt2
+ * It is also the data-gradient kernel (pass the flipped / transposed weight
+ * slabs).  Weight slabs: taps x [in_pitch rows][w_ld cols], zero padded,
+ * tap t = ky*k + kx reads input pixel (y + ky - k/2, x + kx - k/2).
+ * algo: 0 = fp32 SIMT (exact-order fp32, used by the saliency pass),
+ *       1 = tcgen05 TF32 implicit GEMM (sm_100a tensor pipe).
+ * ---------------------------------------------------------------------- */
+int cagc_conv_same(cagc_stream_t stream, const float* in, const float* w_slabs, const float* in_scale,
+                   const float* out_scale, const float* noise, const float* noise_w, const float* bias,
+                   float* out, int B, int H, int W, int in_pitch, int out_pitch, int out_valid,
+                   int ksize, int64_t noise_bstride, int act, int algo);
+
+/* Transposed stride-2 k x k convolution (model.py:259-267) of the modulated
+ * input: out_T[b, 2y+ky, 2x+kx, o] += in[b,y,x,i]*in_scale[b,i]*W[t][i][o];
+ * out_T is [B, 2H+k-2, 2W+k-2, out_pitch] and every element is written once
+ * (4 phase convolutions, no atomics). */
+int cagc_conv_up(cagc_stream_t stream, const float* in, const float* w_slabs, const float* in_scale,
+                 float* out_t, int B, int H, int W, int in_pitch, int out_pitch, int ksize, int algo);
+
+/* Data gradient of cagc_conv_up: g_in[b,y,x,i] = sum_{t,o} g_t[b,2y+ky,2x+kx,o] * Wd[t][o][i]
+ * (weight slabs taps x [g_pitch rows][w_ld = in_pitch cols]). */
+int cagc_conv_up_dgrad(cagc_stream_t stream, const float* g_t, const float* w_slabs, float* g_in,
+                       int B, int H, int W, int g_pitch, int in_pitch, int ksize, int algo);
+
+/* Weight gradient: gw[t][i][o] = sum_{b,y,x} a[b, y*sa+dya_t, x*sa+dxa_t, i]*a_scale[b,i] * g[b, y*sg+dyg_t, x*sg+dxg_t, o]
+ *   mode 0 (same conv): base = output pixel, a = layer input at base + (ky-k/2, kx-k/2), g at base
+ *   mode 1 (up conv)  : base = input pixel,  a at base, g = g_T at 2*base + (ky, kx)
+ * Result slabs taps x [a_pitch][g_pitch]; `partial` is a workspace of
+ * cagc_conv_wgrad_splits(...) such slab sets, reduced in a fixed order
+ * (deterministic) into gw. */
+int cagc_conv_wgrad_splits(int B, int H, int W, int a_pitch, int g_pitch, int ksize);
+int cagc_conv_wgrad(cagc_stream_t stream, const float* a, const float* a_scale, const float* g,
+                    float* gw, float* partial, int nsplits, int B, int H, int W,
+                    int a_pitch, int g_pitch, int ksize, int mode, int algo);
+
+/* NHWC-p FIR filter (up=down=1 case of upfirdn2d, used for the Blur after the
+ * transposed conv, model.py:270) with the StyledConv epilogue fused:
+ *   out = act( out_scale[b,c]*FIR(in) + noise_w*noise + bias[c] ).
+ * fir is the kh x kw kernel as the caller would hand it to upfirdn2d (the
+ * function flips it: true convolution). */
+int cagc_fir_nhwc(cagc_stream_t stream, const float* in, const float* fir, const float* out_scale,
+                  const float* noise, const float* noise_w, const float* bias, float* out,
+                  int B, int in_h, int in_w, int pitch, int valid, int kh, int kw,
+                  int pad_x0, int pad_x1, int pad_y0, int pad_y1, int64_t noise_bstride, int act);
+
+/* Backward of the StyledConv epilogue a = lrelu(d*u + nw*noise + bias)*sqrt2 (or of the bare
+ * demodulation y = d*u when act == 0) on NHWC-p tensors:
+ *   gz = ga*sqrt2*(a>0 ? 1 : 0.2);  gu = d*gz  (written, NHWC-p)
+ *   partial[b][chunk][0][c] = sum_p gz ; [1] = sum_p gz*y/d ; [2] = sum_p gz*noise
+ * ga may have arbitrary element strides (sb, sc, sh, sw). */
+int cagc_act_bwd_chunks(int H, int W);
+int cagc_act_bwd(cagc_stream_t stream, const float* ga, int64_t sb, int64_t sc, int64_t sh, int64_t sw,
+                 const float* a, const float* d, const float* noise, const float* noise_w, const float* bias,
+                 float* gu, float* partial, int B, int H, int W, int pitch, int valid,
+                 int64_t noise_bstride, int act);
+
+/* gs partials and input gradient of the modulation x~ = s*x:
+ *   partial[b][chunk][c] = sum_p gxt[b,p,c]*x[b,p,c];  gxt <- s[b,c]*gxt (in place) */
+int cagc_mod_bwd(cagc_stream_t stream, float* gxt, const float* x, const float* s, float* partial,
+                 int B, int H, int W, int pitch);
+
+/* ToRGB (model.py:380-395): 1x1 modulated conv without demodulation to `nout` (<= 4)
+ * channels + bias + upsampled skip, output NCHW [B, nout, H, W].
+ *   weff[b][o][i] = wscale * w[o][i] * s[b][i]
+ * skip is NCHW [B, nout, H/2, W/2] or NULL; fir (fh x fw, already multiplied by up^2)
+ * with pads as Upsample computes them (model.py:46-51). */
+int cagc_torgb_fwd(cagc_stream_t stream, const float* x, const float* w, const float* s, const float* bias,
+                   const float* skip, const float* fir, float* out, int B, int H, int W, int pitch,
+                   int cin, int nout, float wscale, int fh, int fw, int pad0, int pad1);
+/* gx[b,p,i] = sum_o weff[b,o,i]*g[b,o,p] (NHWC-p, pad channels zero);
+ * partial[b][chunk][o][pitch] = sum_p g[b,o,p]*x[b,p,i]  (caller reduces over chunk) */
+int cagc_torgb_bwd(cagc_stream_t stream, const float* g, const float* x, const float* w, const float* s,
+                   float* gx, float* partial, int B, int H, int W, int pitch, int cin, int nout, float wscale);
+
+/* NCHW (arbitrary strides) <-> NHWC-p conversion; pad channels zeroed. */
+int cagc_to_nhwc(cagc_stream_t stream, const float* src, int64_t sb, int64_t sc, int64_t sh, int64_t sw,
+                 float* dst, int B, int C, int H, int W, int pitch);
+
+/* ------------------------------------------------------------------------
+ * Fused Adam over one flat fp32 bucket (the step after the data-parallel
+ * gradient allreduce, Miscellaneous/distributed.py:57-66 + train.py:308):
+ *   g = grad[i]*grad_scale; m = b1*m + (1-b1)*g; v = b2*v + (1-b2)*g*g;
+ *   p -= lr * (m/bc1) / (sqrt(v/bc2) + eps)     (torch.optim.Adam semantics)
+ * ---------------------------------------------------------------------- */
+int cagc_adam_step(cagc_stream_t stream, float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                   int64_t n, float lr, float beta1, float beta2, float eps, float grad_scale,
+                   float bias_corr1, float bias_corr2);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CAGC_B200_H_ */

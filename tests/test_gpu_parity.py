@@ -1,0 +1,419 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via the drop-in `model` / `op` modules)
+against (a) the golden vectors generated from the unmodified reference (tests/golden/*.npz, fp64)
+and (b) the CPU oracle (oracle/stylegan2_oracle.py, fp64) on seeded inputs.
+
+Tolerances (floating point, stated here as the contract):
+  * bandwidth ops (upfirdn2d, fused_bias_act, ToRGB, FIR): fp32 arithmetic, <= 2e-6 of max |ref|
+  * fp32 SIMT modulated conv (algo 0): <= 2e-5 of max |ref| per layer output / gradient
+  * tcgen05 TF32 modulated conv (algo 1): <= 3e-3 of max |ref| per layer output; whole-generator
+    images <= 1e-2 of max |ref| (TF32 has a 10-bit mantissa; the reference's cuDNN path is TF32 too)
+  * prune masks (the integer product of the saliency pass): bit-exact
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TOL_BW = 2e-6
+TOL_FP32 = 2e-5
+TOL_TF32 = 3e-3
+
+
+def relerr(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+def close(a, b, tol, what=''):
+    if torch.is_tensor(a):
+        a = a.detach().cpu().numpy()
+    if torch.is_tensor(b):
+        b = b.detach().cpu().numpy()
+    e = relerr(a, b)
+    assert e <= tol, f'{what}: rel-to-max error {e:.3e} > {tol:.1e}'
+
+
+def cu(a, grad=False):
+    t = torch.from_numpy(np.asarray(a)).float().cuda()
+    return t.requires_grad_(True) if grad else t
+
+
+@pytest.fixture(scope='module')
+def mods():
+    import model
+    import op
+    from b200gan import config, _lib
+    from oracle import stylegan2_oracle as O
+    return dict(model=model, op=op, config=config, lib=_lib, O=O)
+
+
+# ------------------------------------------------------------------ upfirdn2d
+def test_upfirdn2d_golden(golden_dir, mods):
+    op = mods['op']
+    g = np.load(os.path.join(golden_dir, 'upfirdn2d.npz'))
+    for i in range(int(g['n_cases'])):
+        up, down, p0, p1 = [int(v) for v in g[f'c{i}_cfg']]
+        x = cu(g[f'c{i}_x'], grad=True)
+        k = cu(g[f'c{i}_k'])
+        y = op.upfirdn2d(x, k, up=up, down=down, pad=(p0, p1))
+        close(y, g[f'c{i}_y'], TOL_BW, f'upfirdn2d case {i} fwd')
+        gx, = torch.autograd.grad(y, x, cu(g[f'c{i}_gy']))
+        close(gx, g[f'c{i}_gx'], TOL_BW, f'upfirdn2d case {i} bwd')
+
+
+@pytest.mark.parametrize('shape,pad', [((2, 3, 65, 65), (1, 1)), ((1, 5, 257, 257), (1, 1)), ((2, 2, 64, 64), (2, 2)),
+                                       ((1, 3, 40, 300), (2, 1)), ((3, 1, 128, 128), (1, 1)),
+                                       ((1, 2, 31, 17), (2, 2)), ((1, 1, 70, 130), (-1, 3))])
+def test_upfirdn2d_blur_fast_path(mods, shape, pad):
+    """4x4 FIR, up=down=1 (tiled shared-memory kernel) against the oracle, forward + backward + double backward."""
+    op, O = mods['op'], mods['O']
+    torch.manual_seed(sum(shape))
+    x = torch.randn(*shape, dtype=torch.float64)
+    k = O.fir_kernel_2d([1, 3, 3, 1]) * 4
+    xr = x.clone().requires_grad_(True)
+    ref = O.upfirdn2d(xr, k, pad=pad)
+    gy = torch.randn_like(ref)
+    gref, = torch.autograd.grad(ref, xr, gy)
+    xc = x.float().cuda().requires_grad_(True)
+    y = op.upfirdn2d(xc, k.float().cuda(), pad=pad)
+    close(y, ref, TOL_BW, 'blur fwd')
+    gyc = gy.float().cuda().requires_grad_(True)
+    gx, = torch.autograd.grad(y, xc, gyc, create_graph=True)
+    close(gx, gref, TOL_BW, 'blur bwd')
+    # double backward: d(gx)/d(gy) applied to v is the forward operator on v
+    v = torch.randn_like(x)
+    gg, = torch.autograd.grad(gx, gyc, v.float().cuda())
+    close(gg, O.upfirdn2d(v, k, pad=pad), TOL_BW, 'blur double bwd')
+
+
+def test_upfirdn2d_empty_and_errors(mods):
+    op = mods['op']
+    k = torch.ones(4, 4, device='cuda') / 16
+    y = op.upfirdn2d(torch.zeros(0, 3, 8, 8, device='cuda'), k, pad=(1, 1))
+    assert y.shape == (0, 3, 7, 7)
+    with pytest.raises(RuntimeError):
+        op.upfirdn2d(torch.zeros(1, 1, 4, 4), k)            # CPU tensor: no fallback
+    with pytest.raises(RuntimeError):
+        op.upfirdn2d(torch.zeros(1, 1, 4, 4, device='cuda', dtype=torch.float64), k)
+
+
+# ------------------------------------------------------------------ fused bias act
+def test_fused_act_golden(golden_dir, mods):
+    op = mods['op']
+    g = np.load(os.path.join(golden_dir, 'fused_act.npz'))
+    for i in range(int(g['n_cases'])):
+        x = cu(g[f'c{i}_x'], grad=True)
+        b = cu(g[f'c{i}_b'], grad=True)
+        y = op.fused_leaky_relu(x, b)
+        close(y, g[f'c{i}_y'], TOL_BW, f'fused act {i} fwd')
+        gx, gb = torch.autograd.grad(y, [x, b], cu(g[f'c{i}_gy']))
+        close(gx, g[f'c{i}_gx'], TOL_BW, f'fused act {i} gx')
+        close(gb, g[f'c{i}_gb'], TOL_BW * 10, f'fused act {i} gb')
+    close(op.fused_leaky_relu(cu(g['nobias_x'])), g['nobias_y'], TOL_BW, 'no-bias')
+
+
+@pytest.mark.parametrize('shape,cl', [((4, 16, 64, 64), False), ((4, 16, 64, 64), True), ((2, 7, 33, 35), False),
+                                      ((3, 24, 17, 9), True), ((16, 512), False), ((5, 3, 130, 130), False)])
+def test_fused_act_layouts(mods, shape, cl):
+    """NCHW and channels-last storage, vector and scalar paths, fused bias-gradient reduction."""
+    op, O = mods['op'], mods['O']
+    torch.manual_seed(len(shape) + shape[-1])
+    x = torch.randn(*shape, dtype=torch.float64)
+    b = torch.randn(shape[1], dtype=torch.float64)
+    xr, br = x.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = O.fused_leaky_relu(xr, br)
+    gy = torch.randn_like(ref)
+    gxr, gbr = torch.autograd.grad(ref, [xr, br], gy)
+    xc = x.float().cuda()
+    gyc = gy.float().cuda()
+    if cl:
+        xc = xc.contiguous(memory_format=torch.channels_last)
+        gyc = gyc.contiguous(memory_format=torch.channels_last)
+    xc.requires_grad_(True)
+    bc = b.float().cuda().requires_grad_(True)
+    y = op.fused_leaky_relu(xc, bc)
+    close(y, ref, TOL_BW, 'fwd')
+    gx, gb = torch.autograd.grad(y, [xc, bc], gyc)
+    close(gx, gxr, TOL_BW, 'gx')
+    close(gb, gbr, 2e-5, 'gb')
+
+
+def test_fused_act_double_backward(mods):
+    op = mods['op']
+    torch.manual_seed(5)
+    x = torch.randn(3, 6, 5, 5, device='cuda', requires_grad=True)
+    b = torch.randn(6, device='cuda', requires_grad=True)
+    y = op.fused_leaky_relu(x, b)
+    gy = torch.randn_like(y).requires_grad_(True)
+    gx, gb = torch.autograd.grad(y, [x, b], gy, create_graph=True)
+    v = torch.randn_like(gx)
+    gg, = torch.autograd.grad((gx * v).sum() + gb.sum(), gy)
+    ref = (v + 1.0) * torch.where(y > 0, 1.0, 0.2) * (2 ** 0.5)
+    close(gg, ref, TOL_BW, 'gradgrad')
+
+
+# ------------------------------------------------------------------ single layers
+def _load_layer(model, g, tag, cls, *args, **kw):
+    m = cls(*args, **kw)
+    sd = {k[len(tag) + 4:]: torch.from_numpy(g[k]).float() for k in g.files if k.startswith(f'{tag}.sd.')}
+    m.load_state_dict(sd)
+    return m.cuda()
+
+
+@pytest.mark.parametrize('tag,cin,cout,up', [('same', 10, 7, False), ('up', 10, 7, True), ('same39', 39, 20, False)])
+def test_styled_conv_golden(golden_dir, mods, tag, cin, cout, up):
+    model, config = mods['model'], mods['config']
+    g = np.load(os.path.join(golden_dir, 'layers.npz'))
+    m = _load_layer(model, g, tag, model.StyledConv, cin, cout, 3, 16, upsample=up)
+    x, w = cu(g[f'{tag}.x'], grad=True), cu(g[f'{tag}.w'], grad=True)
+    with config.exact_fp32():
+        y = m(x, w, noise=cu(g[f'{tag}.noise']))
+        close(y, g[f'{tag}.y'], TOL_FP32, f'{tag} fwd')
+        params = dict(m.named_parameters())
+        names = sorted(params)
+        grads = torch.autograd.grad(y, [x, w] + [params[n] for n in names], cu(g[f'{tag}.gy']))
+    close(grads[0], g[f'{tag}.gx'], TOL_FP32, f'{tag} gx')
+    close(grads[1], g[f'{tag}.gw'], TOL_FP32, f'{tag} g_latent')
+    for n, gr in zip(names, grads[2:]):
+        close(gr, g[f'{tag}.grad.{n}'], TOL_FP32 * 2, f'{tag} grad {n}')
+
+
+def test_to_rgb_golden(golden_dir, mods):
+    model = mods['model']
+    g = np.load(os.path.join(golden_dir, 'layers.npz'))
+    m = _load_layer(model, g, 'rgb', model.ToRGB, 10, 16)
+    x, w, skip = cu(g['rgb.x'], grad=True), cu(g['rgb.w'], grad=True), cu(g['rgb.skip'], grad=True)
+    y = m(x, w, skip)
+    close(y, g['rgb.y'], TOL_FP32, 'rgb fwd')
+    params = dict(m.named_parameters())
+    names = sorted(params)
+    grads = torch.autograd.grad(y, [x, w, skip] + [params[n] for n in names], cu(g['rgb.gy']))
+    close(grads[0], g['rgb.gx'], TOL_FP32, 'rgb gx')
+    close(grads[1], g['rgb.gw'], TOL_FP32, 'rgb g_latent')
+    close(grads[2], g['rgb.gskip'], TOL_FP32, 'rgb gskip')
+    for n, gr in zip(names, grads[3:]):
+        close(gr, g[f'rgb.grad.{n}'], TOL_FP32 * 2, f'rgb grad {n}')
+
+
+def test_modulated_conv_module_alone(mods):
+    """ModulatedConv2d called directly (Util/network_util.py:152-164 style use) == oracle."""
+    model, O, config = mods['model'], mods['O'], mods['config']
+    torch.manual_seed(11)
+    for up in (False, True):
+        m = model.ModulatedConv2d(12, 9, 3, 16, upsample=up).cuda()
+        x = torch.randn(2, 12, 6, 6, device='cuda')
+        w = torch.randn(2, 16, device='cuda')
+        with config.exact_fp32():
+            y, sc = m(x, w, return_style_scalars=True)
+        sd = {k: v.double().cpu() for k, v in m.state_dict().items()}
+        ref, s = O.modulated_conv2d(x.double().cpu(), w.double().cpu(), sd['weight'], sd['modulation.weight'],
+                                    sd['modulation.bias'], upsample=up)
+        close(y, ref, TOL_FP32, f'modconv up={up}')
+        assert sc.shape == (2, 1, 12, 1, 1)
+        close(sc.reshape(2, 12), s, TOL_FP32, 'style scalars')
+
+
+# ------------------------------------------------------------------ whole generator (tiny, golden)
+def _tiny(mods, golden_dir, prefix='sd.'):
+    model = mods['model']
+    g = np.load(os.path.join(golden_dir, 'generator_tiny.npz'), allow_pickle=True)
+    shape = [int(v) for v in (g['net_shape'] if prefix == 'sd.' else g['pruned_net_shape'])]
+    gen = model.Generator(32, 32, 2, generator_net_shape=shape)
+    sd = {k[len(prefix):]: torch.from_numpy(g[k]).float() for k in g.files if k.startswith(prefix)}
+    gen.load_state_dict(sd)
+    return gen.cuda(), g
+
+
+def _noise(g, n):
+    return [cu(g[f'noise{i}']) for i in range(n)]
+
+
+def test_generator_tiny_forward_variants(golden_dir, mods):
+    config = mods['config']
+    gen, g = _tiny(mods, golden_dir)
+    noise = _noise(g, gen.num_layers)
+    z1, z2 = cu(g['z1']), cu(g['z2'])
+    with config.exact_fp32(), torch.no_grad():
+        close(gen([z1], noise=noise), g['img_single'], TOL_FP32 * 5, 'single')
+        rgbs = gen([z1, z2], inject_index=int(g['inject_index']), noise=noise, return_rgb_list=True)
+        for i, r in enumerate(rgbs):
+            close(r, g[f'rgb{i}'], TOL_FP32 * 5, f'rgb{i}')
+        close(gen([z1], randomize_noise=False), g['img_fixed_noise'], TOL_FP32 * 5, 'stored noise buffers')
+        close(gen([z1], truncation=0.7, truncation_latent=cu(g['mean_w']), noise=noise), g['img_trunc'],
+              TOL_FP32 * 5, 'truncation')
+        close(gen.get_latent(z1), g['w_latent'], TOL_FP32, 'mapping network')
+        close(gen(None, input_is_latent=True, latent_styles=[cu(g['w_latent'])], noise=noise), g['img_from_w'],
+              TOL_FP32 * 5, 'input_is_latent')
+        out, scalars = gen([z1], noise=noise, return_style_scalars=True)
+        assert len(scalars) == gen.num_layers + 1
+    genp, _ = _tiny(mods, golden_dir, 'pruned_sd.')
+    with config.exact_fp32(), torch.no_grad():
+        close(genp([z1], noise=noise), g['img_pruned'], TOL_FP32 * 5, 'pruned generator')
+
+
+def test_generator_tiny_gradients(golden_dir, mods):
+    config = mods['config']
+    gen, g = _tiny(mods, golden_dir)
+    noise = _noise(g, gen.num_layers)
+    with config.exact_fp32():
+        rgbs = gen([cu(g['z1']), cu(g['z2'])], inject_index=int(g['inject_index']), noise=noise, return_rgb_list=True)
+        loss = (rgbs[-1] * cu(g['cot'])).sum() + sum((r * r).mean() for r in rgbs[:-1])
+        params = dict(gen.named_parameters())
+        names = sorted(params)
+        grads = torch.autograd.grad(loss, [params[n] for n in names])
+    worst = 0.0
+    for n, gr in zip(names, grads):
+        e = relerr(gr.cpu().numpy(), g[f'grad.{n}'])
+        worst = max(worst, e)
+        assert e <= 2e-4, f'grad {n}: {e:.3e}'
+    print('worst parameter-gradient error', worst)
+
+
+def test_saliency_scores_and_prune_mask(golden_dir, mods):
+    """Get_Weight_Gradient semantics (Util/content_aware_pruning.py:174-196): scores close, masks bit-exact."""
+    config, O = mods['config'], mods['O']
+    gen, g = _tiny(mods, golden_dir)
+    noise = _noise(g, gen.num_layers)
+    mask, pm1, hit = g['sal_mask'], g['sal_pm1'], g['sal_hit']
+    sel = torch.from_numpy(mask & hit).cuda()
+    val = torch.from_numpy(pm1.astype(np.float32)).cuda()
+    with config.exact_fp32():
+        gen.zero_grad()
+        img = gen([cu(g['z1'])], noise=noise)
+        noisy = torch.where(sel.view(1, 1, *sel.shape).expand_as(img), val.view(1, 1, *val.shape).expand_as(img),
+                            img.detach())
+        torch.sum(torch.abs(noisy - img)).backward()
+    mods_ = [gen.conv1] + list(gen.convs) + [gen.to_rgbs[-1]]
+    scores = [m.conv.weight.grad.abs().mean(dim=(0, 1, 3, 4)).cpu().numpy() for m in mods_]
+    for i, s in enumerate(scores):
+        close(s, g[f'score{i}'], 1e-4, f'score {i}')
+    masks = O.prune_mask_from_scores(scores, 0.5)
+    for i, m in enumerate(masks):
+        assert np.array_equal(m, np.asarray(g[f'prune_mask{i}'], dtype=bool)), f'prune mask {i} differs'
+
+
+def test_path_length_regulariser(golden_dir, mods):
+    """PPL branch (model.py:661-666) through the second-order composite path."""
+    gen, g = _tiny(mods, golden_dir)
+    noise = _noise(g, gen.num_layers)
+    torch.manual_seed(77)
+    img, pl = gen([cu(g['z1'])], PPL_regularize=True, noise=noise)
+    # the reference drew its path noise on CPU under the same seed: recompute with that noise explicitly
+    from b200gan import config
+    with config.second_order():
+        z = cu(g['z1'])
+        w = gen.get_latent(z)
+        latent = w.unsqueeze(1).repeat(1, gen.n_latent, 1).requires_grad_(True)
+        image = gen(None, input_is_latent=True, latent_styles=[latent], noise=noise)
+        grad, = torch.autograd.grad((image * cu(g['pl_noise'])).sum(), latent, create_graph=True)
+        pl2 = torch.sqrt(grad.pow(2).sum(2).mean(1))
+        pl2.sum().backward()          # second order must run
+    close(pl2, g['path_lengths'], 1e-3, 'path lengths')
+    assert pl.shape == (3,) and torch.isfinite(pl).all()
+
+
+# ------------------------------------------------------------------ larger nets against the oracle
+def _rand_small_params(gen, seed):
+    gsd = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for n, p in gen.named_parameters():
+            if n.endswith('noise.weight') or n.endswith('activate.bias') or (n.endswith('.bias') and p.ndim == 4):
+                p.copy_(torch.randn(p.shape, generator=gsd) * 0.3)
+
+
+@pytest.mark.parametrize('size,shape', [(64, [40, 40, 40, 40, 40, 40, 24, 24, 13, 13]),
+                                        (32, [154, 154, 154, 154, 77, 77, 39, 39])])
+def test_generator_vs_oracle_pruned_widths(mods, size, shape):
+    """Awkward (pruned) channel counts incl. 154/77/39 of the 70%-pruned student: fwd + KD-slice grads."""
+    model, O, config = mods['model'], mods['O'], mods['config']
+    torch.manual_seed(3)
+    gen = model.Generator(size, 64, 2, generator_net_shape=shape)
+    _rand_small_params(gen, 4)
+    sd64 = {k: v.double() for k, v in gen.state_dict().items()}
+    gen = gen.cuda()
+    b = 2
+    z = [torch.randn(b, 64, dtype=torch.float64), torch.randn(b, 64, dtype=torch.float64)]
+    noise = [torch.randn(b, 1, n.shape[2], n.shape[3], dtype=torch.float64) for n in gen.make_noise()]
+    q = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and 'kernel' not in k and 'noises' not in k
+             else v) for k, v in sd64.items()}
+    ref = O.generator_forward(q, size, z, noise, inject_index=2, return_rgb_list=True)
+    cot = torch.randn_like(ref[-1])
+    loss_ref = (ref[-1] * cot).abs().mean() * 3 + sum(r.mean() for r in ref[:-1])
+    names = [k for k, v in q.items() if v.requires_grad]
+    gref = torch.autograd.grad(loss_ref, [q[k] for k in names])
+    with config.exact_fp32():
+        out = gen([t.float().cuda() for t in z], inject_index=2, noise=[n.float().cuda() for n in noise],
+                  return_rgb_list=True)
+        for i, (o, r) in enumerate(zip(out, ref)):
+            close(o, r.detach(), 1e-4, f'rgb {i}')
+        loss = (out[-1] * cot.float().cuda()).abs().mean() * 3 + sum(r.mean() for r in out[:-1])
+        params = dict(gen.named_parameters())
+        grads = torch.autograd.grad(loss, [params[n] for n in names])
+    for n, gr, rr in zip(names, grads, gref):
+        assert relerr(gr.cpu().numpy(), rr.numpy()) <= 5e-4, f'grad {n}: {relerr(gr.cpu().numpy(), rr.numpy()):.3e}'
+
+
+def test_random_noise_path_and_dataparallel_keys(mods):
+    """randomize_noise=True draws one normal_() per layer (model.py:299-301); module works under DataParallel."""
+    model = mods['model']
+    torch.manual_seed(0)
+    gen = model.Generator(32, 32, 2, generator_net_shape=[16] * 8).cuda()
+    _rand_small_params(gen, 1)
+    z = torch.randn(2, 32, device='cuda')
+    torch.manual_seed(123)
+    a = gen([z])
+    torch.manual_seed(123)
+    expected_noise = [torch.empty(2, 1, n.shape[2], n.shape[3], device='cuda').normal_() for n in gen.make_noise()[:0]]
+    torch.manual_seed(123)
+    b = gen([z])
+    assert torch.equal(a, b)
+    dp = torch.nn.DataParallel(gen, device_ids=[0])
+    assert all(k.startswith('module.') for k in dp.state_dict())
+    torch.manual_seed(123)
+    c = dp([z])
+    assert torch.allclose(a, c)
+
+
+# ------------------------------------------------------------------ C ABI behaviour
+def test_c_abi_rejects_bad_arguments(mods):
+    L = mods['lib']
+    x = torch.zeros(16, device='cuda')
+    rc = L.lib.cagc_upfirdn2d(None, None, x.data_ptr(), x.data_ptr(), 1, 4, 4, 1, 2, 2, 1, 1, 1, 1, 0, 0, 0, 0)
+    assert rc == -1 and b'null' in L.lib.cagc_last_error()
+    rc = L.lib.cagc_fused_bias_act(None, x.data_ptr(), None, None, x.data_ptr(), 16, 1, 1, 7, 0, 0.2, 1.0)
+    assert rc == -1
+    rc = L.lib.cagc_conv_same(None, x.data_ptr(), x.data_ptr(), None, None, None, None, None, x.data_ptr(),
+                              1, 2, 2, 6, 8, 8, 3, 0, 0, 0)
+    assert rc == -1 and b'pitch' in L.lib.cagc_last_error()
+    with pytest.raises(L.NativeError):
+        L.check(rc, 'conv_same')
+    n0 = L.launch_count()
+    y = torch.empty_like(x)
+    L.check(L.lib.cagc_fused_bias_act(torch.cuda.current_stream().cuda_stream, x.data_ptr(), None, None, y.data_ptr(),
+                                      16, 1, 1, 3, 0, 0.2, 1.0))
+    assert L.launch_count() == n0 + 1
+
+
+def test_adam_bucket_step(mods):
+    L = mods['lib']
+    torch.manual_seed(9)
+    n = 10007
+    p = torch.randn(n, device='cuda')
+    ref = p.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=0.0016, betas=(0.0, 0.99 ** 0.8), eps=1e-8)
+    m = torch.zeros_like(p)
+    v = torch.zeros_like(p)
+    st = torch.cuda.current_stream().cuda_stream
+    for step in range(1, 4):
+        g = torch.randn(n, device='cuda')
+        ref.grad = (g * 0.5).clone()
+        opt.step()
+        b1, b2 = 0.0, 0.99 ** 0.8
+        L.check(L.lib.cagc_adam_step(st, p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), n, 0.0016, b1, b2,
+                                     1e-8, 0.5, 1 - b1 ** step, 1 - b2 ** step))
+    close(p, ref.detach(), 1e-5, 'adam')
