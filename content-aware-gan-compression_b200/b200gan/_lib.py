@@ -15,7 +15,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), 'lib', 'libcagc_b200.so')
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 _p = C.c_void_p
 _i = C.c_int
@@ -27,6 +27,7 @@ SIGNATURES = {
     'cagc_abi_version': (_i, []),
     'cagc_last_error': (C.c_char_p, []),
     'cagc_launch_count': (_l, []),
+    'cagc_tc_available': (_i, []),
     'cagc_upfirdn2d': (_i, [_p, _p, _p, _p, _l, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i]),
     'cagc_fused_bias_act': (_i, [_p, _p, _p, _p, _p, _l, _l, _i, _i, _i, _f, _f]),
     'cagc_bias_grad_chunks': (_i, [_l]),

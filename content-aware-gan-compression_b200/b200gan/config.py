@@ -15,6 +15,11 @@ def set_default_algo(algo: int):
     _default_algo = int(algo)
 
 
+def best_available_algo() -> int:
+    from ._lib import lib
+    return ALGO_TCGEN05_TF32 if lib.cagc_tc_available() else ALGO_SIMT_FP32
+
+
 def conv_algo() -> int:
     return getattr(_state, 'algo', _default_algo)
 
@@ -52,3 +57,40 @@ def second_order():
         yield
     finally:
         _state.second_order = prev
+
+
+# ------------------------------------------------------------------------------------------------
+# optional per-kernel timing (bench.py): CUDA events around each native convolution / FIR launch
+# ------------------------------------------------------------------------------------------------
+_profiler = None
+
+
+class KernelProfiler:
+    """Collects (kernel name -> algorithmic work, CUDA-event pairs).  Events are recorded on the
+    stream the kernels are launched on (torch's current stream)."""
+
+    def __init__(self):
+        self.records = {}
+
+    def add(self, name, flops, nbytes, e0, e1):
+        r = self.records.setdefault(name, {'flops': 0.0, 'bytes': 0.0, 'events': [], 'launches': 0})
+        r['flops'] += flops
+        r['bytes'] += nbytes
+        r['events'].append((e0, e1))
+        r['launches'] += 1
+
+    def summary(self):
+        out = {}
+        for name, r in self.records.items():
+            ms = sum(a.elapsed_time(b) for a, b in r['events'])
+            out[name] = {'ms': ms, 'launches': r['launches'], 'flops': r['flops'], 'bytes': r['bytes']}
+        return out
+
+
+def set_profiler(p):
+    global _profiler
+    _profiler = p
+
+
+def profiler():
+    return _profiler

@@ -1,0 +1,69 @@
+"""The knowledge-distillation generator step (reference train.py:280-308, `G_Loss_BackProp`) as a
+reusable driver: student forward (RGB list) -> discriminator -> non-saturating GAN loss; teacher
+forward; masked L1 KD loss (train.py:145-164, 'Output_Only'); backward; one flat-bucket gradient
+all-reduce over the data-parallel ranks; fused Adam (train.py:528-532 hyper-parameters).
+
+LPIPS (VGG16) and the BiSeNet face parser are third-party networks outside the hot path
+(SURVEY.md §2 #8/#9); a caller supplies the content mask.  Public API used by bench.py's e2e leg.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.nn.functional as F
+
+from . import dist as D
+from ._lib import lib, check
+
+
+class KDStep:
+    def __init__(self, student, teacher, discriminator, lr: float = 0.002 * 0.8, betas=(0.0, 0.99 ** 0.8),
+                 eps: float = 1e-8, kd_l1_lambda: float = 3.0, mask: Optional[torch.Tensor] = None):
+        self.student, self.teacher, self.disc = student, teacher, discriminator
+        for p in teacher.parameters():
+            p.requires_grad_(False)
+        for p in discriminator.parameters():
+            p.requires_grad_(False)          # train.py:286-287 (requires_grad(D, False))
+        self.bucket = D.FlatBucket(student.parameters())
+        self.exp_avg = torch.zeros_like(self.bucket.flat_param)
+        self.exp_avg_sq = torch.zeros_like(self.bucket.flat_param)
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.kd_l1_lambda = kd_l1_lambda
+        self.mask = mask
+        self.t = 0
+        self.device = self.bucket.flat_param.device
+
+    def losses(self, z: List[torch.Tensor], inject_index: int, s_noise=None, t_noise=None):
+        """GAN + KD losses; per-layer noise is drawn fresh (train.py:291,151) unless given explicitly."""
+        fake = self.student(z, return_rgb_list=True, inject_index=inject_index, noise=s_noise)
+        g_loss = F.softplus(-self.disc(fake[-1])).mean()
+        with torch.no_grad():
+            real = self.teacher(z, return_rgb_list=True, inject_index=inject_index, noise=t_noise)
+        s_img, t_img = fake[-1], real[-1]
+        if self.mask is not None:
+            s_img, t_img = s_img * self.mask, t_img * self.mask
+        kd = self.kd_l1_lambda * torch.mean(torch.abs(t_img - s_img))
+        return g_loss, kd
+
+    def step(self, z: List[torch.Tensor], inject_index: int, s_noise=None, t_noise=None) -> torch.Tensor:
+        """One optimisation step on device-resident latents; returns the (detached) total loss."""
+        self.bucket.zero_grad()
+        g_loss, kd = self.losses(z, inject_index, s_noise, t_noise)
+        total = g_loss + kd
+        total.backward()
+        self.bucket.allreduce_mean_()
+        self.t += 1
+        b1, b2 = self.betas
+        with torch.cuda.device(self.device):
+            check(lib.cagc_adam_step(torch.cuda.current_stream(self.device).cuda_stream,
+                                     self.bucket.flat_param.data_ptr(), self.bucket.flat_grad.data_ptr(),
+                                     self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.bucket.numel,
+                                     self.lr, b1, b2, self.eps, 1.0 / D.get_world_size(),
+                                     1.0 - b1 ** self.t, 1.0 - b2 ** self.t), 'adam_step')
+        return total.detach()
+
+    def step_from_host(self, z_host: List[torch.Tensor], inject_index: int) -> float:
+        """End-to-end form: latents arrive in pinned host memory, the loss is read back."""
+        z = [t.to(self.device, non_blocking=True) for t in z_host]
+        return float(self.step(z, inject_index).item())

@@ -51,6 +51,19 @@ def as_nhwc_buf(x: torch.Tensor) -> torch.Tensor:
     return buf
 
 
+def _timed(name, flops, nbytes, fn):
+    """Run a native launch, bracketing it with CUDA events when bench.py installed a profiler."""
+    prof = config.profiler()
+    if prof is None:
+        return fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    r = fn()
+    e1.record()
+    prof.add(name, flops, nbytes, e0, e1)
+    return r
+
+
 def _pad_last(t: torch.Tensor, p: int) -> torch.Tensor:
     t = t.contiguous()
     if t.shape[-1] == p:
@@ -105,9 +118,12 @@ class _StyledConvFn(Function):
             if not upsample:
                 out = torch.empty((b, h, w, pout), device=dev, dtype=torch.float32)
                 if out.numel():
-                    check(lib.cagc_conv_same(st, xb.data_ptr(), w_fwd.data_ptr(), s_p.data_ptr(), ptr(d_p), ptr(noise),
-                                             ptr(nw), ptr(bias_p), out.data_ptr(), b, h, w, pin, pout, cout, k,
-                                             nstride, int(act), algo), 'conv_same')
+                    flops = 2.0 * b * h * w * cin * cout * k * k          # Util/Calculators.py convention x2
+                    _timed(f'conv_same[algo{algo}]', flops, 4.0 * b * h * w * (cin + cout),
+                           lambda: check(lib.cagc_conv_same(st, xb.data_ptr(), w_fwd.data_ptr(), s_p.data_ptr(),
+                                                            ptr(d_p), ptr(noise), ptr(nw), ptr(bias_p), out.data_ptr(),
+                                                            b, h, w, pin, pout, cout, k, nstride, int(act), algo),
+                                         'conv_same'))
             else:
                 hu, wu = 2 * h + k - 2, 2 * w + k - 2
                 ut = torch.empty((b, hu, wu, pout), device=dev, dtype=torch.float32)
@@ -116,11 +132,15 @@ class _StyledConvFn(Function):
                 ho, wo = hu + pad[0] + pad[1] - kh + 1, wu + pad[0] + pad[1] - kw + 1
                 out = torch.empty((b, ho, wo, pout), device=dev, dtype=torch.float32)
                 if out.numel():
-                    check(lib.cagc_conv_up(st, xb.data_ptr(), w_fwd.data_ptr(), s_p.data_ptr(), ut.data_ptr(),
-                                           b, h, w, pin, pout, k, algo), 'conv_up')
-                    check(lib.cagc_fir_nhwc(st, ut.data_ptr(), fir.data_ptr(), ptr(d_p), ptr(noise), ptr(nw),
-                                            ptr(bias_p), out.data_ptr(), b, hu, wu, pout, cout, kh, kw,
-                                            pad[0], pad[1], pad[0], pad[1], nstride, int(act)), 'fir_nhwc')
+                    flops = 2.0 * b * h * w * cin * cout * k * k          # transposed conv counted at input res
+                    _timed(f'conv_up[algo{algo}]', flops, 4.0 * b * (h * w * cin + hu * wu * cout),
+                           lambda: check(lib.cagc_conv_up(st, xb.data_ptr(), w_fwd.data_ptr(), s_p.data_ptr(),
+                                                          ut.data_ptr(), b, h, w, pin, pout, k, algo), 'conv_up'))
+                    _timed('fir_nhwc', 0.0, 4.0 * b * cout * (hu * wu + ho * wo),
+                           lambda: check(lib.cagc_fir_nhwc(st, ut.data_ptr(), fir.data_ptr(), ptr(d_p), ptr(noise),
+                                                           ptr(nw), ptr(bias_p), out.data_ptr(), b, hu, wu, pout, cout,
+                                                           kh, kw, pad[0], pad[1], pad[0], pad[1], nstride, int(act)),
+                                         'fir_nhwc'))
                 del ut
         ctx.save_for_backward(xb, s_p, d_p, wk, noise, nw, bias_p, out, fir if upsample else None)
         ctx.cfg = (b, cin, cout, h, w, k, pin, pout, upsample, pad, bool(act), nstride, algo, wscale,

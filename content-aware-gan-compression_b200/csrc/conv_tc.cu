@@ -5,3 +5,5 @@
 int cagc_tc_conv(cudaStream_t, const cagc::ConvP&, const char* what) {
     return cagc::fail(CAGC_E_UNSUPPORTED, "%s: tcgen05 path not built", what);
 }
+
+extern "C" int cagc_tc_available(void) { return 0; }

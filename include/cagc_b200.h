@@ -37,12 +37,14 @@ typedef void* cagc_stream_t; /* cudaStream_t */
 #define CAGC_E_UNSUPPORTED (-2) /* shape outside what the kernels implement */
 
 /* bump when a signature changes; the Python loader checks it */
-#define CAGC_ABI_VERSION 5
+#define CAGC_ABI_VERSION 6
 
 int cagc_abi_version(void);
 const char* cagc_last_error(void);
 /* number of kernel launches issued through this library by the calling process (all threads) */
 int64_t cagc_launch_count(void);
+/* 1 when the tcgen05/TMA tensor-pipe convolution path (algo 1) is compiled into this library */
+int cagc_tc_available(void);
 
 /* ------------------------------------------------------------------------
  * upfirdn2d -- replaces upfirdn2d.upfirdn2d (op/upfirdn2d.cpp:4-22,
