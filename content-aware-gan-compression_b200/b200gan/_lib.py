@@ -15,7 +15,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), 'lib', 'libcagc_b200.so')
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 _p = C.c_void_p
 _i = C.c_int
@@ -33,6 +33,7 @@ SIGNATURES = {
     'cagc_bias_grad_chunks': (_i, [_l]),
     'cagc_fused_bias_act_bwd': (_i, [_p, _p, _p, _p, _p, _l, _i, _l, _f, _f]),
     'cagc_conv_same': (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _l, _i, _i]),
+    'cagc_modulate': (_i, [_p, _p, _p, _p, _i, _i, _i, _i]),
     'cagc_conv_up': (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i]),
     'cagc_conv_up_dgrad': (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i]),
     'cagc_conv_wgrad_splits': (_i, [_i, _i, _i, _i, _i, _i]),

@@ -81,6 +81,22 @@ def _slabs(w4: torch.Tensor, rows_p: int, cols_p: int) -> torch.Tensor:
     return F.pad(w, (0, cols_p - c, 0, rows_p - r)).contiguous()
 
 
+def _slabs_tc(w4: torch.Tensor, k_p: int) -> torch.Tensor:
+    """[k,k,N,K] -> K-major slabs [k*k, roundup16(pitch(N)), k_p], rounded to TF32 (tcgen05 B operand)."""
+    k = w4.shape[0]
+    n, kk = w4.shape[2], w4.shape[3]
+    n_rows = (pitch_of(n) + 15) // 16 * 16
+    w = F.pad(w4.reshape(k * k, n, kk), (0, k_p - kk, 0, n_rows - n)).contiguous()
+    check(lib.cagc_modulate(stream_of(w), w.data_ptr(), None, w.data_ptr(), 1, 1, w.numel() // 4, 4), 'round_tf32')
+    return w
+
+
+def _use_tc(algo: int, k_pitch: int) -> bool:
+    """The tcgen05 kernel consumes K in 128-byte (32-channel) TMA boxes; narrower layers (a few
+    channels, latency-bound anyway) stay on the SIMT engine."""
+    return algo == config.ALGO_TCGEN05_TF32 and k_pitch >= 32
+
+
 class _StyledConvFn(Function):
     """a = [lrelu]( d * conv(s*x, c*W) [+ nw*noise] [+ bias] ) on NHWC-p buffers.
 
@@ -104,7 +120,17 @@ class _StyledConvFn(Function):
             d_p = _pad_last(d.detach().float(), pout) if d is not None else None
             bias_p = _pad_last(bias.detach().float(), pout) if bias is not None else None
             wk = (weight.detach()[0] * wscale)                       # [O,I,k,k]
-            w_fwd = _slabs(wk.permute(2, 3, 1, 0), pin, pout)        # [t][i][o]
+            tc = _use_tc(algo, pin)
+            if tc:
+                # tensor-pipe path: operands come straight from TMA, so modulation is a tensor pass
+                w_fwd = _slabs_tc(wk.permute(2, 3, 0, 1), pin)       # [t][o][i], K-major
+                x_in = torch.empty_like(xb)
+                if xb.numel():
+                    check(lib.cagc_modulate(st, xb.data_ptr(), s_p.data_ptr(), x_in.data_ptr(), b, h, w, pin), 'modulate')
+                s_arg, falgo = None, config.ALGO_TCGEN05_TF32
+            else:
+                w_fwd = _slabs(wk.permute(2, 3, 1, 0), pin, pout)    # [t][i][o]
+                x_in, s_arg, falgo = xb, s_p.data_ptr(), config.ALGO_SIMT_FP32
             if noise is not None:
                 noise = noise.detach().contiguous()
                 nb = noise.shape[0]
@@ -119,10 +145,10 @@ class _StyledConvFn(Function):
                 out = torch.empty((b, h, w, pout), device=dev, dtype=torch.float32)
                 if out.numel():
                     flops = 2.0 * b * h * w * cin * cout * k * k          # Util/Calculators.py convention x2
-                    _timed(f'conv_same[algo{algo}]', flops, 4.0 * b * h * w * (cin + cout),
-                           lambda: check(lib.cagc_conv_same(st, xb.data_ptr(), w_fwd.data_ptr(), s_p.data_ptr(),
+                    _timed(f'conv_same[algo{falgo}]', flops, 4.0 * b * h * w * (cin + cout),
+                           lambda: check(lib.cagc_conv_same(st, x_in.data_ptr(), w_fwd.data_ptr(), s_arg,
                                                             ptr(d_p), ptr(noise), ptr(nw), ptr(bias_p), out.data_ptr(),
-                                                            b, h, w, pin, pout, cout, k, nstride, int(act), algo),
+                                                            b, h, w, pin, pout, cout, k, nstride, int(act), falgo),
                                          'conv_same'))
             else:
                 hu, wu = 2 * h + k - 2, 2 * w + k - 2
@@ -133,15 +159,16 @@ class _StyledConvFn(Function):
                 out = torch.empty((b, ho, wo, pout), device=dev, dtype=torch.float32)
                 if out.numel():
                     flops = 2.0 * b * h * w * cin * cout * k * k          # transposed conv counted at input res
-                    _timed(f'conv_up[algo{algo}]', flops, 4.0 * b * (h * w * cin + hu * wu * cout),
-                           lambda: check(lib.cagc_conv_up(st, xb.data_ptr(), w_fwd.data_ptr(), s_p.data_ptr(),
-                                                          ut.data_ptr(), b, h, w, pin, pout, k, algo), 'conv_up'))
+                    _timed(f'conv_up[algo{falgo}]', flops, 4.0 * b * (h * w * cin + hu * wu * cout),
+                           lambda: check(lib.cagc_conv_up(st, x_in.data_ptr(), w_fwd.data_ptr(), s_arg,
+                                                          ut.data_ptr(), b, h, w, pin, pout, k, falgo), 'conv_up'))
                     _timed('fir_nhwc', 0.0, 4.0 * b * cout * (hu * wu + ho * wo),
                            lambda: check(lib.cagc_fir_nhwc(st, ut.data_ptr(), fir.data_ptr(), ptr(d_p), ptr(noise),
                                                            ptr(nw), ptr(bias_p), out.data_ptr(), b, hu, wu, pout, cout,
                                                            kh, kw, pad[0], pad[1], pad[0], pad[1], nstride, int(act)),
                                          'fir_nhwc'))
                 del ut
+            del x_in
         ctx.save_for_backward(xb, s_p, d_p, wk, noise, nw, bias_p, out, fir if upsample else None)
         ctx.cfg = (b, cin, cout, h, w, k, pin, pout, upsample, pad, bool(act), nstride, algo, wscale,
                    d is not None, bias is not None)
@@ -190,12 +217,23 @@ class _StyledConvFn(Function):
                 gxt = torch.empty((b, h, w, pin), device=dev, dtype=torch.float32)
                 if upsample:
                     w_d = _slabs(wk.permute(2, 3, 0, 1), pout, pin)                 # [t][o][i]
-                    check(lib.cagc_conv_up_dgrad(st, g_conv.data_ptr(), w_d.data_ptr(), gxt.data_ptr(), b, h, w,
-                                                 pout, pin, k, algo), 'conv_up_dgrad')
+                    _timed('conv_up_dgrad[algo0]', 2.0 * b * h * w * cin * cout * k * k,
+                           4.0 * b * (h * w * cin + hu * wu * cout),
+                           lambda: check(lib.cagc_conv_up_dgrad(st, g_conv.data_ptr(), w_d.data_ptr(), gxt.data_ptr(),
+                                                                b, h, w, pout, pin, k, config.ALGO_SIMT_FP32),
+                                         'conv_up_dgrad'))
+                elif _use_tc(algo, pout):
+                    w_d = _slabs_tc(torch.flip(wk, [2, 3]).permute(2, 3, 1, 0), pout)   # [t'][i][o], K = o
+                    _timed('conv_same[algo1]', 2.0 * b * h * w * cin * cout * k * k, 4.0 * b * h * w * (cin + cout),
+                           lambda: check(lib.cagc_conv_same(st, g_conv.data_ptr(), w_d.data_ptr(), None, None, None,
+                                                            None, None, gxt.data_ptr(), b, h, w, pout, pin, pin, k, 0,
+                                                            0, config.ALGO_TCGEN05_TF32), 'conv_same(dgrad,tc)'))
                 else:
                     w_d = _slabs(torch.flip(wk, [2, 3]).permute(2, 3, 0, 1), pout, pin)
-                    check(lib.cagc_conv_same(st, g_conv.data_ptr(), w_d.data_ptr(), None, None, None, None, None,
-                                             gxt.data_ptr(), b, h, w, pout, pin, pin, k, 0, 0, algo), 'conv_same(dgrad)')
+                    _timed('conv_same[algo0]', 2.0 * b * h * w * cin * cout * k * k, 4.0 * b * h * w * (cin + cout),
+                           lambda: check(lib.cagc_conv_same(st, g_conv.data_ptr(), w_d.data_ptr(), None, None, None,
+                                                            None, None, gxt.data_ptr(), b, h, w, pout, pin, pin, k, 0,
+                                                            0, config.ALGO_SIMT_FP32), 'conv_same(dgrad)'))
                 mchunks = lib.cagc_act_bwd_chunks(h, w)
                 mpartial = torch.empty((b, mchunks, pin), device=dev, dtype=torch.float32)
                 check(lib.cagc_mod_bwd(st, gxt.data_ptr(), xb.data_ptr(), s_p.data_ptr(), mpartial.data_ptr(),
@@ -209,9 +247,10 @@ class _StyledConvFn(Function):
                 nsp = lib.cagc_conv_wgrad_splits(b, h, w, pin, pout, k)
                 gw = torch.empty((k * k, pin, pout), device=dev, dtype=torch.float32)
                 wpart = torch.empty((nsp, k * k, pin, pout), device=dev, dtype=torch.float32)
-                check(lib.cagc_conv_wgrad(st, xb.data_ptr(), s_p.data_ptr(), g_conv.data_ptr(), gw.data_ptr(),
-                                          wpart.data_ptr(), nsp, b, h, w, pin, pout, k, 1 if upsample else 0, 0),
-                      'conv_wgrad')
+                _timed('conv_wgrad[algo0]', 2.0 * b * h * w * cin * cout * k * k, 4.0 * b * h * w * (cin + cout),
+                       lambda: check(lib.cagc_conv_wgrad(st, xb.data_ptr(), s_p.data_ptr(), g_conv.data_ptr(),
+                                                         gw.data_ptr(), wpart.data_ptr(), nsp, b, h, w, pin, pout, k,
+                                                         1 if upsample else 0, 0), 'conv_wgrad'))
                 g_w = (gw[:, :cin, :cout].reshape(k, k, cin, cout).permute(3, 2, 0, 1) * wscale).unsqueeze(0)
         return (g_x, g_s, g_d, g_w, None, g_nw, g_bias, None, None, None, None, None, None)
 

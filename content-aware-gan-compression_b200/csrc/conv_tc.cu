@@ -1,9 +1,421 @@
-// tcgen05 / TMEM / TMA implicit-GEMM path for the modulated convolution (placeholder until the
-// tensor-pipe kernel lands: reports "unsupported" so that callers fail loudly).
+// tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a (B200).
+//
+// GEMM view of the modulated convolution (model.py:241-289 in the fused form of SURVEY.md App. B):
+//     M = 128 output pixels per CTA (a bb x bh x bw box of the NHWC-p activation tensor),
+//     N = output channels (<= 256 per CTA, multiple of 16),
+//     K = taps x input channels, consumed as (tap, 32-channel chunk) stages.
+// A operand: one TMA 4-D box load per stage from the *shifted* activation tensor
+//     coords (c0, x0 + dx, y0 + dy, b0); the halo of the convolution is TMA out-of-bounds zero fill.
+// B operand: one TMA 3-D box load per stage from the K-major weight slabs [tap][n][k].
+// Both land in shared memory in the 128-byte swizzled K-major layout that tcgen05.mma reads.
+// One elected thread issues tcgen05.mma.kind::tf32 (M=128, N, K=8) into a TMEM accumulator;
+// four epilogue warps read it back with tcgen05.ld, apply demodulation / noise / bias / leaky-ReLU
+// and store NHWC-p.  Warp roles: 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..5 = epilogue.
+// Two CTAs are resident per SM (<= 110 KB of shared memory, <= 256 TMEM columns each), so one CTA's
+// epilogue overlaps the other's main loop.
+#include <cuda.h>
+
+#include <algorithm>
+
 #include "conv_params.cuh"
 
-int cagc_tc_conv(cudaStream_t, const cagc::ConvP&, const char* what) {
-    return cagc::fail(CAGC_E_UNSUPPORTED, "%s: tcgen05 path not built", what);
+namespace cagc {
+namespace tc {
+
+constexpr int kThreads = 192;
+constexpr int kTileM = 128;
+constexpr int kChunkK = 32;                      // fp32 elements per 128-byte swizzle row
+constexpr int kABytes = kTileM * kChunkK * 4;    // 16 KB
+constexpr int kMaxStages = 6;
+constexpr int kSmemBudget = 110 * 1024;          // two CTAs per SM
+
+struct TcParams {
+    const float* out_scale;
+    const float* noise;
+    const float* noise_w;
+    const float* bias;
+    float* out;
+    int B, Ho, Wo;              // iteration domain
+    int bw, bh, bb;             // box: bw*bh*bb == 128
+    int tiles_x, tiles_y;       // tiles per sample group
+    int k_valid;                // in_pitch
+    int n_pitch, out_valid;     // output pitch / logical channels
+    int n_tile;                 // MMA N of this launch's full tiles (multiple of 16, <= 256)
+    int n_rows;                 // rows per weight slab
+    int Hout, Wout, out_stride, out_oy, out_ox;
+    int64_t noise_bstride;
+    int act, ntaps, stages;
+    uint32_t b_bytes;           // bytes of one B stage
+    Tap taps[kMaxTaps];
+};
+
+// ---------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// bounded wait: a protocol bug traps (sticky launch error) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {
+            printf("cagc conv_tc: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y,
+                   threadIdx.x);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-extern "C" int cagc_tc_available(void) { return 0; }
+// K-major, 128-byte swizzle shared-memory matrix descriptor: 8-row groups of 1024 bytes
+// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout [61,64))
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fff);
+    d |= (uint64_t)1 << 16;            // leading byte offset (unused for swizzled K-major; canonical value 1)
+    d |= (uint64_t)(1024 >> 4) << 32;  // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;            // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;            // SWIZZLE_128B
+    return d;
+}
+
+__global__ void __launch_bounds__(kThreads, 2)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 1];
+    __shared__ uint32_t tmem_base_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int S = p.stages;
+    const uint32_t stage_bytes = kABytes + p.b_bytes;
+    auto a_addr = [&](int s) { return smem_base + (uint32_t)s * stage_bytes; };
+    auto b_addr = [&](int s) { return smem_base + (uint32_t)s * stage_bytes + kABytes; };
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (kMaxStages + s); };
+    const uint32_t acc_bar = bar0 + 8u * (2 * kMaxStages);
+
+    // ---- tile coordinates
+    int t = blockIdx.x;
+    const int tx = t % p.tiles_x;
+    t /= p.tiles_x;
+    const int ty = t % p.tiles_y;
+    const int tb = t / p.tiles_y;
+    const int x0 = tx * p.bw, y0 = ty * p.bh, b0 = tb * p.bb;
+    const int n0 = blockIdx.y * 256;
+    int n_mma = p.n_tile;
+    {
+        const int rem = ((p.n_pitch - n0) + 15) & ~15;
+        if (rem < n_mma) n_mma = rem;
+    }
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < n_mma) tmem_cols <<= 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        mbar_init(acc_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                     "r"(tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_acc = tmem_base_slot;
+
+    const int nk = (p.k_valid + kChunkK - 1) / kChunkK;
+    const int total = p.ntaps * nk;
+
+    if (warp == 0) {
+        // =============================== TMA producer ===============================
+        if (lane == 0) {
+            for (int it = 0; it < total; ++it) {
+                const int s = it % S;
+                const uint32_t ph = (uint32_t)(it / S) & 1u;
+                mbar_wait(empty_bar(s), ph ^ 1u);
+                const int tap = it / nk, kc = it - tap * nk;
+                const Tap tp = p.taps[tap];
+                mbar_expect_tx(full_bar(s), stage_bytes);
+                tma_load_4d(a_addr(s), &map_a, full_bar(s), kc * kChunkK, x0 + tp.dx, y0 + tp.dy, b0);
+                tma_load_3d(b_addr(s), &map_b, full_bar(s), kc * kChunkK, n0, tp.slab);
+            }
+        }
+    } else if (warp == 1) {
+        // =============================== MMA issuer =================================
+        if (lane == 0) {
+            // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32, K-major both, N>>3, M>>4
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n_mma >> 3) << 17) |
+                                   ((uint32_t)(kTileM >> 4) << 24);
+            for (int it = 0; it < total; ++it) {
+                const int s = it % S;
+                const uint32_t ph = (uint32_t)(it / S) & 1u;
+                mbar_wait(full_bar(s), ph);
+                tc_fence_after();
+                const int kc = it % nk;
+                int kk = (p.k_valid - kc * kChunkK + 7) >> 3;   // 8-wide tf32 MMAs with real data
+                if (kk > 4) kk = 4;
+                const uint64_t ad = make_desc_sw128(a_addr(s));
+                const uint64_t bd = make_desc_sw128(b_addr(s));
+                for (int k = 0; k < kk; ++k) {
+                    // advance 8 tf32 = 32 bytes along K inside the swizzle row: +2 in 16-byte units
+                    tc_mma_tf32(tmem_acc, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc,
+                                (it > 0 || k > 0) ? 1u : 0u);
+                }
+                tc_commit(empty_bar(s));   // frees the smem stage once these MMAs have read it
+            }
+            tc_commit(acc_bar);            // accumulator complete
+        }
+    } else {
+        // =============================== epilogue ===================================
+        const int q = warp & 3;            // TMEM lane quarter this warp may access
+        const int m = q * 32 + lane;       // accumulator row == pixel of the box
+        const int lx = m % p.bw;
+        const int ly = (m / p.bw) % p.bh;
+        const int lb = m / (p.bw * p.bh);
+        const int ox = x0 + lx, oy = y0 + ly, b = b0 + lb;
+        const bool pvalid = (ox < p.Wo) && (oy < p.Ho) && (b < p.B);
+        const int yy = oy * p.out_stride + p.out_oy, xx = ox * p.out_stride + p.out_ox;
+        float nz = 0.f;
+        if (p.noise && pvalid)
+            nz = __ldg(p.noise_w) * __ldg(p.noise + (int64_t)b * p.noise_bstride + (int64_t)yy * p.Wout + xx);
+        float* dst = p.out + (((int64_t)b * p.Hout + yy) * p.Wout + xx) * p.n_pitch;
+        const float* sc = p.out_scale ? p.out_scale + (int64_t)b * p.n_pitch : nullptr;
+
+        mbar_wait(acc_bar, 0);
+        tc_fence_after();
+        for (int c = 0; c < n_mma; c += 16) {
+            float v[16];
+            tc_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);   // warp-collective
+            if (!pvalid) continue;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const int n = n0 + c + g * 4;
+                if (n >= p.n_pitch) break;
+                float o[4] = {v[g * 4 + 0], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]};
+                if (sc) {
+                    const float4 s4 = ldg4(sc + n);
+                    o[0] *= s4.x; o[1] *= s4.y; o[2] *= s4.z; o[3] *= s4.w;
+                }
+                if (p.noise) { o[0] += nz; o[1] += nz; o[2] += nz; o[3] += nz; }
+                if (p.bias) {
+                    const float4 b4 = ldg4(p.bias + n);
+                    o[0] += b4.x; o[1] += b4.y; o[2] += b4.z; o[3] += b4.w;
+                }
+                if (p.act) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) o[j] = lrelu_sqrt2(o[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (n + j >= p.out_valid) o[j] = 0.f;
+                st4(dst + n, make_float4(o[0], o[1], o[2], o[3]));
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(tmem_cols) : "memory");
+    }
+}
+
+// elementwise x~ = round_tf32(x * s[b, c])  (s == nullptr: plain rounding); NHWC-p, float4
+__global__ void __launch_bounds__(256) modulate_kernel(const float* __restrict__ x, const float* __restrict__ s,
+                                                       float* __restrict__ out, int64_t n4, int64_t per_sample4,
+                                                       int c4n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 v = ld4(x + 4 * i);
+        if (s) {
+            const int64_t b = i / per_sample4;
+            const int c4 = (int)(i % c4n);
+            const float4 sv = ldg4(s + (b * c4n + c4) * 4);
+            v.x *= sv.x; v.y *= sv.y; v.z *= sv.z; v.w *= sv.w;
+        }
+        uint32_t r0, r1, r2, r3;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r0) : "f"(v.x));
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r1) : "f"(v.y));
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r2) : "f"(v.z));
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r3) : "f"(v.w));
+        st4(out + 4 * i, make_float4(__uint_as_float(r0), __uint_as_float(r1), __uint_as_float(r2), __uint_as_float(r3)));
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)sym;
+    }
+    return fn;
+}
+
+static int next_pow2(int v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+}  // namespace tc
+}  // namespace cagc
+
+using namespace cagc;
+
+int cagc_tc_conv(cudaStream_t stream, const ConvP& c, const char* what) {
+    using namespace cagc::tc;
+    CAGC_REQUIRE(c.in_scale == nullptr, "%s: the tcgen05 path takes a pre-modulated input (cagc_modulate)", what);
+    CAGC_REQUIRE(c.in_stride == 1, "%s: strided input is not implemented on the tcgen05 path", what);
+    CAGC_REQUIRE(c.in_pitch % 8 == 0 && c.n_cols % 8 == 0, "%s: tcgen05 path needs channel pitches that are multiples of 8",
+                 what);
+    EncodeTiledFn encode = get_encode();
+    if (!encode) return fail(CAGC_E_UNSUPPORTED, "%s: cuTensorMapEncodeTiled not available from the driver", what);
+    if ((int64_t)c.B * c.Ho * c.Wo == 0) return 0;
+
+    TcParams p{};
+    p.out_scale = c.out_scale; p.noise = c.noise; p.noise_w = c.noise_w; p.bias = c.bias; p.out = c.out;
+    p.B = c.B; p.Ho = c.Ho; p.Wo = c.Wo;
+    p.bw = std::min(16, next_pow2(c.Wo));
+    p.bh = std::min(kTileM / p.bw, next_pow2(c.Ho));
+    p.bb = kTileM / (p.bw * p.bh);
+    p.tiles_x = ceil_div(c.Wo, p.bw);
+    p.tiles_y = ceil_div(c.Ho, p.bh);
+    const int tiles_b = ceil_div(c.B, p.bb);
+    p.k_valid = c.in_pitch;
+    p.n_pitch = c.n_cols; p.out_valid = c.out_valid;
+    p.n_rows = (c.n_cols + 15) & ~15;
+    p.n_tile = std::min(256, p.n_rows);
+    p.Hout = c.Hout; p.Wout = c.Wout; p.out_stride = c.out_stride; p.out_oy = c.out_oy; p.out_ox = c.out_ox;
+    p.noise_bstride = c.noise_bstride; p.act = c.act; p.ntaps = c.ntaps;
+    for (int i = 0; i < c.ntaps; ++i) p.taps[i] = c.taps[i];
+    p.b_bytes = (uint32_t)p.n_tile * kChunkK * 4;
+    const uint32_t stage_bytes = kABytes + p.b_bytes;
+    p.stages = std::max(2, std::min(kMaxStages, (int)((kSmemBudget - 1024) / stage_bytes)));
+    const size_t smem = (size_t)p.stages * stage_bytes + 1024;
+
+    // A: activations [B, Hin, Win, in_pitch] fp32, box (32 ch, bw, bh, bb), 128-byte swizzle, OOB -> 0
+    CUtensorMap map_a, map_b;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)c.in_pitch, (cuuint64_t)c.Win, (cuuint64_t)c.Hin, (cuuint64_t)c.B};
+        cuuint64_t strides[3] = {(cuuint64_t)c.in_pitch * 4, (cuuint64_t)c.Win * c.in_pitch * 4,
+                                 (cuuint64_t)c.Hin * c.Win * c.in_pitch * 4};
+        cuuint32_t box[4] = {(cuuint32_t)kChunkK, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bb};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        CUresult r = encode(&map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(c.in), dims, strides, box, es,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(CAGC_E_INVALID, "%s: cuTensorMapEncodeTiled(A) failed with %d", what, (int)r);
+    }
+    // B: weight slabs [taps][n_rows][in_pitch] fp32 (K contiguous), box (32 k, n_tile, 1)
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)c.in_pitch, (cuuint64_t)p.n_rows, (cuuint64_t)kMaxTaps};
+        cuuint64_t strides[2] = {(cuuint64_t)c.in_pitch * 4, (cuuint64_t)p.n_rows * c.in_pitch * 4};
+        cuuint32_t box[3] = {(cuuint32_t)kChunkK, (cuuint32_t)p.n_tile, 1};
+        cuuint32_t es[3] = {1, 1, 1};
+        int max_slab = 0;
+        for (int i = 0; i < c.ntaps; ++i) max_slab = std::max(max_slab, c.taps[i].slab);
+        dims[2] = (cuuint64_t)(max_slab + 1);
+        CUresult r = encode(&map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(c.w), dims, strides, box, es,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(CAGC_E_INVALID, "%s: cuTensorMapEncodeTiled(B) failed with %d", what, (int)r);
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+        if (e != cudaSuccess) return fail((int)e, "%s: cudaFuncSetAttribute failed: %s", what, cudaGetErrorString(e));
+        attr_set = true;
+    }
+    const int64_t gx = (int64_t)p.tiles_x * p.tiles_y * tiles_b;
+    CAGC_REQUIRE(gx <= 0x7fffffffLL, "%s: too many tiles", what);
+    dim3 grid((unsigned)gx, ceil_div(p.n_rows, 256));
+    conv_tc_kernel<<<grid, kThreads, smem, stream>>>(map_a, map_b, p);
+    return launched(what);
+}
+
+extern "C" {
+
+int cagc_tc_available(void) { return 1; }
+
+int cagc_modulate(cagc_stream_t stream_, const float* x, const float* s, float* out, int B, int H, int W, int pitch) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CAGC_REQUIRE(x && out, "modulate: null pointer");
+    CAGC_REQUIRE(pitch > 0 && pitch % 4 == 0, "modulate: pitch must be a positive multiple of 4");
+    const int64_t n4 = (int64_t)B * H * W * pitch / 4;
+    if (n4 == 0) return 0;
+    int64_t blocks = ceil_div<int64_t>(n4, 256);
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    cagc::tc::modulate_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, s, out, n4, (int64_t)H * W * pitch / 4, pitch / 4);
+    return launched("modulate_kernel");
+}
+
+}  // extern "C"

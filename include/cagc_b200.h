@@ -37,7 +37,7 @@ typedef void* cagc_stream_t; /* cudaStream_t */
 #define CAGC_E_UNSUPPORTED (-2) /* shape outside what the kernels implement */
 
 /* bump when a signature changes; the Python loader checks it */
-#define CAGC_ABI_VERSION 6
+#define CAGC_ABI_VERSION 7
 
 int cagc_abi_version(void);
 const char* cagc_last_error(void);
@@ -98,6 +98,12 @@ int cagc_conv_same(cagc_stream_t stream, const float* in, const float* w_slabs, 
                    const float* out_scale, const float* noise, const float* noise_w, const float* bias,
                    float* out, int B, int H, int W, int in_pitch, int out_pitch, int out_valid,
                    int ksize, int64_t noise_bstride, int act, int algo);
+
+/* x~ = round_to_tf32(x * s[b, c]) on NHWC-p (s == NULL: rounding only).  The tcgen05 path (algo 1)
+ * feeds the tensor pipe straight from shared memory filled by TMA, so it takes the style-modulated
+ * input as a tensor: call this first and pass in_scale = NULL to cagc_conv_same / cagc_conv_up, with
+ * K-major weight slabs taps x [roundup16(out_pitch) rows][in_pitch] instead of the SIMT layout. */
+int cagc_modulate(cagc_stream_t stream, const float* x, const float* s, float* out, int B, int H, int W, int pitch);
 
 /* Transposed stride-2 k x k convolution (model.py:259-267) of the modulated
  * input: out_T[b, 2y+ky, 2x+kx, o] += in[b,y,x,i]*in_scale[b,i]*W[t][i][o];

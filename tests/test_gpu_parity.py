@@ -417,3 +417,57 @@ def test_adam_bucket_step(mods):
         L.check(L.lib.cagc_adam_step(st, p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), n, 0.0016, b1, b2,
                                      1e-8, 0.5, 1 - b1 ** step, 1 - b2 ** step))
     close(p, ref.detach(), 1e-5, 'adam')
+
+
+# ------------------------------------------------------------------ tcgen05 (TF32 tensor pipe) path
+@pytest.mark.parametrize('b,cin,cout,h,up', [(2, 32, 32, 16, False), (1, 39, 39, 16, False), (3, 128, 128, 32, False),
+                                             (2, 154, 154, 16, False), (16, 512, 512, 4, False), (2, 256, 256, 32, False),
+                                             (2, 77, 39, 16, True), (2, 154, 77, 8, True), (1, 64, 32, 5, False),
+                                             (2, 320, 300, 8, False)])
+def test_tcgen05_styled_conv_vs_oracle(mods, b, cin, cout, h, up):
+    """algo 1 (TMA + tcgen05.mma kind::tf32 + TMEM) against the fp64 oracle: forward and all gradients."""
+    model, O, config = mods['model'], mods['O'], mods['config']
+    torch.manual_seed(b * 1000 + cin + cout + h)
+    m = model.StyledConv(cin, cout, 3, 32, upsample=up)
+    with torch.no_grad():
+        m.noise.weight.fill_(0.4)
+        m.activate.bias.copy_(torch.randn(cout) * 0.3)
+    sd = {k: v.double() for k, v in m.state_dict().items()}
+    x = torch.randn(b, cin, h, h, dtype=torch.float64)
+    w = torch.randn(b, 32, dtype=torch.float64)
+    ho = 2 * h if up else h
+    nz = torch.randn(b, 1, ho, ho, dtype=torch.float64)
+    q = {('m.' + k): (v.clone().requires_grad_(True) if 'kernel' not in k else v) for k, v in sd.items()}
+    xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    ref = O.styled_conv(xr, wr, q, 'm', nz, upsample=up)
+    gy = torch.randn_like(ref)
+    names = [k for k, v in q.items() if v.requires_grad]
+    gref = torch.autograd.grad(ref, [xr, wr] + [q[k] for k in names], gy)
+    m = m.cuda()
+    xc, wc = x.float().cuda().requires_grad_(True), w.float().cuda().requires_grad_(True)
+    with config.use_algo(config.ALGO_TCGEN05_TF32):
+        y = m(xc, wc, noise=nz.float().cuda())
+        params = dict(m.named_parameters())
+        grads = torch.autograd.grad(y, [xc, wc] + [params[n[2:]] for n in names], gy.float().cuda())
+    close(y, ref, TOL_TF32, 'tc fwd')
+    close(grads[0], gref[0], TOL_TF32, 'tc gx')
+    close(grads[1], gref[1], TOL_TF32 * 2, 'tc g_latent')
+    for n, gr, rr in zip(names, grads[2:], gref[2:]):
+        close(gr, rr, TOL_TF32 * 2, f'tc grad {n}')
+
+
+def test_tcgen05_generator_vs_golden(golden_dir, mods):
+    """Whole (wider) generator on the tensor pipe vs the oracle: image within 1e-2 of max."""
+    model, O, config = mods['model'], mods['O'], mods['config']
+    torch.manual_seed(21)
+    shape = [64, 64, 64, 64, 48, 48, 40, 40]
+    gen = model.Generator(32, 64, 2, generator_net_shape=shape)
+    _rand_small_params(gen, 5)
+    sd = {k: v.double() for k, v in gen.state_dict().items()}
+    gen = gen.cuda()
+    z = torch.randn(3, 64, dtype=torch.float64)
+    noise = [torch.randn(3, 1, n.shape[2], n.shape[3], dtype=torch.float64) for n in gen.make_noise()]
+    ref = O.generator_forward(sd, 32, [z], noise)
+    with config.use_algo(config.ALGO_TCGEN05_TF32), torch.no_grad():
+        img = gen([z.float().cuda()], noise=[n.float().cuda() for n in noise])
+    close(img, ref, 1e-2, 'tc generator image')
