@@ -15,7 +15,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), 'lib', 'libcagc_b200.so')
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 _p = C.c_void_p
 _i = C.c_int
@@ -36,7 +36,7 @@ SIGNATURES = {
     'cagc_modulate': (_i, [_p, _p, _p, _p, _i, _i, _i, _i]),
     'cagc_conv_up': (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i]),
     'cagc_conv_up_dgrad': (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i]),
-    'cagc_conv_wgrad_splits': (_i, [_i, _i, _i, _i, _i, _i]),
+    'cagc_conv_wgrad_splits': (_i, [_i, _i, _i, _i, _i, _i, _i]),
     'cagc_conv_wgrad': (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i]),
     'cagc_fir_nhwc': (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _l, _i]),
     'cagc_act_bwd_chunks': (_i, [_i, _i]),

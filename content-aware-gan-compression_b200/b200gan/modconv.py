@@ -168,15 +168,15 @@ class _StyledConvFn(Function):
                                                            kh, kw, pad[0], pad[1], pad[0], pad[1], nstride, int(act)),
                                          'fir_nhwc'))
                 del ut
-            del x_in
-        ctx.save_for_backward(xb, s_p, d_p, wk, noise, nw, bias_p, out, fir if upsample else None)
+        xm = x_in if tc else None      # modulated, TF32-rounded input: A operand of the tensor-pipe wgrad
+        ctx.save_for_backward(xb, s_p, d_p, wk, noise, nw, bias_p, out, fir if upsample else None, xm)
         ctx.cfg = (b, cin, cout, h, w, k, pin, pout, upsample, pad, bool(act), nstride, algo, wscale,
                    d is not None, bias is not None)
         return nhwc_view(out, cout)
 
     @staticmethod
     def backward(ctx, ga):
-        xb, s_p, d_p, wk, noise, nw, bias_p, out, fir = ctx.saved_tensors
+        xb, s_p, d_p, wk, noise, nw, bias_p, out, fir, xm = ctx.saved_tensors
         (b, cin, cout, h, w, k, pin, pout, upsample, pad, act, nstride, algo, wscale, has_d, has_bias) = ctx.cfg
         if torch.is_grad_enabled() and ga.requires_grad:
             raise RuntimeError('double backward through the fused modulated convolution is not implemented; '
@@ -215,7 +215,14 @@ class _StyledConvFn(Function):
             g_x = g_s = g_w = None
             if need_x or need_s:
                 gxt = torch.empty((b, h, w, pin), device=dev, dtype=torch.float32)
-                if upsample:
+                if upsample and _use_tc(algo, pout):
+                    w_d = _slabs_tc(wk.permute(2, 3, 1, 0), pout)                    # [t][i][o], K = o
+                    _timed('conv_up_dgrad[algo1]', 2.0 * b * h * w * cin * cout * k * k,
+                           4.0 * b * (h * w * cin + hu * wu * cout),
+                           lambda: check(lib.cagc_conv_up_dgrad(st, g_conv.data_ptr(), w_d.data_ptr(), gxt.data_ptr(),
+                                                                b, h, w, pout, pin, k, config.ALGO_TCGEN05_TF32),
+                                         'conv_up_dgrad(tc)'))
+                elif upsample:
                     w_d = _slabs(wk.permute(2, 3, 0, 1), pout, pin)                 # [t][o][i]
                     _timed('conv_up_dgrad[algo0]', 2.0 * b * h * w * cin * cout * k * k,
                            4.0 * b * (h * w * cin + hu * wu * cout),
@@ -243,14 +250,19 @@ class _StyledConvFn(Function):
                 if need_x:
                     g_x = nhwc_view(gxt, cin)
             if need_w:
-                # the weight gradient always runs on the exact-fp32 engine (fixed reduction order)
-                nsp = lib.cagc_conv_wgrad_splits(b, h, w, pin, pout, k)
+                # exact-fp32 mode (saliency): SIMT engine; tensor-pipe mode: tcgen05 TF32.  Both reduce the
+            # split-K partials in a fixed order (deterministic)
+                walgo = config.ALGO_TCGEN05_TF32 if (xm is not None and _use_tc(algo, min(pin, pout))
+                                                     and pout <= 256) else config.ALGO_SIMT_FP32
+                nsp = lib.cagc_conv_wgrad_splits(b, h, w, pin, pout, k, walgo)
                 gw = torch.empty((k * k, pin, pout), device=dev, dtype=torch.float32)
                 wpart = torch.empty((nsp, k * k, pin, pout), device=dev, dtype=torch.float32)
-                _timed('conv_wgrad[algo0]', 2.0 * b * h * w * cin * cout * k * k, 4.0 * b * h * w * (cin + cout),
-                       lambda: check(lib.cagc_conv_wgrad(st, xb.data_ptr(), s_p.data_ptr(), g_conv.data_ptr(),
+                a_in, a_sc = (xm, None) if walgo == config.ALGO_TCGEN05_TF32 else (xb, s_p.data_ptr())
+                _timed(f'conv_wgrad[algo{walgo}]', 2.0 * b * h * w * cin * cout * k * k,
+                       4.0 * b * h * w * (cin + cout),
+                       lambda: check(lib.cagc_conv_wgrad(st, a_in.data_ptr(), a_sc, g_conv.data_ptr(),
                                                          gw.data_ptr(), wpart.data_ptr(), nsp, b, h, w, pin, pout, k,
-                                                         1 if upsample else 0, 0), 'conv_wgrad'))
+                                                         1 if upsample else 0, walgo), 'conv_wgrad'))
                 g_w = (gw[:, :cin, :cout].reshape(k, k, cin, cout).permute(3, 2, 0, 1) * wscale).unsqueeze(0)
         return (g_x, g_s, g_d, g_w, None, g_nw, g_bias, None, None, None, None, None, None)
 

@@ -345,7 +345,8 @@ int cagc_conv_up_dgrad(cagc_stream_t stream_, const float* g_t, const float* w_s
     return launch_conv(stream, p, "conv_up_dgrad[simt]");
 }
 
-int cagc_conv_wgrad_splits(int B, int H, int W, int a_pitch, int g_pitch, int ksize) {
+int cagc_conv_wgrad_splits(int B, int H, int W, int a_pitch, int g_pitch, int ksize, int algo) {
+    if (algo == 1) return cagc_tc_wgrad_splits(B, H, W, a_pitch, g_pitch, ksize);
     const int64_t M = (int64_t)B * H * W;
     const int64_t tiles = (int64_t)ceil_div(a_pitch, WT) * ceil_div(g_pitch, WT) * ksize * ksize;
     int64_t want = ceil_div<int64_t>(4 * kNumSMs, tiles);       // aim for ~4 CTAs per SM
@@ -364,7 +365,21 @@ int cagc_conv_wgrad(cagc_stream_t stream_, const float* a, const float* a_scale,
     CAGC_REQUIRE(a && g && gw && partial, "conv_wgrad: null pointer");
     CAGC_REQUIRE(nsplits >= 1 && nsplits <= 4096, "conv_wgrad: bad nsplits %d", nsplits);
     CAGC_REQUIRE(mode == 0 || mode == 1, "conv_wgrad: mode must be 0 (same) or 1 (up)");
-    CAGC_REQUIRE(algo == 0, "conv_wgrad: only the fp32 SIMT algorithm is implemented");
+    if (algo == 1) {
+        CAGC_REQUIRE(a_scale == nullptr, "conv_wgrad: the tcgen05 path takes a pre-modulated input (cagc_modulate)");
+        const int64_t n1 = (int64_t)ksize * ksize * a_pitch * g_pitch;
+        if ((int64_t)B * H * W == 0) {
+            cudaError_t e = cudaMemsetAsync(gw, 0, n1 * sizeof(float), stream);
+            return e == cudaSuccess ? 0 : fail((int)e, "conv_wgrad: memset failed");
+        }
+        const int tiles_cap = cagc_tc_wgrad_splits(B, H, W, a_pitch, g_pitch, ksize);
+        if (nsplits > tiles_cap) nsplits = tiles_cap;
+        CAGC_TRY(cagc_tc_wgrad(stream, a, g, partial, nsplits, B, H, W, a_pitch, g_pitch, ksize, mode));
+        int64_t blocks1 = ceil_div<int64_t>(n1 / 4, 256);
+        if (blocks1 > kNumSMs * 8) blocks1 = kNumSMs * 8;
+        split_reduce_kernel<<<(unsigned)blocks1, 256, 0, stream>>>(partial, gw, n1 / 4, nsplits);
+        return launched("split_reduce_kernel");
+    }
     WgradP p{};
     p.a = a; p.a_scale = a_scale; p.g = g; p.partial = partial;
     p.B = B; p.H = H; p.W = W; p.a_pitch = a_pitch; p.g_pitch = g_pitch;

@@ -44,7 +44,7 @@ struct TcParams {
     int n_rows;                 // rows per weight slab
     int Hout, Wout, out_stride, out_oy, out_ox;
     int64_t noise_bstride;
-    int act, ntaps, stages;
+    int act, ntaps, stages, in_stride;
     uint32_t b_bytes;           // bytes of one B stage
     Tap taps[kMaxTaps];
 };
@@ -197,7 +197,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 const int tap = it / nk, kc = it - tap * nk;
                 const Tap tp = p.taps[tap];
                 mbar_expect_tx(full_bar(s), stage_bytes);
-                tma_load_4d(a_addr(s), &map_a, full_bar(s), kc * kChunkK, x0 + tp.dx, y0 + tp.dy, b0);
+                tma_load_4d(a_addr(s), &map_a, full_bar(s), kc * kChunkK, x0 * p.in_stride + tp.dx,
+                            y0 * p.in_stride + tp.dy, b0);
                 tma_load_3d(b_addr(s), &map_b, full_bar(s), kc * kChunkK, n0, tp.slab);
             }
         }
@@ -320,6 +321,162 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
+
+// ================================================================================================
+// Weight gradient on the tensor pipe:  gw[t][i][o] = sum_pixels a[pix + off_a(t)][i] * g[pix*sg + off_g(t)][o]
+// GEMM with M = input channels (128 per CTA), N = output channels (<= 256), K = pixels.  Both operands
+// are channel-contiguous in memory, i.e. MN-major for the MMA: each stage is a 32-pixel box, loaded as
+// 32-channel x 32-pixel TMA boxes (4 KB: 32 K-rows of 128 bytes).  MN-major tf32 operands exist only
+// in the "128B swizzle, 32-byte atom" layout (TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B <-> UMMA
+// SWIZZLE_128B_BASE32B, Swizzle<2,5,2>: 4-row x 128-byte atoms): chunks of 32 channels sit 4 KB apart
+// (descriptor LBO), groups of 4 K-rows 512 bytes apart (SBO); each tf32 MMA (K = 8 pixels) reads two.  One tap per CTA, split-K over pixel tiles with a fixed-order reduction afterwards.
+// ================================================================================================
+struct WgTcParams {
+    float* partial;
+    int a_pitch, g_pitch, n_mma, b_boxes;
+    int ntaps, nsplits, tiles_total, tiles_per_split;
+    int tiles_x, tiles_y, bw, bh, bb;
+    int g_stride, stages;
+    int dya[kMaxTaps], dxa[kMaxTaps], dyg[kMaxTaps], dxg[kMaxTaps];
+};
+
+constexpr int kWgPix = 32;           // pixels (GEMM K) per stage
+constexpr int kBoxBytes = 32 * kWgPix * 4;   // 4 KB
+
+__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fff);
+    d |= (uint64_t)(kBoxBytes >> 4) << 16;   // LBO: next 32-channel chunk along M / N
+    d |= (uint64_t)(512 >> 4) << 32;         // SBO: next group of 4 K-rows (one 32B-atom swizzle period)
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;                  // SWIZZLE_128B_BASE32B
+    return d;
+}
+
+__global__ void __launch_bounds__(kThreads, 2)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_g, const WgTcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 1];
+    __shared__ uint32_t tmem_base_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int S = p.stages;
+    const uint32_t a_bytes = 4 * kBoxBytes, b_bytes = (uint32_t)p.b_boxes * kBoxBytes;
+    const uint32_t stage_bytes = a_bytes + b_bytes;
+    auto a_addr = [&](int s) { return smem_base + (uint32_t)s * stage_bytes; };
+    auto b_addr = [&](int s) { return smem_base + (uint32_t)s * stage_bytes + a_bytes; };
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (kMaxStages + s); };
+    const uint32_t acc_bar = bar0 + 8u * (2 * kMaxStages);
+
+    const int i0 = blockIdx.x * kTileM;
+    const int tap = blockIdx.y, split = blockIdx.z;
+    const int t_lo = split * p.tiles_per_split;
+    const int t_hi = min(p.tiles_total, t_lo + p.tiles_per_split);
+    const int total = t_hi - t_lo;            // host guarantees >= 1
+
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < p.n_mma) tmem_cols <<= 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        mbar_init(acc_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                     "r"(tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_acc = tmem_base_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const int dya = p.dya[tap], dxa = p.dxa[tap], dyg = p.dyg[tap], dxg = p.dxg[tap];
+            for (int it = 0; it < total; ++it) {
+                const int s = it % S;
+                const uint32_t ph = (uint32_t)(it / S) & 1u;
+                mbar_wait(empty_bar(s), ph ^ 1u);
+                int t = t_lo + it;
+                const int tx = t % p.tiles_x;
+                t /= p.tiles_x;
+                const int ty = t % p.tiles_y;
+                const int tb = t / p.tiles_y;
+                const int x0 = tx * p.bw, y0 = ty * p.bh, b0 = tb * p.bb;
+                mbar_expect_tx(full_bar(s), stage_bytes);
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    tma_load_4d(a_addr(s) + c * kBoxBytes, &map_a, full_bar(s), i0 + 32 * c, x0 + dxa, y0 + dya, b0);
+                for (int c = 0; c < p.b_boxes; ++c)
+                    tma_load_4d(b_addr(s) + c * kBoxBytes, &map_g, full_bar(s), 32 * c, x0 * p.g_stride + dxg,
+                                y0 * p.g_stride + dyg, b0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // D=f32, A=B=tf32, both MN-major (bits 15, 16), N>>3, M>>4
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                                   ((uint32_t)(p.n_mma >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+            for (int it = 0; it < total; ++it) {
+                const int s = it % S;
+                const uint32_t ph = (uint32_t)(it / S) & 1u;
+                mbar_wait(full_bar(s), ph);
+                tc_fence_after();
+#pragma unroll
+                for (int j = 0; j < kWgPix / 8; ++j) {
+                    const uint64_t ad = make_desc_mn_sw128(a_addr(s) + j * 1024);
+                    const uint64_t bd = make_desc_mn_sw128(b_addr(s) + j * 1024);
+                    tc_mma_tf32(tmem_acc, ad, bd, idesc, (it > 0 || j > 0) ? 1u : 0u);
+                }
+                tc_commit(empty_bar(s));
+            }
+            tc_commit(acc_bar);
+        }
+    } else {
+        const int q = warp & 3;
+        const int ii = i0 + q * 32 + lane;     // accumulator row = input channel
+        float* dst = p.partial + (((int64_t)split * p.ntaps + tap) * p.a_pitch + ii) * p.g_pitch;
+        mbar_wait(acc_bar, 0);
+        tc_fence_after();
+        for (int c = 0; c < p.n_mma; c += 16) {
+            float v[16];
+            tc_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+            if (ii >= p.a_pitch) continue;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const int o = c + g * 4;
+                if (o < p.g_pitch) st4(dst + o, make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(tmem_cols) : "memory");
+    }
+}
+
+static int encode_act_map(EncodeTiledFn encode, CUtensorMap* map, const float* ptr, int B, int H, int W, int pitch,
+                          int bw, int bh, int bb, int stride) {
+    cuuint64_t dims[4] = {(cuuint64_t)pitch, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)pitch * 4, (cuuint64_t)W * pitch * 4, (cuuint64_t)H * W * pitch * 4};
+    cuuint32_t box[4] = {32, (cuuint32_t)(bw * stride), (cuuint32_t)(bh * stride), (cuuint32_t)bb};
+    cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+    return (int)encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(ptr), dims, strides, box, es,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+}
+
 static int next_pow2(int v) {
     int p = 1;
     while (p < v) p <<= 1;
@@ -334,7 +491,7 @@ using namespace cagc;
 int cagc_tc_conv(cudaStream_t stream, const ConvP& c, const char* what) {
     using namespace cagc::tc;
     CAGC_REQUIRE(c.in_scale == nullptr, "%s: the tcgen05 path takes a pre-modulated input (cagc_modulate)", what);
-    CAGC_REQUIRE(c.in_stride == 1, "%s: strided input is not implemented on the tcgen05 path", what);
+    CAGC_REQUIRE(c.in_stride == 1 || c.in_stride == 2, "%s: input stride must be 1 or 2", what);
     CAGC_REQUIRE(c.in_pitch % 8 == 0 && c.n_cols % 8 == 0, "%s: tcgen05 path needs channel pitches that are multiples of 8",
                  what);
     EncodeTiledFn encode = get_encode();
@@ -355,7 +512,7 @@ int cagc_tc_conv(cudaStream_t stream, const ConvP& c, const char* what) {
     p.n_rows = (c.n_cols + 15) & ~15;
     p.n_tile = std::min(256, p.n_rows);
     p.Hout = c.Hout; p.Wout = c.Wout; p.out_stride = c.out_stride; p.out_oy = c.out_oy; p.out_ox = c.out_ox;
-    p.noise_bstride = c.noise_bstride; p.act = c.act; p.ntaps = c.ntaps;
+    p.noise_bstride = c.noise_bstride; p.act = c.act; p.ntaps = c.ntaps; p.in_stride = c.in_stride;
     for (int i = 0; i < c.ntaps; ++i) p.taps[i] = c.taps[i];
     p.b_bytes = (uint32_t)p.n_tile * kChunkK * 4;
     const uint32_t stage_bytes = kABytes + p.b_bytes;
@@ -368,8 +525,11 @@ int cagc_tc_conv(cudaStream_t stream, const ConvP& c, const char* what) {
         cuuint64_t dims[4] = {(cuuint64_t)c.in_pitch, (cuuint64_t)c.Win, (cuuint64_t)c.Hin, (cuuint64_t)c.B};
         cuuint64_t strides[3] = {(cuuint64_t)c.in_pitch * 4, (cuuint64_t)c.Win * c.in_pitch * 4,
                                  (cuuint64_t)c.Hin * c.Win * c.in_pitch * 4};
-        cuuint32_t box[4] = {(cuuint32_t)kChunkK, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bb};
-        cuuint32_t es[4] = {1, 1, 1, 1};
+        // strided gather (data gradient of the transposed conv): TMA traverses the box with element
+        // stride 2 and delivers ceil(box / stride) elements per dimension
+        const cuuint32_t st = (cuuint32_t)c.in_stride;
+        cuuint32_t box[4] = {(cuuint32_t)kChunkK, (cuuint32_t)p.bw * st, (cuuint32_t)p.bh * st, (cuuint32_t)p.bb};
+        cuuint32_t es[4] = {1, st, st, 1};
         CUresult r = encode(&map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(c.in), dims, strides, box, es,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -399,6 +559,70 @@ int cagc_tc_conv(cudaStream_t stream, const ConvP& c, const char* what) {
     CAGC_REQUIRE(gx <= 0x7fffffffLL, "%s: too many tiles", what);
     dim3 grid((unsigned)gx, ceil_div(p.n_rows, 256));
     conv_tc_kernel<<<grid, kThreads, smem, stream>>>(map_a, map_b, p);
+    return launched(what);
+}
+
+
+int cagc_tc_wgrad_splits(int B, int H, int W, int a_pitch, int g_pitch, int ksize) {
+    using namespace cagc::tc;
+    const int bw = std::min(kWgPix, next_pow2(W)), bh = std::min(kWgPix / bw, next_pow2(H)), bb = kWgPix / (bw * bh);
+    const int64_t tiles = (int64_t)ceil_div(W, bw) * ceil_div(H, bh) * ceil_div(B, bb);
+    const int64_t ctas = (int64_t)ceil_div(a_pitch, kTileM) * ksize * ksize;
+    int64_t want = ceil_div<int64_t>(2 * 2 * kNumSMs, ctas);   // two waves of two CTAs per SM
+    const int64_t max_by_k = std::max<int64_t>(1, tiles / 8);  // at least 8 pixel tiles per split
+    want = std::min(want, max_by_k);
+    want = std::min<int64_t>(want, 512);
+    return (int)std::max<int64_t>(1, want);
+}
+
+int cagc_tc_wgrad(cudaStream_t stream, const float* a, const float* g, float* partial, int nsplits, int B, int H, int W,
+                  int a_pitch, int g_pitch, int ksize, int mode) {
+    using namespace cagc::tc;
+    const char* what = "conv_wgrad[tc]";
+    CAGC_REQUIRE(a_pitch % 8 == 0 && g_pitch % 8 == 0 && a_pitch >= 32 && g_pitch >= 32,
+                 "%s: channel pitches must be multiples of 8 and >= 32", what);
+    CAGC_REQUIRE(g_pitch <= 256, "%s: more than 256 gradient channels per call (caller splits)", what);
+    EncodeTiledFn encode = get_encode();
+    if (!encode) return fail(CAGC_E_UNSUPPORTED, "%s: cuTensorMapEncodeTiled not available from the driver", what);
+    WgTcParams p{};
+    p.partial = partial; p.a_pitch = a_pitch; p.g_pitch = g_pitch;
+    p.n_mma = (g_pitch + 15) & ~15;
+    p.b_boxes = ceil_div(p.n_mma, 32);
+    p.ntaps = ksize * ksize;
+    p.bw = std::min(kWgPix, next_pow2(W));
+    p.bh = std::min(kWgPix / p.bw, next_pow2(H));
+    p.bb = kWgPix / (p.bw * p.bh);
+    p.tiles_x = ceil_div(W, p.bw); p.tiles_y = ceil_div(H, p.bh);
+    const int tiles_b = ceil_div(B, p.bb);
+    p.tiles_total = p.tiles_x * p.tiles_y * tiles_b;
+    if (nsplits > p.tiles_total) nsplits = p.tiles_total;
+    p.tiles_per_split = ceil_div(p.tiles_total, nsplits);
+    CAGC_REQUIRE((int64_t)(nsplits - 1) * p.tiles_per_split < p.tiles_total, "%s: empty split", what);
+    p.nsplits = nsplits;
+    p.g_stride = (mode == 1) ? 2 : 1;
+    for (int ky = 0; ky < ksize; ++ky)
+        for (int kx = 0; kx < ksize; ++kx) {
+            const int t = ky * ksize + kx;
+            if (mode == 0) { p.dya[t] = ky - ksize / 2; p.dxa[t] = kx - ksize / 2; p.dyg[t] = 0; p.dxg[t] = 0; }
+            else           { p.dya[t] = 0; p.dxa[t] = 0; p.dyg[t] = ky; p.dxg[t] = kx; }
+        }
+    const uint32_t stage_bytes = (4 + p.b_boxes) * kBoxBytes;
+    p.stages = std::max(2, std::min(kMaxStages, (int)((kSmemBudget - 1024) / stage_bytes)));
+    const size_t smem = (size_t)p.stages * stage_bytes + 1024;
+    CUtensorMap map_a, map_g;
+    int r = encode_act_map(encode, &map_a, a, B, H, W, a_pitch, p.bw, p.bh, p.bb, 1);
+    if (r != 0) return fail(CAGC_E_INVALID, "%s: cuTensorMapEncodeTiled(a) failed with %d", what, r);
+    const int Hg = mode == 1 ? 2 * H + ksize - 2 : H, Wg = mode == 1 ? 2 * W + ksize - 2 : W;
+    r = encode_act_map(encode, &map_g, g, B, Hg, Wg, g_pitch, p.bw, p.bh, p.bb, p.g_stride);
+    if (r != 0) return fail(CAGC_E_INVALID, "%s: cuTensorMapEncodeTiled(g) failed with %d", what, r);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+        if (e != cudaSuccess) return fail((int)e, "%s: cudaFuncSetAttribute failed: %s", what, cudaGetErrorString(e));
+        attr_set = true;
+    }
+    dim3 grid(ceil_div(a_pitch, kTileM), p.ntaps, nsplits);
+    wgrad_tc_kernel<<<grid, kThreads, smem, stream>>>(map_a, map_g, p);
     return launched(what);
 }
 

@@ -37,7 +37,7 @@ typedef void* cagc_stream_t; /* cudaStream_t */
 #define CAGC_E_UNSUPPORTED (-2) /* shape outside what the kernels implement */
 
 /* bump when a signature changes; the Python loader checks it */
-#define CAGC_ABI_VERSION 7
+#define CAGC_ABI_VERSION 8
 
 int cagc_abi_version(void);
 const char* cagc_last_error(void);
@@ -122,8 +122,9 @@ int cagc_conv_up_dgrad(cagc_stream_t stream, const float* g_t, const float* w_sl
  *   mode 1 (up conv)  : base = input pixel,  a at base, g = g_T at 2*base + (ky, kx)
  * Result slabs taps x [a_pitch][g_pitch]; `partial` is a workspace of
  * cagc_conv_wgrad_splits(...) such slab sets, reduced in a fixed order
- * (deterministic) into gw. */
-int cagc_conv_wgrad_splits(int B, int H, int W, int a_pitch, int g_pitch, int ksize);
+ * (deterministic) into gw.  algo 1 (tcgen05, TF32): `a` must already be modulated (a_scale = NULL),
+ * pitches >= 32 and g_pitch <= 256. */
+int cagc_conv_wgrad_splits(int B, int H, int W, int a_pitch, int g_pitch, int ksize, int algo);
 int cagc_conv_wgrad(cagc_stream_t stream, const float* a, const float* a_scale, const float* g,
                     float* gw, float* partial, int nsplits, int B, int H, int W,
                     int a_pitch, int g_pitch, int ksize, int mode, int algo);

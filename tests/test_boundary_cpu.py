@@ -32,9 +32,9 @@ def test_pure_host_entry_points():
     L = _lib.lib
     assert L.cagc_bias_grad_chunks(16) == 0 and L.cagc_bias_grad_chunks(65536) == 16
     assert L.cagc_act_bwd_chunks(4, 4) == 1 and L.cagc_act_bwd_chunks(256, 256) == 64
-    s = L.cagc_conv_wgrad_splits(16, 256, 256, 40, 40, 3)
+    s = L.cagc_conv_wgrad_splits(16, 256, 256, 40, 40, 3, 0)
     assert 1 <= s <= 256
-    assert L.cagc_conv_wgrad_splits(16, 4, 4, 512, 512, 3) <= 2
+    assert L.cagc_conv_wgrad_splits(16, 4, 4, 512, 512, 3, 0) <= 2
 
 
 def test_state_dict_contract_matches_reference(golden_dir):
