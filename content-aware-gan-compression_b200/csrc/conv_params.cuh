@@ -36,5 +36,5 @@ struct ConvP {
 int cagc_tc_conv(cudaStream_t stream, const cagc::ConvP& p, const char* what);
 // weight gradient on the tensor pipe; `a` is the pre-modulated layer input; returns the number of splits used
 int cagc_tc_wgrad_splits(int B, int H, int W, int a_pitch, int g_pitch, int ksize);
-int cagc_tc_wgrad(cudaStream_t stream, const float* a, const float* g, float* partial, int nsplits, int B, int H, int W,
-                  int a_pitch, int g_pitch, int ksize, int mode);
+int cagc_tc_wgrad(cudaStream_t stream, const float* a, const float* g, float* partial, int* nsplits_io, int B, int H,
+                  int W, int a_pitch, int g_pitch, int ksize, int mode);

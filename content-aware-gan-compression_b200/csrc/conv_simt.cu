@@ -374,7 +374,7 @@ int cagc_conv_wgrad(cagc_stream_t stream_, const float* a, const float* a_scale,
         }
         const int tiles_cap = cagc_tc_wgrad_splits(B, H, W, a_pitch, g_pitch, ksize);
         if (nsplits > tiles_cap) nsplits = tiles_cap;
-        CAGC_TRY(cagc_tc_wgrad(stream, a, g, partial, nsplits, B, H, W, a_pitch, g_pitch, ksize, mode));
+        CAGC_TRY(cagc_tc_wgrad(stream, a, g, partial, &nsplits, B, H, W, a_pitch, g_pitch, ksize, mode));
         int64_t blocks1 = ceil_div<int64_t>(n1 / 4, 256);
         if (blocks1 > kNumSMs * 8) blocks1 = kNumSMs * 8;
         split_reduce_kernel<<<(unsigned)blocks1, 256, 0, stream>>>(partial, gw, n1 / 4, nsplits);

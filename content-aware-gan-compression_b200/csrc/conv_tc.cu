@@ -575,8 +575,9 @@ int cagc_tc_wgrad_splits(int B, int H, int W, int a_pitch, int g_pitch, int ksiz
     return (int)std::max<int64_t>(1, want);
 }
 
-int cagc_tc_wgrad(cudaStream_t stream, const float* a, const float* g, float* partial, int nsplits, int B, int H, int W,
-                  int a_pitch, int g_pitch, int ksize, int mode) {
+int cagc_tc_wgrad(cudaStream_t stream, const float* a, const float* g, float* partial, int* nsplits_io, int B, int H,
+                  int W, int a_pitch, int g_pitch, int ksize, int mode) {
+    int nsplits = *nsplits_io;
     using namespace cagc::tc;
     const char* what = "conv_wgrad[tc]";
     CAGC_REQUIRE(a_pitch % 8 == 0 && g_pitch % 8 == 0 && a_pitch >= 32 && g_pitch >= 32,
@@ -597,7 +598,8 @@ int cagc_tc_wgrad(cudaStream_t stream, const float* a, const float* g, float* pa
     p.tiles_total = p.tiles_x * p.tiles_y * tiles_b;
     if (nsplits > p.tiles_total) nsplits = p.tiles_total;
     p.tiles_per_split = ceil_div(p.tiles_total, nsplits);
-    CAGC_REQUIRE((int64_t)(nsplits - 1) * p.tiles_per_split < p.tiles_total, "%s: empty split", what);
+    nsplits = ceil_div(p.tiles_total, p.tiles_per_split);      // no empty split
+    *nsplits_io = nsplits;
     p.nsplits = nsplits;
     p.g_stride = (mode == 1) ? 2 : 1;
     for (int ky = 0; ky < ksize; ++ky)
