@@ -155,6 +155,7 @@ def main():
     ap.add_argument('--batch', type=int, default=16, help='images per GPU per step (weak scaling)')
     ap.add_argument('--algo', default='auto', choices=['auto', 'simt', 'tc'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='launch every kernel from Python instead of one CUDA graph per step')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -194,25 +195,28 @@ def main():
         D.synchronize()
         torch.cuda.synchronize(dev)
 
-    # ---------------- device-resident timing (value) + per-kernel events (roofline)
+    # ---------------- device-resident timing (value)
+    use_graph = not args.no_graph
+    if use_graph:
+        kd.capture(B, inject)            # includes 3 eager warm-up steps on a side stream
+        run_step = lambda z: kd.step_graphed(z)
+    else:
+        run_step = lambda z: kd.step(z, inject)
     for _ in range(args.warmup):
-        kd.step(fresh_latents(), inject)
+        run_step(fresh_latents())
     lat = [fresh_latents() for _ in range(args.steps)]
-    prof = config.KernelProfiler()
     sampler = ClockSampler(local)
     barrier_sync()
     if rank == 0:
         sampler.start()
-    config.set_profiler(prof)
     n0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
-        kd.step(lat[i], inject)
+        run_step(lat[i])
     e1.record()
     barrier_sync()
-    launches = _lib.launch_count() - n0
-    config.set_profiler(None)
+    launches = (kd.launches_per_replay * args.steps) if use_graph else (_lib.launch_count() - n0)
     clocks = sampler.stop() if rank == 0 else None
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
@@ -236,6 +240,17 @@ def main():
         torch.distributed.all_reduce(ems, op=torch.distributed.ReduceOp.MAX)
     e2e_value = world * B * args.steps / (float(ems.item()) / 1e3)
 
+    # ---------------- per-kernel CUDA events (roofline): eager steps, events on the launching stream
+    prof = config.KernelProfiler()
+    kd.step(lat[0], inject)
+    barrier_sync()
+    config.set_profiler(prof)
+    prof_steps = min(args.steps, 5)
+    for i in range(prof_steps):
+        kd.step(lat[i], inject)
+    barrier_sync()
+    config.set_profiler(None)
+
     # ---------------- generator slice alone (student f+b, teacher f) for the Amdahl picture
     def slice_step(z):
         kd.bucket.zero_grad()
@@ -243,13 +258,27 @@ def main():
         with torch.no_grad():
             real = teacher(z, return_rgb_list=True, inject_index=inject)
         (3.0 * (real[-1] - fake[-1]).abs().mean()).backward()
-    for _ in range(2):
-        slice_step(lat[0])
+    zs = fresh_latents()
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            slice_step(zs)
+    torch.cuda.current_stream(dev).wait_stream(side)
+    barrier_sync()
+    if use_graph:
+        sg = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(sg):
+            slice_step(zs)
+        run_slice = sg.replay
+    else:
+        run_slice = lambda: slice_step(zs)
+    run_slice()
     barrier_sync()
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s0.record()
     for i in range(args.steps):
-        slice_step(lat[i])
+        run_slice()
     s1.record()
     barrier_sync()
     slice_ms = s0.elapsed_time(s1) / args.steps
@@ -261,7 +290,7 @@ def main():
     kernels = {}
     for name, r in summ.items():
         per = r['ms'] / max(r['launches'], 1)
-        kernels[name] = {'launches_per_step': r['launches'] / args.steps, 'ms_per_step': r['ms'] / args.steps,
+        kernels[name] = {'launches_per_step': r['launches'] / prof_steps, 'ms_per_step': r['ms'] / prof_steps,
                          'avg_launch_us': per * 1e3,
                          'tflops': (r['flops'] / (r['ms'] / 1e3) / 1e12) if r['flops'] and r['ms'] else None,
                          'gbs': (r['bytes'] / (r['ms'] / 1e3) / 1e9) if r['bytes'] and r['ms'] else None}
@@ -304,7 +333,9 @@ def main():
                                f'grad all-reduce, fused Adam; batch {B}/GPU; style mixing inject_index={inject}',
                    'global_batch': B * world, 'parallelism': f'dp{world}',
                    'l2': 'per-step working set (>=4 GB of activations) exceeds the 126 MB L2; no explicit flush',
-                   'conv_algo': 'tcgen05-tf32' if algo == config.ALGO_TCGEN05_TF32 else 'simt-fp32'},
+                   'conv_algo': 'tcgen05-tf32' if algo == config.ALGO_TCGEN05_TF32 else 'simt-fp32',
+                   'launch': 'one CUDA graph per step' if use_graph else 'eager launches',
+                   'kernel_timing': f'CUDA events around each native launch over {prof_steps} eager steps in this run'},
         'e2e': {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': 2 * B * 512 * 4,
                 'd2h_bytes_per_step': 4},
         'gpu_launches': int(launches),

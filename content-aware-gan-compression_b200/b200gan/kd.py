@@ -25,19 +25,23 @@ class KDStep:
             p.requires_grad_(False)
         for p in discriminator.parameters():
             p.requires_grad_(False)          # train.py:286-287 (requires_grad(D, False))
+        # the discriminator's library convolutions run NHWC kernels: keep its tensors channels-last so that
+        # no NCHW<->NHWC conversion surrounds them; our upfirdn2d / fused_leaky_relu work on that storage
+        discriminator.to(memory_format=torch.channels_last)
         self.bucket = D.FlatBucket(student.parameters())
         self.exp_avg = torch.zeros_like(self.bucket.flat_param)
         self.exp_avg_sq = torch.zeros_like(self.bucket.flat_param)
         self.lr, self.betas, self.eps = lr, betas, eps
         self.kd_l1_lambda = kd_l1_lambda
         self.mask = mask
-        self.t = 0
         self.device = self.bucket.flat_param.device
+        self.t_dev = torch.zeros(1, device=self.device)      # Adam step count, device-resident (graph-safe)
+        self.graph = None
 
     def losses(self, z: List[torch.Tensor], inject_index: int, s_noise=None, t_noise=None):
         """GAN + KD losses; per-layer noise is drawn fresh (train.py:291,151) unless given explicitly."""
         fake = self.student(z, return_rgb_list=True, inject_index=inject_index, noise=s_noise)
-        g_loss = F.softplus(-self.disc(fake[-1])).mean()
+        g_loss = F.softplus(-self.disc(fake[-1].contiguous(memory_format=torch.channels_last))).mean()
         with torch.no_grad():
             real = self.teacher(z, return_rgb_list=True, inject_index=inject_index, noise=t_noise)
         s_img, t_img = fake[-1], real[-1]
@@ -53,17 +57,51 @@ class KDStep:
         total = g_loss + kd
         total.backward()
         self.bucket.allreduce_mean_()
-        self.t += 1
+        self.t_dev += 1
         b1, b2 = self.betas
         with torch.cuda.device(self.device):
             check(lib.cagc_adam_step(torch.cuda.current_stream(self.device).cuda_stream,
                                      self.bucket.flat_param.data_ptr(), self.bucket.flat_grad.data_ptr(),
                                      self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.bucket.numel,
-                                     self.lr, b1, b2, self.eps, 1.0 / D.get_world_size(),
-                                     1.0 - b1 ** self.t, 1.0 - b2 ** self.t), 'adam_step')
+                                     self.lr, b1, b2, self.eps, 1.0 / D.get_world_size(), 1.0, 1.0,
+                                     self.t_dev.data_ptr()), 'adam_step')
         return total.detach()
+
+    # ------------------------------------------------------------------ CUDA-graph form
+    def capture(self, batch: int, inject_index: int, style_dim: int = 512):
+        """Capture the whole step (forward, backward, all-reduce, Adam) into one CUDA graph: a few
+        thousand launches per step become one graph launch.  Shapes, inject_index and the set of
+        tensors are frozen; latents are fed through static input buffers; per-layer noise is drawn
+        inside the graph by torch's graph-safe Philox generator."""
+        dev = self.device
+        self.z_static = [torch.zeros(batch, style_dim, device=dev), torch.zeros(batch, style_dim, device=dev)]
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                self.z_static[0].normal_()
+                self.z_static[1].normal_()
+                self.step(self.z_static, inject_index)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        from ._lib import launch_count
+        n0 = launch_count()
+        with torch.cuda.graph(self.graph):
+            self.loss_static = self.step(self.z_static, inject_index)
+        self.launches_per_replay = launch_count() - n0
+        return self
+
+    def step_graphed(self, z: List[torch.Tensor]) -> torch.Tensor:
+        """Replay the captured step on new latents (device or pinned-host tensors)."""
+        for dst, src in zip(self.z_static, z):
+            dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self.loss_static
 
     def step_from_host(self, z_host: List[torch.Tensor], inject_index: int) -> float:
         """End-to-end form: latents arrive in pinned host memory, the loss is read back."""
+        if self.graph is not None:
+            return float(self.step_graphed(z_host).item())
         z = [t.to(self.device, non_blocking=True) for t in z_host]
         return float(self.step(z, inject_index).item())

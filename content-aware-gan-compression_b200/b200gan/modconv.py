@@ -51,6 +51,27 @@ def as_nhwc_buf(x: torch.Tensor) -> torch.Tensor:
     return buf
 
 
+_frozen = {}
+
+
+def cached_frozen(param: torch.Tensor, tag, fn):
+    """Weight-derived tensors (scaled weights, operand slabs, sum-of-squares for the demodulation) of
+    a FROZEN parameter -- the teacher generator in the KD step -- are computed once and reused; a
+    trainable parameter is always re-derived (its storage may be updated behind torch's version
+    counter by the fused optimizer kernel)."""
+    if param.requires_grad or torch.is_grad_enabled() and param.grad_fn is not None:
+        return fn()
+    key = (param.data_ptr(), param._version, tuple(param.shape), tag)
+    hit = _frozen.get(key)
+    if hit is None:
+        if len(_frozen) > 4096:
+            _frozen.clear()
+        with torch.no_grad():
+            hit = fn()
+        _frozen[key] = hit
+    return hit
+
+
 def _timed(name, flops, nbytes, fn):
     """Run a native launch, bracketing it with CUDA events when bench.py installed a profiler."""
     prof = config.profiler()
@@ -119,17 +140,19 @@ class _StyledConvFn(Function):
             s_p = _pad_last(s.detach().float(), pin)
             d_p = _pad_last(d.detach().float(), pout) if d is not None else None
             bias_p = _pad_last(bias.detach().float(), pout) if bias is not None else None
-            wk = (weight.detach()[0] * wscale)                       # [O,I,k,k]
+            wk = cached_frozen(weight, ('wk', wscale), lambda: weight.detach()[0] * wscale)   # [O,I,k,k]
             tc = _use_tc(algo, pin)
             if tc:
                 # tensor-pipe path: operands come straight from TMA, so modulation is a tensor pass
-                w_fwd = _slabs_tc(wk.permute(2, 3, 0, 1), pin)       # [t][o][i], K-major
+                w_fwd = cached_frozen(weight, ('fwd_tc', wscale, pin),
+                                      lambda: _slabs_tc(wk.permute(2, 3, 0, 1), pin))   # [t][o][i], K-major
                 x_in = torch.empty_like(xb)
                 if xb.numel():
                     check(lib.cagc_modulate(st, xb.data_ptr(), s_p.data_ptr(), x_in.data_ptr(), b, h, w, pin), 'modulate')
                 s_arg, falgo = None, config.ALGO_TCGEN05_TF32
             else:
-                w_fwd = _slabs(wk.permute(2, 3, 1, 0), pin, pout)    # [t][i][o]
+                w_fwd = cached_frozen(weight, ('fwd_simt', wscale, pin, pout),
+                                      lambda: _slabs(wk.permute(2, 3, 1, 0), pin, pout))  # [t][i][o]
                 x_in, s_arg, falgo = xb, s_p.data_ptr(), config.ALGO_SIMT_FP32
             if noise is not None:
                 noise = noise.detach().contiguous()
@@ -347,7 +370,7 @@ def to_rgb(x, s, weight, bias, skip, wscale, fir=None, pad=(0, 0)):
 
 def demod_coefficients(s: torch.Tensor, weight: torch.Tensor, wscale: float, eps: float = 1e-8) -> torch.Tensor:
     """d[b,o] = rsqrt(sum_i s[b,i]^2 * Wsq[o,i] + eps), Wsq = sum_taps (c*W)^2   (model.py:251-253)."""
-    wsq = (weight[0] * wscale).square().sum(dim=(2, 3))           # [O,I]
+    wsq = cached_frozen(weight, ('wsq', wscale), lambda: (weight[0] * wscale).square().sum(dim=(2, 3)))   # [O,I]
     return torch.rsqrt(s.square() @ wsq.t() + eps)
 
 

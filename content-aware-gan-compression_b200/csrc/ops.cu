@@ -300,8 +300,13 @@ __global__ void __launch_bounds__(256) to_nhwc_direct_kernel(const float* __rest
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                    float* __restrict__ m, float* __restrict__ v, int64_t n, float lr,
                                                    float b1, float b2, float eps, float gscale, float bc1, float bc2,
-                                                   int vec) {
+                                                   const float* __restrict__ step_dev, int vec) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    if (step_dev) {  // step count lives on the device so that a captured CUDA graph stays valid across replays
+        const float t = __ldg(step_dev);
+        bc1 = 1.f - powf(b1, t);
+        bc2 = 1.f - powf(b2, t);
+    }
     const float step = lr / bc1;
     const float inv_sqrt_bc2 = rsqrtf(bc2);
     auto upd = [&](float& pp, float gg, float& mm, float& vv) {
@@ -444,13 +449,13 @@ int cagc_to_nhwc(cagc_stream_t stream_, const float* src, int64_t sb, int64_t sc
 
 int cagc_adam_step(cagc_stream_t stream_, float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
                    int64_t n, float lr, float beta1, float beta2, float eps, float grad_scale, float bias_corr1,
-                   float bias_corr2) {
+                   float bias_corr2, const float* step_dev) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (n == 0) return 0;
     CAGC_REQUIRE(param && grad && exp_avg && exp_avg_sq, "adam_step: null pointer");
     const int vec = aligned16(param) && aligned16(grad) && aligned16(exp_avg) && aligned16(exp_avg_sq);
     adam_kernel<<<grid_for(vec ? n / 4 + 1 : n), 256, 0, stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1,
-                                                                    beta2, eps, grad_scale, bias_corr1, bias_corr2, vec);
+                                                                    beta2, eps, grad_scale, bias_corr1, bias_corr2, step_dev, vec);
     return launched("adam_kernel");
 }
 

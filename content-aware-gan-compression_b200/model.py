@@ -125,7 +125,7 @@ class EqualLinear(nn.Module):
         self.lr_mul = lr_mul
 
     def forward(self, input):
-        w = self.weight * self.scale
+        w = _mc.cached_frozen(self.weight, ('eqlin', self.scale), lambda: self.weight * self.scale)
         if self.activation:
             return fused_leaky_relu(F.linear(input, w), self.bias * self.lr_mul)
         return F.linear(input, w, bias=self.bias * self.lr_mul)

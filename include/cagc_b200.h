@@ -37,7 +37,7 @@ typedef void* cagc_stream_t; /* cudaStream_t */
 #define CAGC_E_UNSUPPORTED (-2) /* shape outside what the kernels implement */
 
 /* bump when a signature changes; the Python loader checks it */
-#define CAGC_ABI_VERSION 8
+#define CAGC_ABI_VERSION 9
 
 int cagc_abi_version(void);
 const char* cagc_last_error(void);
@@ -177,10 +177,12 @@ int cagc_to_nhwc(cagc_stream_t stream, const float* src, int64_t sb, int64_t sc,
  * gradient allreduce, Miscellaneous/distributed.py:57-66 + train.py:308):
  *   g = grad[i]*grad_scale; m = b1*m + (1-b1)*g; v = b2*v + (1-b2)*g*g;
  *   p -= lr * (m/bc1) / (sqrt(v/bc2) + eps)     (torch.optim.Adam semantics)
+ * step_dev (optional, device pointer to the step count t as a float): when given, the bias
+ * corrections are computed on the device as 1 - beta^t, so the launch can be replayed from a CUDA graph.
  * ---------------------------------------------------------------------- */
 int cagc_adam_step(cagc_stream_t stream, float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
                    int64_t n, float lr, float beta1, float beta2, float eps, float grad_scale,
-                   float bias_corr1, float bias_corr2);
+                   float bias_corr1, float bias_corr2, const float* step_dev);
 
 #ifdef __cplusplus
 }

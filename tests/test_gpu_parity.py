@@ -415,7 +415,7 @@ def test_adam_bucket_step(mods):
         opt.step()
         b1, b2 = 0.0, 0.99 ** 0.8
         L.check(L.lib.cagc_adam_step(st, p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), n, 0.0016, b1, b2,
-                                     1e-8, 0.5, 1 - b1 ** step, 1 - b2 ** step))
+                                     1e-8, 0.5, 1 - b1 ** step, 1 - b2 ** step, None))
     close(p, ref.detach(), 1e-5, 'adam')
 
 
@@ -508,3 +508,52 @@ def test_tcgen05_generator_vs_golden(golden_dir, mods):
     with config.use_algo(config.ALGO_TCGEN05_TF32), torch.no_grad():
         img = gen([z.float().cuda()], noise=[n.float().cuda() for n in noise])
     close(img, ref, 1e-2, 'tc generator image')
+
+
+def test_upfirdn2d_channels_last_and_discriminator(mods):
+    """Channels-last storage goes through the NHWC FIR kernel; a channels-last Discriminator equals the
+    oracle (its convolutions are library calls; fp32 forced for the comparison)."""
+    op, O, model = mods['op'], mods['O'], mods['model']
+    torch.manual_seed(8)
+    x = torch.randn(2, 8, 19, 23, dtype=torch.float64)
+    k = O.fir_kernel_2d([1, 3, 3, 1])
+    xr = x.clone().requires_grad_(True)
+    ref = O.upfirdn2d(xr, k, pad=(2, 2))
+    gy = torch.randn_like(ref)
+    gref, = torch.autograd.grad(ref, xr, gy)
+    xc = x.float().cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    y = op.upfirdn2d(xc, k.float().cuda(), pad=(2, 2))
+    assert y.is_contiguous(memory_format=torch.channels_last)
+    close(y, ref, TOL_BW, 'nhwc blur fwd')
+    gx, = torch.autograd.grad(y, xc, gy.float().cuda().contiguous(memory_format=torch.channels_last))
+    close(gx, gref, TOL_BW, 'nhwc blur bwd')
+
+    prev = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        d = model.Discriminator(32)
+        with torch.no_grad():
+            for n, p in d.named_parameters():
+                if n.endswith('bias'):
+                    p.copy_(torch.randn_like(p) * 0.2)
+        sd = {kk: v.double() for kk, v in d.state_dict().items()}
+        img = torch.randn(4, 3, 32, 32, dtype=torch.float64)
+        ir = img.clone().requires_grad_(True)
+        ref = O.discriminator_forward(sd, ir, 32)
+        gref, = torch.autograd.grad(ref.sum(), ir)
+        for cl in (False, True):
+            dd = model.Discriminator(32)
+            dd.load_state_dict({kk: v.float() for kk, v in sd.items()})
+            dd = dd.cuda()
+            ic = img.float().cuda()
+            if cl:
+                dd = dd.to(memory_format=torch.channels_last)
+                ic = ic.contiguous(memory_format=torch.channels_last)
+            ic.requires_grad_(True)
+            out = dd(ic)
+            close(out, ref, 1e-4, f'discriminator fwd channels_last={cl}')
+            g, = torch.autograd.grad(out.sum(), ic)
+            close(g, gref, 1e-3, f'discriminator dgrad channels_last={cl}')
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
