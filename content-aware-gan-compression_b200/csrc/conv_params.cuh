@@ -38,3 +38,8 @@ int cagc_tc_conv(cudaStream_t stream, const cagc::ConvP& p, const char* what);
 int cagc_tc_wgrad_splits(int B, int H, int W, int a_pitch, int g_pitch, int ksize);
 int cagc_tc_wgrad(cudaStream_t stream, const float* a, const float* g, float* partial, int* nsplits_io, int B, int H,
                   int W, int a_pitch, int g_pitch, int ksize, int mode);
+
+// TMA-staged NHWC FIR; returns 1 when it handled the call (result code in *rc), 0 to use the plain kernel
+int cagc_tc_fir_nhwc(cudaStream_t stream, const float* in, const float* fir, const float* out_scale, const float* noise,
+                     const float* noise_w, const float* bias, float* out, int B, int in_h, int in_w, int out_h, int out_w,
+                     int pitch, int valid, int pad_x0, int pad_y0, int64_t noise_bstride, int act, int* rc);

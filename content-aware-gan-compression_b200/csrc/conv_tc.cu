@@ -465,6 +465,106 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     }
 }
 
+
+// ================================================================================================
+// NHWC-p FIR (Blur) with TMA staging: one 4-D box load (32 channels x 35 x 11 pixels, zero fill for the
+// padding) per CTA lands the whole input window in shared memory; 256 threads = 32 pixels x 8 channel
+// quads produce 8 output rows from a register ring, conflict-free 128-bit shared loads, fused
+// demodulation / noise / bias / leaky-ReLU epilogue.  Four CTAs per SM keep loads and math overlapped.
+// ================================================================================================
+constexpr int kFirTX = 32, kFirTR = 8, kFirCC = 32;
+
+struct FirParams {
+    const float* fir;
+    const float* out_scale;
+    const float* noise;
+    const float* noise_w;
+    const float* bias;
+    float* out;
+    int out_h, out_w, pitch, valid, c_chunks, pad_x0, pad_y0, act;
+    int64_t noise_bstride;
+};
+
+template <int KH, int KW>
+__global__ void __launch_bounds__(256, 3) fir_nhwc_tma_kernel(const __grid_constant__ CUtensorMap map_in,
+                                                              const FirParams p) {
+    constexpr int BW = kFirTX + KW - 1, BH = kFirTR + KH - 1;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ float skf[KH * KW];
+    const uint32_t tile = (smem_u32(smem_raw) + 127u) & ~127u;
+    const float* tile_ptr = reinterpret_cast<const float*>(smem_raw + (tile - smem_u32(smem_raw)));
+    const int cchunk = blockIdx.x % p.c_chunks, xt = blockIdx.x / p.c_chunks;
+    const int x0 = xt * kFirTX, y0 = blockIdx.y * kFirTR, b = blockIdx.z, c0 = cchunk * kFirCC;
+    const uint32_t bar_a = smem_u32(&bar);
+    if (threadIdx.x == 0) {
+        mbar_init(bar_a, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(bar_a, BW * BH * kFirCC * 4);
+        tma_load_4d(tile, &map_in, bar_a, c0, x0 - p.pad_x0, y0 - p.pad_y0, b);
+    }
+    if (threadIdx.x < KH * KW) {
+        const int ky = threadIdx.x / KW, kx = threadIdx.x % KW;
+        skf[threadIdx.x] = p.fir[(KH - 1 - ky) * KW + (KW - 1 - kx)];
+    }
+    __syncthreads();
+    float kf[KH * KW];
+#pragma unroll
+    for (int i = 0; i < KH * KW; ++i) kf[i] = skf[i];
+
+    const int c4 = threadIdx.x & 7, tx = threadIdx.x >> 3;
+    const int c = c0 + c4 * 4, ox = x0 + tx;
+    const bool live = (ox < p.out_w) && (c < p.pitch);
+    float4 scale4 = make_float4(1.f, 1.f, 1.f, 1.f), bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float nw = 0.f;
+    if (live) {
+        if (p.out_scale) scale4 = ldg4(p.out_scale + (int64_t)b * p.pitch + c);
+        if (p.bias) bias4 = ldg4(p.bias + c);
+        if (p.noise) nw = __ldg(p.noise_w);
+    }
+    mbar_wait(bar_a, 0);
+
+    const float* base = tile_ptr + tx * kFirCC + c4 * 4;
+    float4 ring[KH][KW];
+#pragma unroll
+    for (int r = 0; r < BH; ++r) {
+#pragma unroll
+        for (int j = 0; j < KW; ++j) ring[r % KH][j] = ld4(base + (r * BW + j) * kFirCC);
+        if (r >= KH - 1) {
+            const int q = r - (KH - 1);
+            const int oy = y0 + q;
+            if (live && oy < p.out_h) {
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int i = 0; i < KH; ++i)
+#pragma unroll
+                    for (int j = 0; j < KW; ++j) {
+                        const float k = kf[i * KW + j];
+                        const float4 v = ring[(q + i) % KH][j];
+                        acc.x = fmaf(k, v.x, acc.x);
+                        acc.y = fmaf(k, v.y, acc.y);
+                        acc.z = fmaf(k, v.z, acc.z);
+                        acc.w = fmaf(k, v.w, acc.w);
+                    }
+                float v[4] = {acc.x * scale4.x, acc.y * scale4.y, acc.z * scale4.z, acc.w * scale4.w};
+                if (p.noise) {
+                    const float nz = nw * __ldg(p.noise + (int64_t)b * p.noise_bstride + (int64_t)oy * p.out_w + ox);
+                    v[0] += nz; v[1] += nz; v[2] += nz; v[3] += nz;
+                }
+                v[0] += bias4.x; v[1] += bias4.y; v[2] += bias4.z; v[3] += bias4.w;
+                if (p.act) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) v[j] = lrelu_sqrt2(v[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (c + j >= p.valid) v[j] = 0.f;
+                st4(p.out + (((int64_t)b * p.out_h + oy) * p.out_w + ox) * p.pitch + c, make_float4(v[0], v[1], v[2], v[3]));
+            }
+        }
+    }
+}
+
 static int encode_act_map(EncodeTiledFn encode, CUtensorMap* map, const float* ptr, int B, int H, int W, int pitch,
                           int bw, int bh, int bb, int stride) {
     cuuint64_t dims[4] = {(cuuint64_t)pitch, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
@@ -626,6 +726,41 @@ int cagc_tc_wgrad(cudaStream_t stream, const float* a, const float* g, float* pa
     dim3 grid(ceil_div(a_pitch, kTileM), p.ntaps, nsplits);
     wgrad_tc_kernel<<<grid, kThreads, smem, stream>>>(map_a, map_g, p);
     return launched(what);
+}
+
+// returns 1 if the TMA path took the call, 0 if the caller should use the plain kernel, <0 / >1 on error
+int cagc_tc_fir_nhwc(cudaStream_t stream, const float* in, const float* fir, const float* out_scale, const float* noise,
+                     const float* noise_w, const float* bias, float* out, int B, int in_h, int in_w, int out_h, int out_w,
+                     int pitch, int valid, int pad_x0, int pad_y0, int64_t noise_bstride, int act, int* rc) {
+    using namespace cagc::tc;
+    *rc = 0;
+    if (pitch < 32 || B > 65535) return 0;
+    EncodeTiledFn encode = get_encode();
+    if (!encode) return 0;
+    CUtensorMap map;
+    cuuint64_t dims[4] = {(cuuint64_t)pitch, (cuuint64_t)in_w, (cuuint64_t)in_h, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)pitch * 4, (cuuint64_t)in_w * pitch * 4, (cuuint64_t)in_h * in_w * pitch * 4};
+    cuuint32_t box[4] = {(cuuint32_t)kFirCC, (cuuint32_t)(kFirTX + 3), (cuuint32_t)(kFirTR + 3), 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    if (encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(in), dims, strides, box, es,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return 0;
+    FirParams p{};
+    p.fir = fir; p.out_scale = out_scale; p.noise = noise; p.noise_w = noise_w; p.bias = bias; p.out = out;
+    p.out_h = out_h; p.out_w = out_w; p.pitch = pitch; p.valid = valid; p.c_chunks = ceil_div(pitch, kFirCC);
+    p.pad_x0 = pad_x0; p.pad_y0 = pad_y0; p.act = act; p.noise_bstride = noise_bstride;
+    const size_t smem = (size_t)(kFirTX + 3) * (kFirTR + 3) * kFirCC * 4 + 128;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(fir_nhwc_tma_kernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { *rc = fail((int)e, "fir_nhwc[tma]: cudaFuncSetAttribute failed"); return 1; }
+        attr_set = true;
+    }
+    dim3 grid(ceil_div(out_w, kFirTX) * p.c_chunks, ceil_div(out_h, kFirTR), B);
+    fir_nhwc_tma_kernel<4, 4><<<grid, 256, smem, stream>>>(map, p);
+    *rc = launched("fir_nhwc_tma_kernel");
+    return 1;
 }
 
 extern "C" {

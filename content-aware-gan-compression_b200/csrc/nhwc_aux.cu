@@ -7,7 +7,7 @@
 // All of them are HBM-bound: one 128-bit access per thread per tensor element, threads contiguous
 // along (pixel, channel), per-thread channel ownership so that the per-channel reductions live in
 // registers, fixed-order (deterministic) partial sums.
-#include "common.cuh"
+#include "conv_params.cuh"
 
 namespace cagc {
 
@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(256) torgb_bwd_kernel(const float* __restrict_
 }
 
 static inline int pixel_chunks(int HW) {
-    int c = ceil_div(HW, kChunkPixels);
+    int c = ceil_div(HW, HW >= 16384 ? kChunkPixels : 256);
     if (c < 1) c = 1;
     if (c > 128) c = 128;
     return c;
@@ -394,6 +394,12 @@ int cagc_fir_nhwc(cagc_stream_t stream_, const float* in, const float* fir, cons
     if (kh != 4 || kw != 4) return fail(CAGC_E_UNSUPPORTED, "fir_nhwc: only 4x4 FIR kernels are implemented (got %dx%d)", kh, kw);
     const int out_h = in_h + pad_y0 + pad_y1 - kh + 1, out_w = in_w + pad_x0 + pad_x1 - kw + 1;
     if (B == 0 || out_h <= 0 || out_w <= 0) return 0;
+    {
+        int rc = 0;
+        if (cagc_tc_fir_nhwc(stream, in, fir, out_scale, noise, noise_w, bias, out, B, in_h, in_w, out_h, out_w, pitch,
+                             valid, pad_x0, pad_y0, noise_bstride, act, &rc))
+            return rc;
+    }
     CAGC_REQUIRE(B <= 65535, "fir_nhwc: batch too large");
     constexpr int TR = 8;
     dim3 grid(ceil_div(out_w * (pitch / 4), 256), ceil_div(out_h, TR), B);
