@@ -26,6 +26,9 @@ for p in (PKG, ROOT):
     if p not in sys.path:
         sys.path.insert(0, p)
 
+if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
+    os.environ['NCCL_DEBUG'] = 'WARN'      # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+
 import torch  # noqa: E402
 
 STUDENT_SHAPES = {256: [154] * 10 + [77, 77, 39, 39],

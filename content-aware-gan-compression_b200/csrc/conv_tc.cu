@@ -16,6 +16,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "conv_params.cuh"
 
@@ -26,8 +27,9 @@ constexpr int kThreads = 192;
 constexpr int kTileM = 128;
 constexpr int kChunkK = 32;                      // fp32 elements per 128-byte swizzle row
 constexpr int kABytes = kTileM * kChunkK * 4;    // 16 KB
-constexpr int kMaxStages = 6;
+constexpr int kMaxStages = 8;
 constexpr int kSmemBudget = 110 * 1024;          // two CTAs per SM
+constexpr int kSmemBudget1 = 220 * 1024;         // one CTA per SM (two M sub-tiles, > 256 TMEM columns)
 
 struct TcParams {
     const float* out_scale;
@@ -45,6 +47,7 @@ struct TcParams {
     int Hout, Wout, out_stride, out_oy, out_ox;
     int64_t noise_bstride;
     int act, ntaps, stages, in_stride;
+    int mt, tiles_total;        // M sub-tiles (128 pixels each) per CTA sharing one weight tile; number of pixel tiles
     uint32_t b_bytes;           // bytes of one B stage
     Tap taps[kMaxTaps];
 };
@@ -141,29 +144,38 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int S = p.stages;
-    const uint32_t stage_bytes = kABytes + p.b_bytes;
-    auto a_addr = [&](int s) { return smem_base + (uint32_t)s * stage_bytes; };
-    auto b_addr = [&](int s) { return smem_base + (uint32_t)s * stage_bytes + kABytes; };
+    const int MT = p.mt;
+    const uint32_t stage_bytes = (uint32_t)MT * kABytes + p.b_bytes;
+    auto a_addr = [&](int s, int j) { return smem_base + (uint32_t)s * stage_bytes + (uint32_t)j * kABytes; };
+    auto b_addr = [&](int s) { return smem_base + (uint32_t)s * stage_bytes + (uint32_t)MT * kABytes; };
     const uint32_t bar0 = smem_u32(bars);
     auto full_bar = [&](int s) { return bar0 + 8u * s; };
     auto empty_bar = [&](int s) { return bar0 + 8u * (kMaxStages + s); };
     const uint32_t acc_bar = bar0 + 8u * (2 * kMaxStages);
 
-    // ---- tile coordinates
-    int t = blockIdx.x;
-    const int tx = t % p.tiles_x;
-    t /= p.tiles_x;
-    const int ty = t % p.tiles_y;
-    const int tb = t / p.tiles_y;
-    const int x0 = tx * p.bw, y0 = ty * p.bh, b0 = tb * p.bb;
-    const int n0 = blockIdx.y * 256;
+    // ---- tile coordinates of the (up to two) 128-pixel sub-tiles; a sub-tile past the end is parked
+    // at batch index B (fully out of bounds: TMA zero-fills, the epilogue stores nothing)
+    int x0s[2], y0s[2], b0s[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        int t = blockIdx.x * MT + j;
+        if (j < MT && t < p.tiles_total) {
+            x0s[j] = (t % p.tiles_x) * p.bw;
+            t /= p.tiles_x;
+            y0s[j] = (t % p.tiles_y) * p.bh;
+            b0s[j] = (t / p.tiles_y) * p.bb;
+        } else {
+            x0s[j] = 0; y0s[j] = 0; b0s[j] = p.B;
+        }
+    }
+    const int n0 = blockIdx.y * p.n_tile;
     int n_mma = p.n_tile;
     {
         const int rem = ((p.n_pitch - n0) + 15) & ~15;
         if (rem < n_mma) n_mma = rem;
     }
     uint32_t tmem_cols = 32;
-    while ((int)tmem_cols < n_mma) tmem_cols <<= 1;
+    while ((int)tmem_cols < MT * n_mma) tmem_cols <<= 1;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
@@ -197,8 +209,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 const int tap = it / nk, kc = it - tap * nk;
                 const Tap tp = p.taps[tap];
                 mbar_expect_tx(full_bar(s), stage_bytes);
-                tma_load_4d(a_addr(s), &map_a, full_bar(s), kc * kChunkK, x0 * p.in_stride + tp.dx,
-                            y0 * p.in_stride + tp.dy, b0);
+                for (int j = 0; j < MT; ++j)
+                    tma_load_4d(a_addr(s, j), &map_a, full_bar(s), kc * kChunkK, x0s[j] * p.in_stride + tp.dx,
+                                y0s[j] * p.in_stride + tp.dy, b0s[j]);
                 tma_load_3d(b_addr(s), &map_b, full_bar(s), kc * kChunkK, n0, tp.slab);
             }
         }
@@ -216,12 +229,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 const int kc = it % nk;
                 int kk = (p.k_valid - kc * kChunkK + 7) >> 3;   // 8-wide tf32 MMAs with real data
                 if (kk > 4) kk = 4;
-                const uint64_t ad = make_desc_sw128(a_addr(s));
                 const uint64_t bd = make_desc_sw128(b_addr(s));
-                for (int k = 0; k < kk; ++k) {
-                    // advance 8 tf32 = 32 bytes along K inside the swizzle row: +2 in 16-byte units
-                    tc_mma_tf32(tmem_acc, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc,
-                                (it > 0 || k > 0) ? 1u : 0u);
+                for (int j = 0; j < MT; ++j) {
+                    const uint64_t ad = make_desc_sw128(a_addr(s, j));
+                    for (int k = 0; k < kk; ++k) {
+                        // advance 8 tf32 = 32 bytes along K inside the swizzle row: +2 in 16-byte units
+                        tc_mma_tf32(tmem_acc + (uint32_t)(j * n_mma), ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k),
+                                    idesc, (it > 0 || k > 0) ? 1u : 0u);
+                    }
                 }
                 tc_commit(empty_bar(s));   // frees the smem stage once these MMAs have read it
             }
@@ -234,7 +249,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int lx = m % p.bw;
         const int ly = (m / p.bw) % p.bh;
         const int lb = m / (p.bw * p.bh);
-        const int ox = x0 + lx, oy = y0 + ly, b = b0 + lb;
+        mbar_wait(acc_bar, 0);
+        tc_fence_after();
+      for (int j = 0; j < MT; ++j) {
+        const int ox = x0s[j] + lx, oy = y0s[j] + ly, b = b0s[j] + lb;
         const bool pvalid = (ox < p.Wo) && (oy < p.Ho) && (b < p.B);
         const int yy = oy * p.out_stride + p.out_oy, xx = ox * p.out_stride + p.out_ox;
         float nz = 0.f;
@@ -242,12 +260,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             nz = __ldg(p.noise_w) * __ldg(p.noise + (int64_t)b * p.noise_bstride + (int64_t)yy * p.Wout + xx);
         float* dst = p.out + (((int64_t)b * p.Hout + yy) * p.Wout + xx) * p.n_pitch;
         const float* sc = p.out_scale ? p.out_scale + (int64_t)b * p.n_pitch : nullptr;
-
-        mbar_wait(acc_bar, 0);
-        tc_fence_after();
         for (int c = 0; c < n_mma; c += 16) {
             float v[16];
-            tc_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);   // warp-collective
+            tc_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * n_mma + c), v);   // warp-collective
             if (!pvalid) continue;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
@@ -273,6 +288,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 st4(dst + n, make_float4(o[0], o[1], o[2], o[3]));
             }
         }
+      }
     }
 
     tc_fence_before();
@@ -402,6 +418,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     if (warp == 0) {
         if (lane == 0) {
             const int dya = p.dya[tap], dxa = p.dxa[tap], dyg = p.dyg[tap], dxg = p.dxg[tap];
+            const int a_boxes = min(4, (p.a_pitch - i0 + 31) / 32);
             for (int it = 0; it < total; ++it) {
                 const int s = it % S;
                 const uint32_t ph = (uint32_t)(it / S) & 1u;
@@ -412,9 +429,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 const int ty = t % p.tiles_y;
                 const int tb = t / p.tiles_y;
                 const int x0 = tx * p.bw, y0 = ty * p.bh, b0 = tb * p.bb;
-                mbar_expect_tx(full_bar(s), stage_bytes);
-#pragma unroll
-                for (int c = 0; c < 4; ++c)
+                // only the 32-channel boxes that hold real input channels are loaded; accumulator rows fed
+                // from the untouched shared memory are never stored
+                mbar_expect_tx(full_bar(s), (uint32_t)(a_boxes + p.b_boxes) * kBoxBytes);
+                for (int c = 0; c < a_boxes; ++c)
                     tma_load_4d(a_addr(s) + c * kBoxBytes, &map_a, full_bar(s), i0 + 32 * c, x0 + dxa, y0 + dya, b0);
                 for (int c = 0; c < p.b_boxes; ++c)
                     tma_load_4d(b_addr(s) + c * kBoxBytes, &map_g, full_bar(s), 32 * c, x0 * p.g_stride + dxg,
@@ -611,12 +629,35 @@ int cagc_tc_conv(cudaStream_t stream, const ConvP& c, const char* what) {
     p.n_pitch = c.n_cols; p.out_valid = c.out_valid;
     p.n_rows = (c.n_cols + 15) & ~15;
     p.n_tile = std::min(256, p.n_rows);
+    p.tiles_total = p.tiles_x * p.tiles_y * tiles_b;
+    // Tile-shape heuristic (measured per layer on B200, scripts/layer_times.py):
+    //  * plenty of pixel tiles, N tile <= 128: two 128-pixel sub-tiles per CTA share each weight tile (the kernel
+    //    is bound by L2->SMEM operand traffic there; +20..27%);
+    //  * plenty of pixel tiles, N tile > 128: one sub-tile, two CTAs per SM (epilogue overlap matters more);
+    //  * few pixel tiles (4x4 .. 16x16 layers): narrower N tiles -> more CTAs and a deeper TMA pipeline per CTA
+    //    (those layers are bound by the serial K loop's load latency).
+    p.mt = 1;
+    if ((int64_t)p.tiles_total * ceil_div(p.n_rows, p.n_tile) >= 4 * kNumSMs) {
+        if (p.n_tile <= 128) p.mt = 2;
+    } else {
+        while (p.n_tile > 32 && (int64_t)p.tiles_total * ceil_div(p.n_rows, p.n_tile) < kNumSMs) {
+            int nt = (p.n_tile / 2 + 15) & ~15;
+            if (nt < 32) nt = 32;
+            p.n_tile = nt;
+        }
+    }
     p.Hout = c.Hout; p.Wout = c.Wout; p.out_stride = c.out_stride; p.out_oy = c.out_oy; p.out_ox = c.out_ox;
     p.noise_bstride = c.noise_bstride; p.act = c.act; p.ntaps = c.ntaps; p.in_stride = c.in_stride;
     for (int i = 0; i < c.ntaps; ++i) p.taps[i] = c.taps[i];
     p.b_bytes = (uint32_t)p.n_tile * kChunkK * 4;
-    const uint32_t stage_bytes = kABytes + p.b_bytes;
-    p.stages = std::max(2, std::min(kMaxStages, (int)((kSmemBudget - 1024) / stage_bytes)));
+    if (const char* e = getenv("CAGC_TC_MT")) p.mt = (atoi(e) == 2 && p.tiles_total >= 2) ? 2 : 1;   // tuning knob
+    if (const char* e = getenv("CAGC_TC_NTILE")) p.n_tile = std::min(p.n_tile, std::max(32, atoi(e) & ~15));
+    p.b_bytes = (uint32_t)p.n_tile * kChunkK * 4;
+    const uint32_t stage_bytes = (uint32_t)p.mt * kABytes + p.b_bytes;
+    int tmem_need = 32;
+    while (tmem_need < p.mt * p.n_tile) tmem_need <<= 1;
+    const int budget = (tmem_need <= 256 && 2 * stage_bytes + 1024 <= (uint32_t)kSmemBudget) ? kSmemBudget : kSmemBudget1;
+    p.stages = std::max(2, std::min(kMaxStages, (int)((budget - 1024) / stage_bytes)));
     const size_t smem = (size_t)p.stages * stage_bytes + 1024;
 
     // A: activations [B, Hin, Win, in_pitch] fp32, box (32 ch, bw, bh, bb), 128-byte swizzle, OOB -> 0
@@ -651,13 +692,13 @@ int cagc_tc_conv(cudaStream_t stream, const ConvP& c, const char* what) {
     }
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget1);
         if (e != cudaSuccess) return fail((int)e, "%s: cudaFuncSetAttribute failed: %s", what, cudaGetErrorString(e));
         attr_set = true;
     }
-    const int64_t gx = (int64_t)p.tiles_x * p.tiles_y * tiles_b;
+    const int64_t gx = ceil_div<int64_t>(p.tiles_total, p.mt);
     CAGC_REQUIRE(gx <= 0x7fffffffLL, "%s: too many tiles", what);
-    dim3 grid((unsigned)gx, ceil_div(p.n_rows, 256));
+    dim3 grid((unsigned)gx, ceil_div(p.n_rows, p.n_tile));
     conv_tc_kernel<<<grid, kThreads, smem, stream>>>(map_a, map_b, p);
     return launched(what);
 }
