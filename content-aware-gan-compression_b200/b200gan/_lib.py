@@ -15,7 +15,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), 'lib', 'libcagc_b200.so')
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 _p = C.c_void_p
 _i = C.c_int
@@ -32,6 +32,8 @@ SIGNATURES = {
     'cagc_fused_bias_act': (_i, [_p, _p, _p, _p, _p, _l, _l, _i, _i, _i, _f, _f]),
     'cagc_bias_grad_chunks': (_i, [_l]),
     'cagc_fused_bias_act_bwd': (_i, [_p, _p, _p, _p, _p, _l, _i, _l, _f, _f]),
+    'cagc_bias_grad_rows_chunks': (_i, [_l, _i]),
+    'cagc_fused_bias_act_bwd_rows': (_i, [_p, _p, _p, _p, _p, _l, _i, _f, _f]),
     'cagc_conv_same': (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _l, _i, _i]),
     'cagc_modulate': (_i, [_p, _p, _p, _p, _i, _i, _i, _i]),
     'cagc_conv_up': (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i]),

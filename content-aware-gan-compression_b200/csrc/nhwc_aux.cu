@@ -359,6 +359,42 @@ __global__ void __launch_bounds__(256) torgb_bwd_kernel(const float* __restrict_
     }
 }
 
+
+// fused leaky-ReLU backward on channel-contiguous storage [rows][C] (channels-last activations, 2-D
+// [B, C] tensors) with the bias gradient reduced in the same pass: block = (C/4, PY) threads
+__global__ void __launch_bounds__(256) bias_act_bwd_rows_kernel(const float* __restrict__ g, const float* __restrict__ refer,
+                                                                float* __restrict__ gin, float* __restrict__ partial,
+                                                                int64_t rows, int C, int chunks, float alpha, float scale) {
+    extern __shared__ float4 red[];  // [PY][c4n]
+    const int c4n = blockDim.x, PY = blockDim.y;
+    const int cx = threadIdx.x, py = threadIdx.y, c = cx * 4;
+    const int chunk = blockIdx.x;
+    const int64_t per = ceil_div<int64_t>(rows, chunks);
+    const int64_t r_lo = chunk * per, r_hi = min(rows, r_lo + per);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t r = r_lo + py; r < r_hi; r += PY) {
+        const int64_t off = r * C + c;
+        const float4 gv = ld4(g + off), rv = ld4(refer + off);
+        float4 o;
+        o.x = (rv.x > 0.f ? gv.x : gv.x * alpha) * scale;
+        o.y = (rv.y > 0.f ? gv.y : gv.y * alpha) * scale;
+        o.z = (rv.z > 0.f ? gv.z : gv.z * alpha) * scale;
+        o.w = (rv.w > 0.f ? gv.w : gv.w * alpha) * scale;
+        st4(gin + off, o);
+        acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+    }
+    red[py * c4n + cx] = acc;
+    __syncthreads();
+    if (py == 0) {
+        float4 t = red[cx];
+        for (int k = 1; k < PY; ++k) {
+            const float4 v = red[k * c4n + cx];
+            t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+        }
+        st4(partial + (int64_t)chunk * C + c, t);
+    }
+}
+
 static inline int pixel_chunks(int HW) {
     int c = ceil_div(HW, HW >= 16384 ? kChunkPixels : 256);
     if (c < 1) c = 1;
@@ -409,6 +445,29 @@ int cagc_fir_nhwc(cagc_stream_t stream_, const float* in, const float* fir, cons
 }
 
 int cagc_act_bwd_chunks(int H, int W) { return pixel_chunks(H * W); }
+
+int cagc_bias_grad_rows_chunks(int64_t rows, int C) {
+    if (C % 4 != 0 || C > 1024 || rows < 64) return 0;   // caller reduces grad_in itself
+    int64_t c = ceil_div<int64_t>(rows, 512);
+    if (c > 4 * kNumSMs) c = 4 * kNumSMs;
+    return (int)c;
+}
+
+int cagc_fused_bias_act_bwd_rows(cagc_stream_t stream_, const float* grad_out, const float* refer, float* grad_in,
+                                 float* bias_partial, int64_t rows, int C, float alpha, float scale) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CAGC_REQUIRE(grad_out && refer && grad_in && bias_partial, "fused_bias_act_bwd_rows: null pointer");
+    const int chunks = cagc_bias_grad_rows_chunks(rows, C);
+    CAGC_REQUIRE(chunks > 0, "fused_bias_act_bwd_rows: shape not eligible for the fused reduction");
+    CAGC_REQUIRE(aligned16(grad_out) && aligned16(refer) && aligned16(grad_in) && aligned16(bias_partial),
+                 "fused_bias_act_bwd_rows: pointers must be 16-byte aligned");
+    dim3 blk;
+    CAGC_REQUIRE(block_shape(C, 1, &blk) == 0, "fused_bias_act_bwd_rows: C %d unsupported", C);
+    bias_act_bwd_rows_kernel<<<chunks, blk, sizeof(float4) * blk.x * blk.y, stream>>>(grad_out, refer, grad_in,
+                                                                                  bias_partial, rows, C, chunks, alpha,
+                                                                                  scale);
+    return launched("bias_act_bwd_rows_kernel");
+}
 
 int cagc_act_bwd(cagc_stream_t stream_, const float* ga, int64_t sb, int64_t sc, int64_t sh, int64_t sw, const float* a,
                  const float* d, const float* noise, const float* noise_w, const float* bias, float* gu, float* partial,

@@ -47,6 +47,15 @@ class _FusedLeakyReLUBackward(Function):
                 else grad_output.contiguous()
         else:
             g = grad_output.contiguous()
+        rows_chunks = lib.cagc_bias_grad_rows_chunks(g.numel() // size_b, size_b) if (has_bias and step_b == 1) else 0
+        if rows_chunks > 0 and g.numel() > 0:
+            grad_input = torch.empty_like(g)
+            partial = torch.empty((rows_chunks, size_b), device=g.device, dtype=g.dtype)
+            with torch.cuda.device(g.device):
+                check(lib.cagc_fused_bias_act_bwd_rows(stream_of(g), g.data_ptr(), out.data_ptr(), grad_input.data_ptr(),
+                                                       partial.data_ptr(), g.numel() // size_b, size_b, negative_slope,
+                                                       scale), 'fused_bias_act_bwd_rows')
+            return grad_input, partial.sum(dim=0)
         chunks = lib.cagc_bias_grad_chunks(step_b) if has_bias else 0
         if chunks > 0 and g.numel() > 0 and (g.numel() // step_b) <= 65535:
             grad_input = torch.empty_like(g)

@@ -37,7 +37,7 @@ typedef void* cagc_stream_t; /* cudaStream_t */
 #define CAGC_E_UNSUPPORTED (-2) /* shape outside what the kernels implement */
 
 /* bump when a signature changes; the Python loader checks it */
-#define CAGC_ABI_VERSION 9
+#define CAGC_ABI_VERSION 10
 
 int cagc_abi_version(void);
 const char* cagc_last_error(void);
@@ -80,6 +80,12 @@ int cagc_bias_grad_chunks(int64_t step_b);
 int cagc_fused_bias_act_bwd(cagc_stream_t stream, const float* grad_out, const float* refer, float* grad_in,
                             float* bias_partial, int64_t outer, int size_b, int64_t step_b,
                             float alpha, float scale);
+
+/* Same for channel-contiguous storage [rows][C] (channels-last 4-D tensors, 2-D [B, C] tensors):
+ * bias_partial is [chunks][C], chunks = cagc_bias_grad_rows_chunks(rows, C) (0 = not eligible). */
+int cagc_bias_grad_rows_chunks(int64_t rows, int C);
+int cagc_fused_bias_act_bwd_rows(cagc_stream_t stream, const float* grad_out, const float* refer, float* grad_in,
+                                 float* bias_partial, int64_t rows, int C, float alpha, float scale);
 
 /* ------------------------------------------------------------------------
  * Modulated convolution (model.py:241-289), fused form of SURVEY.md App. B.
