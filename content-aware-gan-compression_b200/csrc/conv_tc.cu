@@ -298,6 +298,209 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
 }
 
+
+// ================================================================================================
+// Persistent variant: one CTA per SM loops over (n-tile, pixel super-tile) work items; the TMEM
+// accumulator is double buffered, so the four epilogue warps drain tile i while the MMA warp already
+// accumulates tile i+1 and the TMA warp runs further ahead through a deep (up to 8-stage, ~200 KB)
+// shared-memory ring.  TMEM allocation, barrier setup and tensor-map fetch are paid once per SM, which
+// is what the narrow, HBM-bound student layers (K = 9 taps x 2 chunks) were dominated by.
+// ================================================================================================
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                       const TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 4];
+    __shared__ uint32_t tmem_base_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int S = p.stages, MT = p.mt;
+    const uint32_t stage_bytes = (uint32_t)MT * kABytes + p.b_bytes;
+    auto a_addr = [&](int s, int j) { return smem_base + (uint32_t)s * stage_bytes + (uint32_t)j * kABytes; };
+    auto b_addr = [&](int s) { return smem_base + (uint32_t)s * stage_bytes + (uint32_t)MT * kABytes; };
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (kMaxStages + s); };
+    auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * kMaxStages + a); };
+    auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * kMaxStages + 2 + a); };
+
+    const int acc_stride = MT * p.n_tile;           // TMEM columns per accumulator buffer
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < 2 * acc_stride) tmem_cols <<= 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), 4);            // one arrival per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                     "r"(tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_acc = tmem_base_slot;
+
+    const int nk = (p.k_valid + kChunkK - 1) / kChunkK;
+    const int per_item = p.ntaps * nk;
+    const int m_super = (p.tiles_total + MT - 1) / MT;
+    const int n_tiles = (p.n_rows + p.n_tile - 1) / p.n_tile;
+    const int items = m_super * n_tiles;
+
+    // sub-tile coordinates of work item `item`
+    auto decode = [&](int item, int* x0s, int* y0s, int* b0s, int& n0, int& n_mma) {
+        const int n_idx = item / m_super, m_idx = item - n_idx * m_super;
+        n0 = n_idx * p.n_tile;
+        n_mma = p.n_tile;
+        const int rem = ((p.n_pitch - n0) + 15) & ~15;
+        if (rem < n_mma) n_mma = rem;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            int t = m_idx * MT + j;
+            if (j < MT && t < p.tiles_total) {
+                x0s[j] = (t % p.tiles_x) * p.bw;
+                t /= p.tiles_x;
+                y0s[j] = (t % p.tiles_y) * p.bh;
+                b0s[j] = (t / p.tiles_y) * p.bb;
+            } else {
+                x0s[j] = 0; y0s[j] = 0; b0s[j] = p.B;
+            }
+        }
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int item = blockIdx.x; item < items; item += gridDim.x) {
+                int x0s[2], y0s[2], b0s[2], n0, n_mma;
+                decode(item, x0s, y0s, b0s, n0, n_mma);
+                for (int it = 0; it < per_item; ++it) {
+                    mbar_wait(empty_bar(s), ph ^ 1u);
+                    const int tap = it / nk, kc = it - tap * nk;
+                    const Tap tp = p.taps[tap];
+                    mbar_expect_tx(full_bar(s), stage_bytes);
+                    for (int j = 0; j < MT; ++j)
+                        tma_load_4d(a_addr(s, j), &map_a, full_bar(s), kc * kChunkK, x0s[j] * p.in_stride + tp.dx,
+                                    y0s[j] * p.in_stride + tp.dy, b0s[j]);
+                    tma_load_3d(b_addr(s), &map_b, full_bar(s), kc * kChunkK, n0, tp.slab);
+                    if (++s == S) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int s = 0, acc = 0;
+            uint32_t ph = 0, aph = 0;
+            for (int item = blockIdx.x; item < items; item += gridDim.x) {
+                int x0s[2], y0s[2], b0s[2], n0, n_mma;
+                decode(item, x0s, y0s, b0s, n0, n_mma);
+                const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n_mma >> 3) << 17) |
+                                       ((uint32_t)(kTileM >> 4) << 24);
+                mbar_wait(tempty_bar(acc), aph ^ 1u);        // epilogue has drained this accumulator buffer
+                tc_fence_after();
+                const uint32_t d0 = tmem_acc + (uint32_t)(acc * acc_stride);
+                for (int it = 0; it < per_item; ++it) {
+                    mbar_wait(full_bar(s), ph);
+                    tc_fence_after();
+                    const int kc = it % nk;
+                    int kk = (p.k_valid - kc * kChunkK + 7) >> 3;
+                    if (kk > 4) kk = 4;
+                    const uint64_t bd = make_desc_sw128(b_addr(s));
+                    for (int j = 0; j < MT; ++j) {
+                        const uint64_t ad = make_desc_sw128(a_addr(s, j));
+                        for (int k = 0; k < kk; ++k)
+                            tc_mma_tf32(d0 + (uint32_t)(j * p.n_tile), ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc,
+                                        (it > 0 || k > 0) ? 1u : 0u);
+                    }
+                    tc_commit(empty_bar(s));
+                    if (++s == S) { s = 0; ph ^= 1u; }
+                }
+                tc_commit(tfull_bar(acc));
+                if (++acc == 2) { acc = 0; aph ^= 1u; }
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int m = q * 32 + lane;
+        const int lx = m % p.bw;
+        const int ly = (m / p.bw) % p.bh;
+        const int lb = m / (p.bw * p.bh);
+        const float nwv = p.noise ? __ldg(p.noise_w) : 0.f;
+        int acc = 0;
+        uint32_t aph = 0;
+        for (int item = blockIdx.x; item < items; item += gridDim.x) {
+            int x0s[2], y0s[2], b0s[2], n0, n_mma;
+            decode(item, x0s, y0s, b0s, n0, n_mma);
+            mbar_wait(tfull_bar(acc), aph);
+            tc_fence_after();
+            const uint32_t d0 = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * acc_stride);
+            for (int j = 0; j < MT; ++j) {
+                const int ox = x0s[j] + lx, oy = y0s[j] + ly, b = b0s[j] + lb;
+                const bool pvalid = (ox < p.Wo) && (oy < p.Ho) && (b < p.B);
+                const int yy = oy * p.out_stride + p.out_oy, xx = ox * p.out_stride + p.out_ox;
+                float nz = 0.f;
+                if (p.noise && pvalid) nz = nwv * __ldg(p.noise + (int64_t)b * p.noise_bstride + (int64_t)yy * p.Wout + xx);
+                float* dst = p.out + (((int64_t)b * p.Hout + yy) * p.Wout + xx) * p.n_pitch;
+                const float* sc = p.out_scale ? p.out_scale + (int64_t)b * p.n_pitch : nullptr;
+                for (int c = 0; c < n_mma; c += 16) {
+                    float v[16];
+                    tc_ld16(d0 + (uint32_t)(j * p.n_tile + c), v);
+                    if (!pvalid) continue;
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const int n = n0 + c + g * 4;
+                        if (n >= p.n_pitch) break;
+                        float o[4] = {v[g * 4 + 0], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]};
+                        if (sc) {
+                            const float4 s4 = ldg4(sc + n);
+                            o[0] *= s4.x; o[1] *= s4.y; o[2] *= s4.z; o[3] *= s4.w;
+                        }
+                        if (p.noise) { o[0] += nz; o[1] += nz; o[2] += nz; o[3] += nz; }
+                        if (p.bias) {
+                            const float4 b4 = ldg4(p.bias + n);
+                            o[0] += b4.x; o[1] += b4.y; o[2] += b4.z; o[3] += b4.w;
+                        }
+                        if (p.act) {
+#pragma unroll
+                            for (int jj = 0; jj < 4; ++jj) o[jj] = lrelu_sqrt2(o[jj]);
+                        }
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj)
+                            if (n + jj >= p.out_valid) o[jj] = 0.f;
+                        st4(dst + n, make_float4(o[0], o[1], o[2], o[3]));
+                    }
+                }
+            }
+            // this warp has finished reading the accumulator buffer: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (++acc == 2) { acc = 0; aph ^= 1u; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(tmem_cols) : "memory");
+    }
+}
+
 // elementwise x~ = round_tf32(x * s[b, c])  (s == nullptr: plain rounding); NHWC-p, float4
 __global__ void __launch_bounds__(256) modulate_kernel(const float* __restrict__ x, const float* __restrict__ s,
                                                        float* __restrict__ out, int64_t n4, int64_t per_sample4,
@@ -693,8 +896,24 @@ int cagc_tc_conv(cudaStream_t stream, const ConvP& c, const char* what) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget1);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(conv_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget1);
         if (e != cudaSuccess) return fail((int)e, "%s: cudaFuncSetAttribute failed: %s", what, cudaGetErrorString(e));
         attr_set = true;
+    }
+    // persistent form: whenever a double-buffered accumulator fits in TMEM (MT * n_tile <= 256 columns)
+    static const int persist_env = [] { const char* e = getenv("CAGC_TC_PERSIST"); return e ? atoi(e) : 1; }();
+    // (measured: +9% on the large teacher layers; with fewer than ~6 work items per SM the static
+    // round-robin schedule loses more to wave imbalance than the overlap gains)
+    const int64_t items = ceil_div<int64_t>(p.tiles_total, p.mt) * ceil_div(p.n_rows, p.n_tile);
+    if (persist_env && p.mt * p.n_tile <= 256 && (items >= 6 * kNumSMs || persist_env == 2)) {
+        TcParams q = p;
+        const uint32_t sb = (uint32_t)q.mt * kABytes + q.b_bytes;
+        q.stages = std::max(2, std::min(kMaxStages, (int)((kSmemBudget1 - 1024) / sb)));
+        const size_t smem_p = (size_t)q.stages * sb + 1024;
+        const unsigned gridp = (unsigned)std::min<int64_t>(items, kNumSMs);
+        conv_tc_persist_kernel<<<gridp, kThreads, smem_p, stream>>>(map_a, map_b, q);
+        return launched(what);
     }
     const int64_t gx = ceil_div<int64_t>(p.tiles_total, p.mt);
     CAGC_REQUIRE(gx <= 0x7fffffffLL, "%s: too many tiles", what);

@@ -105,7 +105,8 @@ class EqualConv2d(nn.Module):
         self.bias = nn.Parameter(torch.zeros(out_channel)) if bias else None
 
     def forward(self, input):
-        return F.conv2d(input, self.weight * self.scale, bias=self.bias, stride=self.stride, padding=self.padding)
+        w = _mc.cached_frozen(self.weight, ('eqconv', self.scale), lambda: self.weight * self.scale)
+        return F.conv2d(input, w, bias=self.bias, stride=self.stride, padding=self.padding)
 
     def __repr__(self):
         o, i, k, _ = self.weight.shape
