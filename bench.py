@@ -307,8 +307,17 @@ def main():
         # TF32 tensor peak = half the measured bf16 peak (same pipe, half the rate); fp32 SIMT kernels are
         # reported against the same tensor-pipe number so the fraction shows the distance to the target
         peak = peaks['bf16_tflops_sustained'] / 2
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, 'profiles', 'r1_traffic.json')
+        if tf32 and os.path.exists(tpath):
+            tj = json.load(open(tpath)).get('conv_tc_family')
+            if tj:
+                traffic, traffic_src = tj['dram_bytes_per_launch'], tj['source']
         roofline = {'kernel': dom, 'bound': 'tensor', 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s',
-                    'frac': ach / peak, 'traffic': None,
+                    'frac': ach / peak, 'traffic': traffic, 'traffic_source': traffic_src,
+                    'algorithmic_bytes_per_launch': r['bytes'] / max(r['launches'], 1),
+                    'algorithmic_flops_per_launch': r['flops'] / max(r['launches'], 1),
+                    'avg_launch_us': r['ms'] / max(r['launches'], 1) * 1e3,
                     'peak_source': f"{peaks['source']} bf16 sustained {peaks['bf16_tflops_sustained']} TF/s / 2 (TF32)",
                     'precision': 'tf32 tcgen05' if tf32 else 'fp32 SIMT (no tensor pipe)'}
     hbm = {}

@@ -38,21 +38,34 @@ lst = os.path.join(P, f'{tag}_launches_kdstep.csv')
 if os.path.exists(lst):
     rows = csv.DictReader([l for l in open(lst) if not l.startswith('==')])
     agg = collections.defaultdict(lambda: [0, 0.0])
+    dram = collections.defaultdict(float)
     tot = 0.0
     for row in rows:
+        n = row['Kernel Name'].replace('void ', '')[:72]
         try:
-            t = us(row)
+            if row.get('Metric Name', 'gpu__time_duration.sum') == 'gpu__time_duration.sum':
+                t = us(row)
+                agg[n][0] += 1
+                agg[n][1] += t
+                tot += t
+            elif row['Metric Name'].startswith('dram__bytes'):
+                mult = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}.get(row['Metric Unit'], 1)
+                dram[n] += float(row['Metric Value'].replace(',', '')) * mult
         except (ValueError, KeyError):
             continue
-        n = row['Kernel Name'].replace('void ', '')[:72]
-        agg[n][0] += 1
-        agg[n][1] += t
-        tot += t
+    if dram:
+        fam = [k for k in agg if 'conv_tc' in k]
+        traffic = {'conv_tc_family': {'launches': sum(agg[k][0] for k in fam),
+                                      'dram_bytes_per_launch': sum(dram[k] for k in fam) / max(1, sum(agg[k][0] for k in fam)),
+                                      'source': f'{tag}_launches_kdstep.csv (ncu dram__bytes_read.sum + dram__bytes_write.sum, one KD step)'}}
+        for k in agg:
+            traffic[k.split('(')[0]] = {'launches': agg[k][0], 'dram_bytes_per_launch': dram[k] / agg[k][0]}
+        json.dump(traffic, open(os.path.join(P, f'{tag}_traffic.json'), 'w'), indent=1)
     out.append(f'\n## ncu launch list of one KD step (`--metrics gpu__time_duration.sum --clock-control none`, '
                f'cold-cache serialised: compare shares)\n\ntotal {tot / 1e3:.2f} ms over {sum(a[0] for a in agg.values())} launches\n')
-    out.append('| kernel | launches | us | share |\n|---|---|---|---|')
+    out.append('| kernel | launches | us | share | DRAM MB |\n|---|---|---|---|---|')
     for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:25]:
-        out.append(f'| `{k}` | {n} | {t:.0f} | {100 * t / tot:.1f}% |')
+        out.append(f'| `{k}` | {n} | {t:.0f} | {100 * t / tot:.1f}% | {dram.get(k, 0) / 1e6:.0f} |')
 
 raw = os.path.join(P, f'{tag}_ncu_full_layers_raw.csv')
 if os.path.exists(raw):
