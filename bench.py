@@ -256,11 +256,12 @@ def main():
 
     # ---------------- generator slice alone (student f+b, teacher f) for the Amdahl picture
     def slice_step(z):
-        kd.bucket.zero_grad()
+        kd.bucket.detach_grads()
         fake = student(z, return_rgb_list=True, inject_index=inject)
         with torch.no_grad():
             real = teacher(z, return_rgb_list=True, inject_index=inject)
         (3.0 * (real[-1] - fake[-1]).abs().mean()).backward()
+        kd.bucket.pack_grads()
     zs = fresh_latents()
     side = torch.cuda.Stream(device=dev)
     side.wait_stream(torch.cuda.current_stream(dev))

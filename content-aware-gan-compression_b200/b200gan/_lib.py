@@ -15,7 +15,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), 'lib', 'libcagc_b200.so')
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 _p = C.c_void_p
 _i = C.c_int
@@ -40,6 +40,18 @@ SIGNATURES = {
     'cagc_conv_up_dgrad': (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i]),
     'cagc_conv_wgrad_splits': (_i, [_i, _i, _i, _i, _i, _i, _i]),
     'cagc_conv_wgrad': (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i]),
+    'cagc_conv_wgrad_partial': (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, C.POINTER(C.c_int)]),
+    'cagc_weight_prep': (_i, [_p, _p, _f, _i, _i, _i, _p, _i, _i, _i, _p, _i, _i, _i, _i, _p, _p, _i, _i, _p, _p, _i, _i]),
+    'cagc_style_affine': (_i, [_p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _l, _l, _i, _i, _i]),
+    'cagc_style_affine_bwd': (_i, [_p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _l, _l, _p, _i, _i, _i]),
+    'cagc_demod': (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _f]),
+    'cagc_act_bwd_finalize_blocks': (_i, [_i]),
+    'cagc_act_bwd_finalize': (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i]),
+    'cagc_style_grad_finalize': (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i]),
+    'cagc_wgrad_finalize': (_i, [_p, _p, _i, _p, _f, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    'cagc_torgb_bwd_finalize': (_i, [_p, _p, _p, _p, _f, _p, _p, _i, _i, _i, _i, _i]),
+    'cagc_linear_bias_act': (_i, [_p, _p, _p, _p, _i, _i, _f, _f, _i, _f, _f]),
+    'cagc_linear_bias_act_bwd': (_i, [_p, _p, _p, _p, _p, _i, _i, _f, _f, _i, _f, _f]),
     'cagc_fir_nhwc': (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _l, _i]),
     'cagc_act_bwd_chunks': (_i, [_i, _i]),
     'cagc_act_bwd': (_i, [_p, _p, _l, _l, _l, _l, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _l, _i]),

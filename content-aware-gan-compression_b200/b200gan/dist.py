@@ -109,6 +109,26 @@ class FlatBucket:
             if p.grad is None or p.grad.data_ptr() != self.flat_grad.data_ptr() + off * 4:
                 p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
 
+    # -- "detached" protocol: one multi-tensor copy per step instead of one accumulation kernel per parameter.
+    # With .grad pre-attached to the bucket autograd ADDS every gradient into its view (one tiny launch per
+    # parameter, ~135 per student step, after a 22 MB memset).  detach_grads() sets .grad = None, so backward
+    # hands each gradient tensor over without a kernel; pack_grads() then moves all of them into the bucket
+    # with a single batched copy and re-attaches the views.
+    def detach_grads(self):
+        for p in self.params:
+            p.grad = None
+
+    def pack_grads(self):
+        views = [self.flat_grad[off:off + p.numel()].view_as(p) for p, off in zip(self.params, self.offsets)]
+        have = [(v, p.grad) for v, p in zip(views, self.params)
+                if p.grad is not None and p.grad.data_ptr() != v.data_ptr()]
+        if any(p.grad is None for p in self.params):
+            self.flat_grad.zero_()           # parameters the loss did not reach keep a zero gradient
+        if have:
+            torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
+        for p, v in zip(self.params, views):
+            p.grad = v
+
     def allreduce_mean_(self, async_op: bool = False):
         """Sum the bucket over ranks (the division by world size is folded into the optimizer
         kernel's grad_scale).  Semantics of gather_grad (reference :57-66)."""

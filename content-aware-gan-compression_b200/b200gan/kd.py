@@ -52,10 +52,11 @@ class KDStep:
 
     def step(self, z: List[torch.Tensor], inject_index: int, s_noise=None, t_noise=None) -> torch.Tensor:
         """One optimisation step on device-resident latents; returns the (detached) total loss."""
-        self.bucket.zero_grad()
+        self.bucket.detach_grads()
         g_loss, kd = self.losses(z, inject_index, s_noise, t_noise)
         total = g_loss + kd
         total.backward()
+        self.bucket.pack_grads()
         self.bucket.allreduce_mean_()
         self.t_dev += 1
         b1, b2 = self.betas

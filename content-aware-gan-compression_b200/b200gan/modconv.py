@@ -14,12 +14,14 @@ rounded up to a multiple of 8 and the padding channels kept at zero, exposed to 
 """
 from __future__ import annotations
 
+import ctypes as C
 import math
 from typing import Optional
 
 import torch
 import torch.nn.functional as F
 from torch.autograd import Function
+from torch.autograd.function import once_differentiable
 
 from ._lib import lib, check, stream_of, require_cuda, ptr
 from . import config
@@ -92,68 +94,138 @@ def _pad_last(t: torch.Tensor, p: int) -> torch.Tensor:
     return F.pad(t, (0, p - t.shape[-1]))
 
 
-def _slabs(w4: torch.Tensor, rows_p: int, cols_p: int) -> torch.Tensor:
-    """[k,k,R,C] -> zero-padded contiguous [k*k, rows_p, cols_p]."""
-    k = w4.shape[0]
-    r, c = w4.shape[2], w4.shape[3]
-    w = w4.reshape(k * k, r, c)
-    if r == rows_p and c == cols_p:
-        return w.contiguous()
-    return F.pad(w, (0, cols_p - c, 0, rows_p - r)).contiguous()
-
-
-def _slabs_tc(w4: torch.Tensor, k_p: int) -> torch.Tensor:
-    """[k,k,N,K] -> K-major slabs [k*k, roundup16(pitch(N)), k_p], rounded to TF32 (tcgen05 B operand)."""
-    k = w4.shape[0]
-    n, kk = w4.shape[2], w4.shape[3]
-    n_rows = (pitch_of(n) + 15) // 16 * 16
-    w = F.pad(w4.reshape(k * k, n, kk), (0, k_p - kk, 0, n_rows - n)).contiguous()
-    check(lib.cagc_modulate(stream_of(w), w.data_ptr(), None, w.data_ptr(), 1, 1, w.numel() // 4, 4), 'round_tf32')
-    return w
-
-
 def _use_tc(algo: int, k_pitch: int) -> bool:
     """The tcgen05 kernel consumes K in 128-byte (32-channel) TMA boxes; narrower layers (a few
     channels, latency-bound anyway) stay on the SIMT engine."""
     return algo == config.ALGO_TCGEN05_TF32 and k_pitch >= 32
 
 
-class _StyledConvFn(Function):
-    """a = [lrelu]( d * conv(s*x, c*W) [+ nw*noise] [+ bias] ) on NHWC-p buffers.
+def _r16(n: int) -> int:
+    return (n + 15) // 16 * 16
 
-    Inputs: x [B,I,H,W]; s [B,I]; d [B,O] or None; weight [1,O,I,k,k]; noise [B|1,1,Ho,Wo] or None;
-    noise_w [1] or None; bias [O] or None.  Non-tensor: wscale (c), upsample, fir [4,4], pad, act.
+
+def _is_frozen(t: Optional[torch.Tensor]) -> bool:
+    return t is None or not (t.requires_grad or t.grad_fn is not None)
+
+
+class _Prep:
+    """Weight-derived operands of one modulated convolution (one cagc_weight_prep launch)."""
+    __slots__ = ('w_fwd', 'w_dgrad', 'wsq_oi', 'wsq_io', 'bias_p')
+
+
+def _weight_prep(weight, bias, wscale, upsample, tc_fwd, tc_dgrad, pin, pout, want_wsq):
+    """weight [1,O,I,k,k] -> forward / data-gradient operand slabs in the layout of the engine that
+    will consume them, Wsq in both orientations, zero-padded bias.  One launch when forward and
+    data gradient run on the same engine (the usual case), two otherwise."""
+    _, cout, cin, k, _ = weight.shape
+    dev = weight.device
+    kk = k * k
+    r = _Prep()
+    w = weight.detach()
+    if not w.is_contiguous():
+        w = w.contiguous()
+    st = stream_of(w)
+    # forward: tensor pipe wants K-major rows [t][o][i] (orientation A); SIMT wants [t][i][o] (orientation B)
+    # dgrad  : tensor pipe [t'][i][o] (B), SIMT [t'][o][i] (A); taps flipped for the same-resolution conv
+    flip_d = 0 if upsample else 1
+    f_spec = ('A', _r16(pout), pin, 0, 1) if tc_fwd else ('B', pin, pout, 0, 0)
+    d_spec = ('B', _r16(pin), pout, flip_d, 1) if tc_dgrad else ('A', pout, pin, flip_d, 0)
+    r.w_fwd = torch.empty((kk, f_spec[1], f_spec[2]), device=dev, dtype=torch.float32)
+    r.w_dgrad = torch.empty((kk, d_spec[1], d_spec[2]), device=dev, dtype=torch.float32)
+    if want_wsq:
+        r.wsq_oi = torch.empty((pout, pin), device=dev, dtype=torch.float32)
+        r.wsq_io = torch.empty((pin, pout), device=dev, dtype=torch.float32)
+    else:
+        r.wsq_oi = r.wsq_io = None
+    if bias is not None:
+        b_in = bias.detach().contiguous()
+        r.bias_p = torch.empty((pout,), device=dev, dtype=torch.float32)
+    else:
+        b_in, r.bias_p = None, None
+
+    def call(spec_a, out_a, spec_b, out_b, rnd, with_rest):
+        ra, ca, fa = (spec_a[1], spec_a[2], spec_a[3]) if spec_a else (0, 0, 0)
+        rb, cb, fb = (spec_b[1], spec_b[2], spec_b[3]) if spec_b else (0, 0, 0)
+        check(lib.cagc_weight_prep(st, w.data_ptr(), wscale, cout, cin, k,
+                                   ptr(out_a), ra, ca, fa, ptr(out_b), rb, cb, fb, rnd,
+                                   ptr(r.wsq_oi) if with_rest else None, ptr(r.wsq_io) if with_rest else None,
+                                   pout, pin, ptr(b_in) if with_rest else None,
+                                   ptr(r.bias_p) if with_rest else None, cout, pout), 'weight_prep')
+
+    if f_spec[0] != d_spec[0] and f_spec[4] == d_spec[4]:
+        a, b = (f_spec, d_spec) if f_spec[0] == 'A' else (d_spec, f_spec)
+        oa, ob = (r.w_fwd, r.w_dgrad) if f_spec[0] == 'A' else (r.w_dgrad, r.w_fwd)
+        call(a, oa, b, ob, f_spec[4], True)
+    else:
+        for spec, out, rest in ((f_spec, r.w_fwd, True), (d_spec, r.w_dgrad, False)):
+            if spec[0] == 'A':
+                call(spec, out, None, None, spec[4], rest)
+            else:
+                call(None, None, spec, out, spec[4], rest)
+    return r
+
+
+_prep_cache = {}
+
+
+def _prepared(weight, bias, wscale, upsample, tc_fwd, tc_dgrad, pin, pout, want_wsq):
+    """Frozen parameters (the teacher generator in the KD step): prepared once and reused.  A trainable
+    parameter is re-derived every call (its storage may be updated behind torch's version counter by
+    the fused optimizer kernel)."""
+    if not (_is_frozen(weight) and _is_frozen(bias)):
+        return _weight_prep(weight, bias, wscale, upsample, tc_fwd, tc_dgrad, pin, pout, want_wsq)
+    key = (weight.data_ptr(), weight._version, tuple(weight.shape),
+           None if bias is None else (bias.data_ptr(), bias._version), wscale, upsample, tc_fwd, tc_dgrad, want_wsq)
+    hit = _prep_cache.get(key)
+    if hit is None:
+        if len(_prep_cache) > 1024:
+            _prep_cache.clear()
+        hit = _weight_prep(weight, bias, wscale, upsample, tc_fwd, tc_dgrad, pin, pout, want_wsq)
+        _prep_cache[key] = hit
+    return hit
+
+
+class _StyledConvFn(Function):
+    """a = [lrelu]( d * conv(s*x, c*W) [+ nw*noise] [+ bias] ) on NHWC-p buffers, d = rsqrt(s^2 Wsq + eps).
+
+    Inputs: x [B,I,H,W]; s_p [B,pitch(I)] (zero padded); weight [1,O,I,k,k]; noise [B|1,1,Ho,Wo] or None;
+    noise_w [1] or None; bias [O] or None.  Non-tensor: wscale (c), demodulate, eps, upsample, fir [4,4], pad, act.
     """
 
     @staticmethod
-    def forward(ctx, x, s, d, weight, noise, noise_w, bias, wscale, upsample, fir, pad, act, algo):
+    def forward(ctx, x, s_p, weight, noise, noise_w, bias, wscale, demodulate, eps, upsample, fir, pad, act, algo):
         require_cuda(x, 'ModulatedConv2d')
         b, cin, h, w = x.shape
         _, cout, cin_w, k, _ = weight.shape
         if cin_w != cin:
             raise RuntimeError(f'ModulatedConv2d: input has {cin} channels, weight expects {cin_w}')
         pin, pout = pitch_of(cin), pitch_of(cout)
+        if s_p.shape != (b, pin):
+            raise RuntimeError(f'ModulatedConv2d: style scalars have shape {tuple(s_p.shape)}, expected {(b, pin)}')
         dev = x.device
         with torch.cuda.device(dev):
             st = stream_of(x)
             xb = as_nhwc_buf(x.detach())
-            s_p = _pad_last(s.detach().float(), pin)
-            d_p = _pad_last(d.detach().float(), pout) if d is not None else None
-            bias_p = _pad_last(bias.detach().float(), pout) if bias is not None else None
-            wk = cached_frozen(weight, ('wk', wscale), lambda: weight.detach()[0] * wscale)   # [O,I,k,k]
+            s_p = s_p.detach().contiguous()
             tc = _use_tc(algo, pin)
+            tc_d = _use_tc(algo, pout)
+            prep = _prepared(weight, bias, wscale, upsample, tc, tc_d, pin, pout, demodulate)
+            bias_p = prep.bias_p
+            if demodulate:
+                d_p = torch.empty((b, pout), device=dev, dtype=torch.float32)
+                check(lib.cagc_demod(st, s_p.data_ptr(), prep.wsq_io.data_ptr(), d_p.data_ptr(), b, pin, cout, pout,
+                                     eps), 'demod')
+            else:
+                d_p = None
             if tc:
                 # tensor-pipe path: operands come straight from TMA, so modulation is a tensor pass
-                w_fwd = cached_frozen(weight, ('fwd_tc', wscale, pin),
-                                      lambda: _slabs_tc(wk.permute(2, 3, 0, 1), pin))   # [t][o][i], K-major
                 x_in = torch.empty_like(xb)
                 if xb.numel():
                     check(lib.cagc_modulate(st, xb.data_ptr(), s_p.data_ptr(), x_in.data_ptr(), b, h, w, pin), 'modulate')
                 s_arg, falgo = None, config.ALGO_TCGEN05_TF32
             else:
-                w_fwd = cached_frozen(weight, ('fwd_simt', wscale, pin, pout),
-                                      lambda: _slabs(wk.permute(2, 3, 1, 0), pin, pout))  # [t][i][o]
                 x_in, s_arg, falgo = xb, s_p.data_ptr(), config.ALGO_SIMT_FP32
+            w_fwd = prep.w_fwd
             if noise is not None:
                 noise = noise.detach().contiguous()
                 nb = noise.shape[0]
@@ -192,22 +264,21 @@ class _StyledConvFn(Function):
                                          'fir_nhwc'))
                 del ut
         xm = x_in if tc else None      # modulated, TF32-rounded input: A operand of the tensor-pipe wgrad
-        ctx.save_for_backward(xb, s_p, d_p, wk, noise, nw, bias_p, out, fir if upsample else None, xm)
+        ctx.save_for_backward(xb, s_p, d_p, weight, noise, nw, bias_p, out, fir if upsample else None, xm,
+                              prep.w_dgrad, prep.wsq_oi)
         ctx.cfg = (b, cin, cout, h, w, k, pin, pout, upsample, pad, bool(act), nstride, algo, wscale,
-                   d is not None, bias is not None)
+                   demodulate, bias is not None)
         return nhwc_view(out, cout)
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, ga):
-        xb, s_p, d_p, wk, noise, nw, bias_p, out, fir, xm = ctx.saved_tensors
+        xb, s_p, d_p, weight, noise, nw, bias_p, out, fir, xm, w_d, wsq_oi = ctx.saved_tensors
         (b, cin, cout, h, w, k, pin, pout, upsample, pad, act, nstride, algo, wscale, has_d, has_bias) = ctx.cfg
-        if torch.is_grad_enabled() and ga.requires_grad:
-            raise RuntimeError('double backward through the fused modulated convolution is not implemented; '
-                               'use b200gan.config.second_order() (composite path) for the PPL regulariser')
         dev = xb.device
         ho, wo = out.shape[1], out.shape[2]
-        need_x, need_s, need_d, need_w = ctx.needs_input_grad[0:4]
-        need_nw, need_bias = ctx.needs_input_grad[5], ctx.needs_input_grad[6]
+        need_x, need_s, need_w = ctx.needs_input_grad[0:3]
+        need_nw, need_bias = ctx.needs_input_grad[4], ctx.needs_input_grad[5]
         with torch.cuda.device(dev):
             st = stream_of(xb)
             gu = torch.empty_like(out)
@@ -217,10 +288,20 @@ class _StyledConvFn(Function):
             check(lib.cagc_act_bwd(st, ga.data_ptr(), sb, sc, sh, sw, out.data_ptr(), ptr(d_p), ptr(noise), ptr(nw),
                                    ptr(bias_p), gu.data_ptr(), partial.data_ptr(), b, ho, wo, pout, cout,
                                    nstride, int(act)), 'act_bwd')
-            sums = partial.sum(1)                                   # [B,3,P]
-            g_bias = sums[:, 0, :cout].sum(0) if (has_bias and need_bias) else None
-            g_d = sums[:, 1, :cout].contiguous() if (has_d and need_d) else None
-            g_nw = sums[:, 2, :cout].sum().reshape(1) if (noise is not None and need_nw) else None
+            # chunk partials -> g_bias, gq = dL/d(demodulation radicand) = -1/2 d^3 gd, noise-weight partials
+            want_bias = has_bias and need_bias
+            want_q = has_d and (need_s or need_w)
+            want_nw = noise is not None and need_nw
+            g_bias_p = torch.empty((pout,), device=dev, dtype=torch.float32) if want_bias else None
+            gq = torch.empty((b, pout), device=dev, dtype=torch.float32) if want_q else None
+            nblk = lib.cagc_act_bwd_finalize_blocks(pout)
+            nw_part = torch.empty((nblk,), device=dev, dtype=torch.float32) if want_nw else None
+            if want_bias or want_q or want_nw:
+                check(lib.cagc_act_bwd_finalize(st, partial.data_ptr(), ptr(d_p), ptr(g_bias_p), ptr(gq), ptr(nw_part),
+                                                b, chunks, pout), 'act_bwd_finalize')
+            g_bias = g_bias_p[:cout] if want_bias else None
+            g_nw = nw_part.sum().reshape(1) if want_nw else None
+            del partial
 
             if upsample:
                 # blur backward: correlation with the FIR kernel, pads of op/upfirdn2d.py:111-116
@@ -228,7 +309,7 @@ class _StyledConvFn(Function):
                 hu, wu = 2 * h + k - 2, 2 * w + k - 2
                 gp0, gp1 = kh - pad[0] - 1, hu - ho + pad[0]
                 g_t = torch.empty((b, hu, wu, pout), device=dev, dtype=torch.float32)
-                firf = torch.flip(fir, [0, 1]).contiguous()
+                firf = _flipped(fir)
                 check(lib.cagc_fir_nhwc(st, gu.data_ptr(), firf.data_ptr(), None, None, None, None, g_t.data_ptr(),
                                         b, ho, wo, pout, pout, kh, kw, gp0, gp1, gp0, gp1, 0, 0), 'fir_nhwc(bwd)')
                 g_conv = g_t
@@ -238,60 +319,73 @@ class _StyledConvFn(Function):
             g_x = g_s = g_w = None
             if need_x or need_s:
                 gxt = torch.empty((b, h, w, pin), device=dev, dtype=torch.float32)
-                if upsample and _use_tc(algo, pout):
-                    w_d = _slabs_tc(wk.permute(2, 3, 1, 0), pout)                    # [t][i][o], K = o
-                    _timed('conv_up_dgrad[algo1]', 2.0 * b * h * w * cin * cout * k * k,
-                           4.0 * b * (h * w * cin + hu * wu * cout),
+                dalgo = config.ALGO_TCGEN05_TF32 if _use_tc(algo, pout) else config.ALGO_SIMT_FP32
+                flops, nbytes = 2.0 * b * h * w * cin * cout * k * k, 4.0 * b * h * w * (cin + cout)
+                if upsample:
+                    _timed(f'conv_up_dgrad[algo{dalgo}]', flops, 4.0 * b * (h * w * cin + hu * wu * cout),
                            lambda: check(lib.cagc_conv_up_dgrad(st, g_conv.data_ptr(), w_d.data_ptr(), gxt.data_ptr(),
-                                                                b, h, w, pout, pin, k, config.ALGO_TCGEN05_TF32),
-                                         'conv_up_dgrad(tc)'))
-                elif upsample:
-                    w_d = _slabs(wk.permute(2, 3, 0, 1), pout, pin)                 # [t][o][i]
-                    _timed('conv_up_dgrad[algo0]', 2.0 * b * h * w * cin * cout * k * k,
-                           4.0 * b * (h * w * cin + hu * wu * cout),
-                           lambda: check(lib.cagc_conv_up_dgrad(st, g_conv.data_ptr(), w_d.data_ptr(), gxt.data_ptr(),
-                                                                b, h, w, pout, pin, k, config.ALGO_SIMT_FP32),
-                                         'conv_up_dgrad'))
-                elif _use_tc(algo, pout):
-                    w_d = _slabs_tc(torch.flip(wk, [2, 3]).permute(2, 3, 1, 0), pout)   # [t'][i][o], K = o
-                    _timed('conv_same[algo1]', 2.0 * b * h * w * cin * cout * k * k, 4.0 * b * h * w * (cin + cout),
-                           lambda: check(lib.cagc_conv_same(st, g_conv.data_ptr(), w_d.data_ptr(), None, None, None,
-                                                            None, None, gxt.data_ptr(), b, h, w, pout, pin, pin, k, 0,
-                                                            0, config.ALGO_TCGEN05_TF32), 'conv_same(dgrad,tc)'))
+                                                                b, h, w, pout, pin, k, dalgo), 'conv_up_dgrad'))
                 else:
-                    w_d = _slabs(torch.flip(wk, [2, 3]).permute(2, 3, 0, 1), pout, pin)
-                    _timed('conv_same[algo0]', 2.0 * b * h * w * cin * cout * k * k, 4.0 * b * h * w * (cin + cout),
+                    _timed(f'conv_same[algo{dalgo}]', flops, nbytes,
                            lambda: check(lib.cagc_conv_same(st, g_conv.data_ptr(), w_d.data_ptr(), None, None, None,
                                                             None, None, gxt.data_ptr(), b, h, w, pout, pin, pin, k, 0,
-                                                            0, config.ALGO_SIMT_FP32), 'conv_same(dgrad)'))
+                                                            0, dalgo), 'conv_same(dgrad)'))
                 mchunks = lib.cagc_act_bwd_chunks(h, w)
                 mpartial = torch.empty((b, mchunks, pin), device=dev, dtype=torch.float32)
                 check(lib.cagc_mod_bwd(st, gxt.data_ptr(), xb.data_ptr(), s_p.data_ptr(), mpartial.data_ptr(),
                                        b, h, w, pin), 'mod_bwd')
                 if need_s:
-                    g_s = mpartial.sum(1)[:, :cin]
+                    g_s = torch.empty((b, pin), device=dev, dtype=torch.float32)
+                    check(lib.cagc_style_grad_finalize(st, mpartial.data_ptr(), ptr(gq), s_p.data_ptr(), ptr(wsq_oi),
+                                                       g_s.data_ptr(), b, mchunks, pin, cout, pout),
+                          'style_grad_finalize')
                 if need_x:
                     g_x = nhwc_view(gxt, cin)
+            elif need_s and gq is not None:
+                raise RuntimeError('ModulatedConv2d: style gradient without input gradient is not implemented')
             if need_w:
-                # exact-fp32 mode (saliency): SIMT engine; tensor-pipe mode: tcgen05 TF32.  Both reduce the
-            # split-K partials in a fixed order (deterministic)
+                # exact-fp32 mode (saliency): SIMT engine; tensor-pipe mode: tcgen05 TF32.  Both leave split-K
+                # partials that cagc_wgrad_finalize reduces in a fixed order (deterministic), folding in the
+                # weight scale, the demodulation term and the [O,I,k,k] parameter layout
                 walgo = config.ALGO_TCGEN05_TF32 if (xm is not None and _use_tc(algo, min(pin, pout))
                                                      and pout <= 256) else config.ALGO_SIMT_FP32
                 nsp = lib.cagc_conv_wgrad_splits(b, h, w, pin, pout, k, walgo)
-                gw = torch.empty((k * k, pin, pout), device=dev, dtype=torch.float32)
                 wpart = torch.empty((nsp, k * k, pin, pout), device=dev, dtype=torch.float32)
                 a_in, a_sc = (xm, None) if walgo == config.ALGO_TCGEN05_TF32 else (xb, s_p.data_ptr())
+                used = C.c_int(0)
                 _timed(f'conv_wgrad[algo{walgo}]', 2.0 * b * h * w * cin * cout * k * k,
                        4.0 * b * h * w * (cin + cout),
-                       lambda: check(lib.cagc_conv_wgrad(st, a_in.data_ptr(), a_sc, g_conv.data_ptr(),
-                                                         gw.data_ptr(), wpart.data_ptr(), nsp, b, h, w, pin, pout, k,
-                                                         1 if upsample else 0, walgo), 'conv_wgrad'))
-                g_w = (gw[:, :cin, :cout].reshape(k, k, cin, cout).permute(3, 2, 0, 1) * wscale).unsqueeze(0)
-        return (g_x, g_s, g_d, g_w, None, g_nw, g_bias, None, None, None, None, None, None)
+                       lambda: check(lib.cagc_conv_wgrad_partial(st, a_in.data_ptr(), a_sc, g_conv.data_ptr(),
+                                                                 wpart.data_ptr(), nsp, b, h, w, pin, pout, k,
+                                                                 1 if upsample else 0, walgo, C.byref(used)),
+                                     'conv_wgrad'))
+                g_w = torch.empty((1, cout, cin, k, k), device=dev, dtype=torch.float32)
+                wc = weight.detach()
+                wc = wc if wc.is_contiguous() else wc.contiguous()
+                check(lib.cagc_wgrad_finalize(st, wpart.data_ptr(), used.value, wc.data_ptr(), wscale, ptr(gq),
+                                              s_p.data_ptr(), b, cout, cin, k, pin, pout, g_w.data_ptr()),
+                      'wgrad_finalize')
+        return (g_x, g_s, g_w, None, g_nw, g_bias, None, None, None, None, None, None, None, None)
 
 
-def styled_conv(x, s, d, weight, noise, noise_w, bias, wscale, upsample=False, fir=None, pad=(0, 0), act=True):
-    return _StyledConvFn.apply(x, s, d, weight, noise, noise_w, bias, wscale, upsample, fir, pad, act,
+_flip_cache = {}
+
+
+def _flipped(fir: torch.Tensor) -> torch.Tensor:
+    """flip(fir) of a (constant) FIR buffer, computed once per buffer version."""
+    key = (fir.data_ptr(), fir._version, tuple(fir.shape))
+    hit = _flip_cache.get(key)
+    if hit is None:
+        if len(_flip_cache) > 256:
+            _flip_cache.clear()
+        hit = torch.flip(fir, [0, 1]).contiguous()
+        _flip_cache[key] = hit
+    return hit
+
+
+def styled_conv(x, s_p, weight, noise, noise_w, bias, wscale, demodulate=True, eps=1e-8, upsample=False, fir=None,
+                pad=(0, 0), act=True):
+    return _StyledConvFn.apply(x, s_p, weight, noise, noise_w, bias, wscale, demodulate, eps, upsample, fir, pad, act,
                                config.conv_algo())
 
 
@@ -299,16 +393,18 @@ class _ToRGBFn(Function):
     """rgb = conv1x1(s*x, c*W) + bias + Upsample(skip), output NCHW [B,3,H,W] (model.py:380-395)."""
 
     @staticmethod
-    def forward(ctx, x, s, weight, bias, skip, wscale, fir, pad):
+    def forward(ctx, x, s_p, weight, bias, skip, wscale, fir, pad):
         require_cuda(x, 'ToRGB')
         b, cin, h, w = x.shape
         nout = weight.shape[1]
         pin = pitch_of(cin)
+        if s_p.shape != (b, pin):
+            raise RuntimeError(f'ToRGB: style scalars have shape {tuple(s_p.shape)}, expected {(b, pin)}')
         dev = x.device
         with torch.cuda.device(dev):
             st = stream_of(x)
             xb = as_nhwc_buf(x.detach())
-            s_p = _pad_last(s.detach().float(), pin)
+            s_p = s_p.detach().contiguous()
             w2 = weight.detach().reshape(nout, cin).contiguous()
             bias_c = bias.detach().reshape(nout).contiguous() if bias is not None else None
             out = torch.empty((b, nout, h, w), device=dev, dtype=torch.float32)
@@ -329,12 +425,10 @@ class _ToRGBFn(Function):
         return out
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, g):
         xb, s_p, w2, fir = ctx.saved_tensors
         b, cin, nout, h, w, pin, wscale, pad, has_bias, has_skip = ctx.cfg
-        if torch.is_grad_enabled() and g.requires_grad:
-            raise RuntimeError('double backward through the fused ToRGB is not implemented; '
-                               'use b200gan.config.second_order()')
         dev = xb.device
         g = g.contiguous()
         with torch.cuda.device(dev):
@@ -344,13 +438,13 @@ class _ToRGBFn(Function):
             partial = torch.empty((b, chunks, nout, pin), device=dev, dtype=torch.float32)
             check(lib.cagc_torgb_bwd(st, g.data_ptr(), xb.data_ptr(), w2.data_ptr(), s_p.data_ptr(), gx.data_ptr(),
                                      partial.data_ptr(), b, h, w, pin, cin, nout, wscale), 'torgb_bwd')
-            t = partial.sum(1)[:, :, :cin]                                   # [B,nout,I] = sum_p g*x
-            s = s_p[:, :cin]
             g_w = g_s = g_bias = g_skip = None
-            if ctx.needs_input_grad[2]:
-                g_w = (wscale * torch.einsum('boi,bi->oi', t, s)).reshape(1, nout, cin, 1, 1)
-            if ctx.needs_input_grad[1]:
-                g_s = wscale * torch.einsum('boi,oi->bi', t, w2)
+            need_s, need_w = ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+            if need_s or need_w:
+                g_w = torch.empty((1, nout, cin, 1, 1), device=dev, dtype=torch.float32) if need_w else None
+                g_s = torch.empty((b, pin), device=dev, dtype=torch.float32) if need_s else None
+                check(lib.cagc_torgb_bwd_finalize(st, partial.data_ptr(), s_p.data_ptr(), w2.data_ptr(), wscale,
+                                                  ptr(g_w), ptr(g_s), b, chunks, cin, pin, nout), 'torgb_bwd_finalize')
             if has_bias and ctx.needs_input_grad[3]:
                 g_bias = g.sum(dim=(0, 2, 3)).reshape(1, nout, 1, 1)
             if has_skip and ctx.needs_input_grad[4]:
@@ -359,18 +453,156 @@ class _ToRGBFn(Function):
                 # backward of Upsample(up=2, pad): down=2 with the flipped kernel (op/upfirdn2d.py:111-116)
                 gp0 = fh - pad[0] - 1
                 gp1 = (h // 2) * 2 - h + pad[0] - 2 + 1
-                g_skip = _launch(g, torch.flip(fir, [0, 1]).contiguous(), (1, 1), (2, 2), (gp0, gp1, gp0, gp1))
+                g_skip = _launch(g, _flipped(fir), (1, 1), (2, 2), (gp0, gp1, gp0, gp1))
             g_x = nhwc_view(gx, cin) if ctx.needs_input_grad[0] else None
         return g_x, g_s, g_w, g_bias, g_skip, None, None, None
 
 
-def to_rgb(x, s, weight, bias, skip, wscale, fir=None, pad=(0, 0)):
-    return _ToRGBFn.apply(x, s, weight, bias, skip, wscale, fir, pad)
+def to_rgb(x, s_p, weight, bias, skip, wscale, fir=None, pad=(0, 0)):
+    return _ToRGBFn.apply(x, s_p, weight, bias, skip, wscale, fir, pad)
+
+
+# ------------------------------------------------------------------------------------------------
+# Style modulation of many layers in one launch (EqualLinear, model.py:156-166, as used at :248)
+# ------------------------------------------------------------------------------------------------
+def _ptr_array(tensors):
+    return (C.c_void_p * len(tensors))(*[None if t is None else t.data_ptr() for t in tensors])
+
+
+class _StyleAffineFn(Function):
+    """s_l = scale_l * latent[:, idx_l] @ A_l^T + lr_mul_l * bias_l for every layer l of `meta`, zero padded
+    to the channel pitch.  args: latent [B, n_latent, D], meta = [(I, pitch, idx, scale, lr_mul)], then
+    A_0, bias_0, A_1, bias_1, ...  Returns one [B, pitch_l] tensor per layer."""
+
+    @staticmethod
+    def forward(ctx, latent, meta, *params):
+        require_cuda(latent, 'style modulation')
+        n = len(meta)
+        b, n_latent, dim = latent.shape
+        lat = latent.detach()
+        if lat.stride(2) != 1:
+            lat = lat.contiguous()
+        As = [params[2 * i].detach().contiguous() for i in range(n)]
+        bs = [None if params[2 * i + 1] is None else params[2 * i + 1].detach().contiguous() for i in range(n)]
+        dev = latent.device
+        outs = [torch.empty((b, m[1]), device=dev, dtype=torch.float32) for m in meta]
+        arr_i = (C.c_int * n)(*[m[0] for m in meta])
+        arr_p = (C.c_int * n)(*[m[1] for m in meta])
+        arr_l = (C.c_int * n)(*[m[2] for m in meta])
+        arr_s = (C.c_float * n)(*[m[3] for m in meta])
+        arr_m = (C.c_float * n)(*[m[4] for m in meta])
+        with torch.cuda.device(dev):
+            check(lib.cagc_style_affine(stream_of(lat), n, _ptr_array(As), _ptr_array(bs), _ptr_array(outs), arr_i,
+                                        arr_p, arr_l, arr_s, arr_m, lat.data_ptr(), lat.stride(0), lat.stride(1),
+                                        b, dim, n_latent), 'style_affine')
+        ctx.save_for_backward(lat, *As)
+        ctx.meta = meta
+        ctx.has_bias = [x is not None for x in bs]
+        return tuple(outs)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, *gs):
+        lat, *As = ctx.saved_tensors
+        meta = ctx.meta
+        n = len(meta)
+        b, n_latent, dim = lat.shape
+        dev = lat.device
+        gs = [None if g is None else g.contiguous() for g in gs]
+        need_lat = ctx.needs_input_grad[0]
+        need_par = any(ctx.needs_input_grad[2:])
+        gA = [torch.empty_like(a) for a in As] if need_par else None
+        gb = [torch.empty((m[0],), device=dev, dtype=torch.float32) if hb else None
+              for m, hb in zip(meta, ctx.has_bias)] if need_par else None
+        g_lat = torch.empty((b, n_latent, dim), device=dev, dtype=torch.float32) if need_lat else None
+        arr_i = (C.c_int * n)(*[m[0] for m in meta])
+        arr_p = (C.c_int * n)(*[m[1] for m in meta])
+        arr_l = (C.c_int * n)(*[m[2] for m in meta])
+        arr_s = (C.c_float * n)(*[m[3] for m in meta])
+        arr_m = (C.c_float * n)(*[m[4] for m in meta])
+        with torch.cuda.device(dev):
+            check(lib.cagc_style_affine_bwd(stream_of(lat), n, _ptr_array(As), _ptr_array(gs),
+                                            _ptr_array(gA) if need_par else None,
+                                            _ptr_array(gb) if need_par else None, arr_i, arr_p, arr_l, arr_s, arr_m,
+                                            lat.data_ptr(), lat.stride(0), lat.stride(1), ptr(g_lat), b, dim, n_latent),
+                  'style_affine_bwd')
+        grads = [g_lat, None]
+        for i in range(n):
+            grads.append(gA[i] if need_par and ctx.needs_input_grad[2 + 2 * i] else None)
+            grads.append(gb[i] if need_par and ctx.has_bias[i] and ctx.needs_input_grad[3 + 2 * i] else None)
+        return tuple(grads)
+
+
+_MAX_STYLE_LAYERS = 40
+
+
+def style_affine(latent: torch.Tensor, mods, indices):
+    """latent [B, n_latent, D]; mods: EqualLinear-like objects (weight [I,D], bias [I] or None, scale,
+    lr_mul); indices: which latent row each layer reads.  Returns the list of zero-padded style
+    scalars s_l [B, pitch(I_l)] -- one launch for the whole generator."""
+    outs = []
+    for lo in range(0, len(mods), _MAX_STYLE_LAYERS):
+        chunk = mods[lo:lo + _MAX_STYLE_LAYERS]
+        meta = [(m.weight.shape[0], pitch_of(m.weight.shape[0]), int(i), float(m.scale), float(m.lr_mul))
+                for m, i in zip(chunk, indices[lo:lo + _MAX_STYLE_LAYERS])]
+        params = []
+        for m in chunk:
+            params += [m.weight, m.bias]
+        outs += list(_StyleAffineFn.apply(latent, meta, *params))
+    return outs
+
+
+# ------------------------------------------------------------------------------------------------
+# EqualLinear (model.py:137-171): library GEMM + ONE epilogue kernel (scale, bias*lr_mul, leaky ReLU)
+# ------------------------------------------------------------------------------------------------
+class _EqualLinearFn(Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, scale, lr_mul, act):
+        require_cuda(x, 'EqualLinear')
+        n_out, n_in = weight.shape
+        x2 = x.detach().reshape(-1, n_in)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        w = weight.detach()
+        acc = torch.mm(x2, w.t())
+        m = acc.shape[0]
+        out = torch.empty_like(acc)
+        bias_c = bias.detach().contiguous() if bias is not None else None
+        with torch.cuda.device(x.device):
+            check(lib.cagc_linear_bias_act(stream_of(acc), acc.data_ptr(), ptr(bias_c), out.data_ptr(), m, n_out,
+                                           scale, lr_mul, int(act), 0.2, math.sqrt(2)), 'linear_bias_act')
+        ctx.save_for_backward(x2, w, out if act else None)
+        ctx.cfg = (scale, lr_mul, act, bias is not None, x.shape)
+        return out.reshape(*x.shape[:-1], n_out)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        x2, w, out = ctx.saved_tensors
+        scale, lr_mul, act, has_bias, xshape = ctx.cfg
+        n_out, n_in = w.shape
+        m = x2.shape[0]
+        g2 = g.reshape(m, n_out).contiguous()
+        g_acc = torch.empty_like(g2)
+        g_bias = torch.empty((n_out,), device=g.device, dtype=torch.float32) \
+            if (has_bias and ctx.needs_input_grad[2]) else None
+        with torch.cuda.device(g.device):
+            check(lib.cagc_linear_bias_act_bwd(stream_of(g2), g2.data_ptr(), ptr(out), g_acc.data_ptr(), ptr(g_bias),
+                                               m, n_out, scale, lr_mul, int(act), 0.2, math.sqrt(2)),
+                  'linear_bias_act_bwd')
+        g_x = torch.mm(g_acc, w).reshape(xshape) if ctx.needs_input_grad[0] else None
+        g_w = torch.mm(g_acc.t(), x2) if ctx.needs_input_grad[1] else None
+        return g_x, g_w, g_bias, None, None, None
+
+
+def equal_linear(x, weight, bias, scale, lr_mul, act):
+    return _EqualLinearFn.apply(x, weight, bias, scale, lr_mul, bool(act))
 
 
 def demod_coefficients(s: torch.Tensor, weight: torch.Tensor, wscale: float, eps: float = 1e-8) -> torch.Tensor:
-    """d[b,o] = rsqrt(sum_i s[b,i]^2 * Wsq[o,i] + eps), Wsq = sum_taps (c*W)^2   (model.py:251-253)."""
-    wsq = cached_frozen(weight, ('wsq', wscale), lambda: (weight[0] * wscale).square().sum(dim=(2, 3)))   # [O,I]
+    """d[b,o] = rsqrt(sum_i s[b,i]^2 * Wsq[o,i] + eps), Wsq = sum_taps (c*W)^2   (model.py:251-253);
+    differentiable torch form, used by the second-order composite only."""
+    wsq = (weight[0] * wscale).square().sum(dim=(2, 3))   # [O,I]
     return torch.rsqrt(s.square() @ wsq.t() + eps)
 
 

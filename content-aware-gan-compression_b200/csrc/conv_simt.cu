@@ -357,24 +357,28 @@ int cagc_conv_wgrad_splits(int B, int H, int W, int a_pitch, int g_pitch, int ks
     return (int)want;
 }
 
-int cagc_conv_wgrad(cagc_stream_t stream_, const float* a, const float* a_scale, const float* g, float* gw,
-                    float* partial, int nsplits, int B, int H, int W, int a_pitch, int g_pitch, int ksize, int mode,
-                    int algo) {
-    cudaStream_t stream = (cudaStream_t)stream_;
+// gw == nullptr: leave the split partials unreduced (the caller folds the reduction into
+// cagc_wgrad_finalize); *used receives the number of partial slab sets actually written
+static int conv_wgrad_impl(cudaStream_t stream, const float* a, const float* a_scale, const float* g, float* gw,
+                           float* partial, int nsplits, int B, int H, int W, int a_pitch, int g_pitch, int ksize,
+                           int mode, int algo, int* used) {
     CAGC_TRY(check_nhwc("conv_wgrad", B, H, W, a_pitch, g_pitch, ksize));
-    CAGC_REQUIRE(a && g && gw && partial, "conv_wgrad: null pointer");
+    CAGC_REQUIRE(a && g && partial, "conv_wgrad: null pointer");
     CAGC_REQUIRE(nsplits >= 1 && nsplits <= 4096, "conv_wgrad: bad nsplits %d", nsplits);
     CAGC_REQUIRE(mode == 0 || mode == 1, "conv_wgrad: mode must be 0 (same) or 1 (up)");
     if (algo == 1) {
         CAGC_REQUIRE(a_scale == nullptr, "conv_wgrad: the tcgen05 path takes a pre-modulated input (cagc_modulate)");
         const int64_t n1 = (int64_t)ksize * ksize * a_pitch * g_pitch;
         if ((int64_t)B * H * W == 0) {
-            cudaError_t e = cudaMemsetAsync(gw, 0, n1 * sizeof(float), stream);
+            *used = 1;
+            cudaError_t e = cudaMemsetAsync(gw ? gw : partial, 0, n1 * sizeof(float), stream);
             return e == cudaSuccess ? 0 : fail((int)e, "conv_wgrad: memset failed");
         }
         const int tiles_cap = cagc_tc_wgrad_splits(B, H, W, a_pitch, g_pitch, ksize);
         if (nsplits > tiles_cap) nsplits = tiles_cap;
         CAGC_TRY(cagc_tc_wgrad(stream, a, g, partial, &nsplits, B, H, W, a_pitch, g_pitch, ksize, mode));
+        *used = nsplits;
+        if (!gw) return 0;
         int64_t blocks1 = ceil_div<int64_t>(n1 / 4, 256);
         if (blocks1 > kNumSMs * 8) blocks1 = kNumSMs * 8;
         split_reduce_kernel<<<(unsigned)blocks1, 256, 0, stream>>>(partial, gw, n1 / 4, nsplits);
@@ -404,17 +408,37 @@ int cagc_conv_wgrad(cagc_stream_t stream_, const float* a, const float* a_scale,
     }
     const int64_t n = (int64_t)p.ntaps * a_pitch * g_pitch;
     if (M == 0) {
-        cudaError_t e = cudaMemsetAsync(gw, 0, n * sizeof(float), stream);
+        *used = 1;
+        cudaError_t e = cudaMemsetAsync(gw ? gw : partial, 0, n * sizeof(float), stream);
         if (e != cudaSuccess) return fail((int)e, "conv_wgrad: memset failed");
         return 0;
     }
     dim3 grid(ceil_div(a_pitch, WT), ceil_div(g_pitch, WT), p.ntaps * nsplits);
     wgrad_simt_kernel<<<grid, 256, 0, stream>>>(p);
     CAGC_TRY(launched("wgrad_simt_kernel"));
+    *used = nsplits;
+    if (!gw) return 0;
     int64_t blocks = ceil_div<int64_t>(n / 4, 256);
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
     split_reduce_kernel<<<(unsigned)blocks, 256, 0, stream>>>(partial, gw, n / 4, nsplits);
     return launched("split_reduce_kernel");
+}
+
+int cagc_conv_wgrad(cagc_stream_t stream_, const float* a, const float* a_scale, const float* g, float* gw,
+                    float* partial, int nsplits, int B, int H, int W, int a_pitch, int g_pitch, int ksize, int mode,
+                    int algo) {
+    CAGC_REQUIRE(gw, "conv_wgrad: null pointer");
+    int used = 0;
+    return conv_wgrad_impl((cudaStream_t)stream_, a, a_scale, g, gw, partial, nsplits, B, H, W, a_pitch, g_pitch, ksize,
+                           mode, algo, &used);
+}
+
+int cagc_conv_wgrad_partial(cagc_stream_t stream_, const float* a, const float* a_scale, const float* g,
+                            float* partial, int nsplits, int B, int H, int W, int a_pitch, int g_pitch, int ksize,
+                            int mode, int algo, int* nsplits_used) {
+    CAGC_REQUIRE(nsplits_used, "conv_wgrad_partial: null pointer");
+    return conv_wgrad_impl((cudaStream_t)stream_, a, a_scale, g, nullptr, partial, nsplits, B, H, W, a_pitch, g_pitch,
+                           ksize, mode, algo, nsplits_used);
 }
 
 }  // extern "C"

@@ -125,7 +125,13 @@ class EqualLinear(nn.Module):
         self.scale = (1 / math.sqrt(in_dim)) * lr_mul
         self.lr_mul = lr_mul
 
+    # Generator marks its own layers: library GEMM + ONE epilogue kernel (first-order autograd only).  Everything
+    # else (the discriminator head, any second-order path) runs the differentiable torch composition.
+    _fused = False
+
     def forward(self, input):
+        if self._fused and not _cfg.is_second_order() and input.is_cuda:
+            return _mc.equal_linear(input, self.weight, self.bias, self.scale, self.lr_mul, bool(self.activation))
         w = _mc.cached_frozen(self.weight, ('eqlin', self.scale), lambda: self.weight * self.scale)
         if self.activation:
             return fused_leaky_relu(F.linear(input, w), self.bias * self.lr_mul)
@@ -179,33 +185,42 @@ class ModulatedConv2d(nn.Module):
         return (f'{self.__class__.__name__}({self.in_channel}, {self.out_channel}, {self.kernel_size}, '
                 f'upsample={self.upsample}, downsample={self.downsample})')
 
-    def _run(self, input, style, noise=None, noise_weight=None, act_bias=None, act=False):
-        """Shared body of ModulatedConv2d.forward and the fused StyledConv.forward."""
-        s = self.modulation(style)                                            # [B, I]
-        d = _mc.demod_coefficients(s, self.weight, self.scale, self.eps) if self.demodulate else None
-        if self.downsample:
-            # not used by the generator or the discriminator of this repo; differentiable composite
-            w = (self.weight[0] * self.scale)
-            x = self.blur(input * s[:, :, None, None])
-            out = F.conv2d(x, w, stride=2)
-            if d is not None:
-                out = out * d[:, :, None, None]
-            if noise is not None:
-                out = out + noise_weight * noise
-            if act:
-                out = fused_leaky_relu(out, act_bias)
+    def _run(self, input, style, noise=None, noise_weight=None, act_bias=None, act=False, s_p=None):
+        """Shared body of ModulatedConv2d.forward and the fused StyledConv.forward.  `s_p`: style scalars
+        already computed (zero padded to the channel pitch) by the generator's one-launch modulation."""
+        if self.downsample or _cfg.is_second_order():
+            s = self.modulation(style)                                            # [B, I]
+            d = _mc.demod_coefficients(s, self.weight, self.scale, self.eps) if self.demodulate else None
+            if self.downsample:
+                # not used by the generator or the discriminator of this repo; differentiable composite
+                w = (self.weight[0] * self.scale)
+                x = self.blur(input * s[:, :, None, None])
+                out = F.conv2d(x, w, stride=2)
+                if d is not None:
+                    out = out * d[:, :, None, None]
+                if noise is not None:
+                    out = out + noise_weight * noise
+                if act:
+                    out = fused_leaky_relu(out, act_bias)
+                return out, s
+            fir = self.blur.kernel if self.upsample else None
+            pad = self.blur.pad if self.upsample else (0, 0)
+            out = _mc.styled_conv_composite(input, s, d, self.weight, noise, noise_weight, act_bias, self.scale,
+                                            upsample=self.upsample, fir=fir, pad=pad, act=act)
             return out, s
+        if s_p is None:
+            s_p = _mc.style_affine(style.unsqueeze(1), [self.modulation], [0])[0]
         fir = self.blur.kernel if self.upsample else None
         pad = self.blur.pad if self.upsample else (0, 0)
-        fn = _mc.styled_conv_composite if _cfg.is_second_order() else _mc.styled_conv
-        out = fn(input, s, d, self.weight, noise, noise_weight, act_bias, self.scale,
-                 upsample=self.upsample, fir=fir, pad=pad, act=act)
-        return out, s
+        out = _mc.styled_conv(input, s_p, self.weight, noise, noise_weight, act_bias, self.scale,
+                              demodulate=self.demodulate, eps=self.eps, upsample=self.upsample, fir=fir, pad=pad,
+                              act=act)
+        return out, s_p[:, :self.in_channel]
 
     def forward(self, input, style, return_style_scalars=False):
         out, s = self._run(input, style)
         if return_style_scalars:
-            return out, s.view(s.shape[0], 1, self.in_channel, 1, 1)
+            return out, s.reshape(s.shape[0], 1, self.in_channel, 1, 1)
         return out
 
 
@@ -246,7 +261,7 @@ class StyledConv(nn.Module):
         self.noise = NoiseInjection()
         self.activate = FusedLeakyReLU(out_channel)
 
-    def forward(self, input, style, return_style_scalars=False, noise=None):
+    def forward(self, input, style, return_style_scalars=False, noise=None, _s=None):
         if noise is None:
             # same RNG consumption as the reference: one normal_() per layer, in call order (model.py:299-301)
             b, _, h, w = input.shape
@@ -255,13 +270,13 @@ class StyledConv(nn.Module):
         act = self.activate
         if act.negative_slope != 0.2 or abs(act.scale - math.sqrt(2)) > 1e-12:
             # non-default activation constants: unfused tail
-            out, s = self.conv._run(input, style)
+            out, s = self.conv._run(input, style, s_p=_s)
             out = act(self.noise(out, noise=noise))
         else:
             out, s = self.conv._run(input, style, noise=noise, noise_weight=self.noise.weight, act_bias=act.bias,
-                                    act=True)
+                                    act=True, s_p=_s)
         if return_style_scalars:
-            return out, s.view(s.shape[0], 1, self.conv.in_channel, 1, 1)
+            return out, s.reshape(s.shape[0], 1, self.conv.in_channel, 1, 1)
         return out
 
 
@@ -275,9 +290,8 @@ class ToRGB(nn.Module):
         self.conv = ModulatedConv2d(in_channel, 3, 1, style_dim, demodulate=False)
         self.bias = nn.Parameter(torch.zeros(1, 3, 1, 1))
 
-    def forward(self, input, style, skip=None, return_style_scalars=False):
+    def forward(self, input, style, skip=None, return_style_scalars=False, _s=None):
         conv = self.conv
-        s = conv.modulation(style)
         if skip is not None:
             up = self.upsample
             if up.factor != 2:
@@ -285,10 +299,15 @@ class ToRGB(nn.Module):
             fir, pad = up.kernel, up.pad
         else:
             fir, pad = None, (0, 0)
-        fn = _mc.to_rgb_composite if _cfg.is_second_order() else _mc.to_rgb
-        out = fn(input, s, conv.weight, self.bias, skip, conv.scale, fir=fir, pad=pad)
+        if _cfg.is_second_order():
+            s = conv.modulation(style)
+            out = _mc.to_rgb_composite(input, s, conv.weight, self.bias, skip, conv.scale, fir=fir, pad=pad)
+        else:
+            s_p = _s if _s is not None else _mc.style_affine(style.unsqueeze(1), [conv.modulation], [0])[0]
+            out = _mc.to_rgb(input, s_p, conv.weight, self.bias, skip, conv.scale, fir=fir, pad=pad)
+            s = s_p[:, :conv.in_channel]
         if return_style_scalars:
-            return out, s.view(s.shape[0], 1, conv.in_channel, 1, 1)
+            return out, s.reshape(s.shape[0], 1, conv.in_channel, 1, 1)
         return out
 
 
@@ -306,6 +325,8 @@ class Generator(nn.Module):
         for _ in range(n_mlp):
             mapping.append(EqualLinear(style_dim, style_dim, lr_mul=lr_mlp, activation='fused_lrelu'))
         self.style = nn.Sequential(*mapping)
+        for m in mapping[1:]:
+            m._fused = True
 
         self.channels = {4: 512, 8: 512, 16: 512, 32: 512, 64: 256 * channel_multiplier,
                          128: 128 * channel_multiplier, 256: 64 * channel_multiplier,
@@ -364,7 +385,13 @@ class Generator(nn.Module):
                                     latent_styles, input_is_latent, noise, randomize_noise, True,
                                     return_rgb_list, return_style_scalars)
 
-        styles = latent_styles if input_is_latent else [self.style(z) for z in noise_z]
+        if input_is_latent:
+            styles = latent_styles
+        elif len(noise_z) == 2 and noise_z[0].shape == noise_z[1].shape and noise_z[0].ndim == 2:
+            # style mixing: both latents through the mapping network in one pass
+            styles = list(self.style(torch.cat([noise_z[0], noise_z[1]], 0)).chunk(2, 0))
+        else:
+            styles = [self.style(z) for z in noise_z]
 
         if noise is None:
             if randomize_noise:
@@ -386,16 +413,28 @@ class Generator(nn.Module):
 
         scalars = []
 
+        # style modulation of every layer in ONE launch (the reference runs one EqualLinear per layer,
+        # model.py:248): layer order = execution order, latent rows as in model.py:618-644
+        if _cfg.is_second_order():
+            s_of = {}
+        else:
+            mods, rows = [self.conv1.conv, self.to_rgb1.conv], [0, 1]
+            for blk, to_rgb in enumerate(self.to_rgbs):
+                mods += [self.convs[2 * blk].conv, self.convs[2 * blk + 1].conv, to_rgb.conv]
+                rows += [1 + 2 * blk, 2 + 2 * blk, 3 + 2 * blk]
+            s_all = _mc.style_affine(latent, [m.modulation for m in mods], rows)
+            s_of = {id(m): sp for m, sp in zip(mods, s_all)}
+
         def styled(layer, x, w_lat, nz):
             if return_style_scalars:
-                y, sc = layer(x, w_lat, True, noise=nz)
+                y, sc = layer(x, w_lat, True, noise=nz, _s=s_of.get(id(layer.conv)))
                 scalars.append(sc)
                 return y
-            return layer(x, w_lat, noise=nz)
+            return layer(x, w_lat, noise=nz, _s=s_of.get(id(layer.conv)))
 
         out = self.input(latent)
         out = styled(self.conv1, out, latent[:, 0], noise[0])
-        skip = self.to_rgb1(out, latent[:, 1])
+        skip = self.to_rgb1(out, latent[:, 1], _s=s_of.get(id(self.to_rgb1.conv)))
         rgbs = [skip]
 
         i = 1
@@ -403,10 +442,10 @@ class Generator(nn.Module):
             out = styled(self.convs[2 * blk], out, latent[:, i], noise[1 + 2 * blk])
             out = styled(self.convs[2 * blk + 1], out, latent[:, i + 1], noise[2 + 2 * blk])
             if return_style_scalars and (i + 3) == latent.shape[1]:   # only the last ToRGB reports (model.py:636-638)
-                skip, sc = to_rgb(out, latent[:, i + 2], skip, True)
+                skip, sc = to_rgb(out, latent[:, i + 2], skip, True, _s=s_of.get(id(to_rgb.conv)))
                 scalars.append(sc)
             else:
-                skip = to_rgb(out, latent[:, i + 2], skip)
+                skip = to_rgb(out, latent[:, i + 2], skip, _s=s_of.get(id(to_rgb.conv)))
             rgbs.append(skip)
             i += 2
 

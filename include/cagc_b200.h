@@ -37,7 +37,7 @@ typedef void* cagc_stream_t; /* cudaStream_t */
 #define CAGC_E_UNSUPPORTED (-2) /* shape outside what the kernels implement */
 
 /* bump when a signature changes; the Python loader checks it */
-#define CAGC_ABI_VERSION 10
+#define CAGC_ABI_VERSION 11
 
 int cagc_abi_version(void);
 const char* cagc_last_error(void);
@@ -134,6 +134,81 @@ int cagc_conv_wgrad_splits(int B, int H, int W, int a_pitch, int g_pitch, int ks
 int cagc_conv_wgrad(cagc_stream_t stream, const float* a, const float* a_scale, const float* g,
                     float* gw, float* partial, int nsplits, int B, int H, int W,
                     int a_pitch, int g_pitch, int ksize, int mode, int algo);
+
+/* Same as cagc_conv_wgrad without the final reduction: the `*nsplits_used` partial slab sets
+ * [split][tap][a_pitch][g_pitch] are left in `partial` for cagc_wgrad_finalize. */
+int cagc_conv_wgrad_partial(cagc_stream_t stream, const float* a, const float* a_scale, const float* g,
+                            float* partial, int nsplits, int B, int H, int W,
+                            int a_pitch, int g_pitch, int ksize, int mode, int algo, int* nsplits_used);
+
+/* ------------------------------------------------------------------------
+ * Layer bookkeeping around the convolution, one launch each (prep.cu).  They
+ * replace the ATen elementwise / reduction / tiny-GEMM chains of
+ * model.py:248-257 (weight scaling, modulation, demodulation) and of their
+ * autograd backward.
+ * ---------------------------------------------------------------------- */
+
+/* W [O][I][k][k] (the reference parameter layout, model.py:225-227) -> operand slabs
+ *   outA [k*k][RA][CA], element (t, o, i) = wscale*W[o][i][flipA ? k*k-1-t : t]   (nullable)
+ *   outB [k*k][RB][CB], element (t, i, o) = wscale*W[o][i][flipB ? k*k-1-t : t]   (nullable)
+ * zero padded, rounded to TF32 when round_tf32 != 0;
+ *   wsq_oi [SO][SI], wsq_io [SI][SO] = sum_t (wscale*W)^2 (nullable, zero padded)   (model.py:252)
+ *   bias_out [bias_np] = bias_in zero padded (nullable). */
+int cagc_weight_prep(cagc_stream_t stream, const float* w, float wscale, int O, int I, int ksize,
+                     float* outA, int RA, int CA, int flipA, float* outB, int RB, int CB, int flipB,
+                     int round_tf32, float* wsq_oi, float* wsq_io, int SO, int SI,
+                     const float* bias_in, float* bias_out, int bias_n, int bias_np);
+
+/* Style modulation of up to 40 layers in one launch (EqualLinear, model.py:156-166 as used at :248):
+ *   out_l[b][i] = scale_l * <A_l[i][:], latent[b][lat_l][:]> + bias_mul_l*bias_l[i]   (i < I_l), 0 for I_l <= i < pin_l
+ * A, bias, out, I, pin, lat, scale, bias_mul are HOST arrays of n_layers entries (device pointers
+ * inside); latent is [B][n_latent][D] with element strides (lat_sb, lat_sl, 1). */
+int cagc_style_affine(cagc_stream_t stream, int n_layers, const void* const* A, const void* const* bias,
+                      void* const* out, const int* I, const int* pin, const int* lat, const float* scale,
+                      const float* bias_mul, const float* latent, int64_t lat_sb, int64_t lat_sl,
+                      int B, int D, int n_latent);
+/* Backward: gs_l [B][pin_l] (a NULL entry = zero gradient);
+ *   gA_l[i][:] = scale_l * sum_b gs_l[b][i]*latent[b][lat_l][:],  gbias_l[i] = bias_mul_l * sum_b gs_l[b][i]
+ *   g_latent[b][idx][:] = sum_{l: lat_l == idx} scale_l * sum_i gs_l[b][i]*A_l[i][:]   (contiguous [B][n_latent][D])
+ * gA/gbias (host arrays) or g_latent may be NULL to skip that half. */
+int cagc_style_affine_bwd(cagc_stream_t stream, int n_layers, const void* const* A, const void* const* gs,
+                          void* const* gA, void* const* gbias, const int* I, const int* pin, const int* lat,
+                          const float* scale, const float* bias_mul, const float* latent, int64_t lat_sb,
+                          int64_t lat_sl, float* g_latent, int B, int D, int n_latent);
+
+/* d[b][o] = rsqrt(sum_i s[b][i]^2 * wsq_io[i][o] + eps) for o < O, 0 for O <= o < pout (model.py:251-253) */
+int cagc_demod(cagc_stream_t stream, const float* s, const float* wsq_io, float* d, int B, int pin, int O, int pout,
+               float eps);
+
+/* Reduce the chunk partials of cagc_act_bwd: g_bias[c] = sum_{b,chunk} partial[..][0][c];
+ * gq[b][c] = -1/2 d[b][c]^3 * sum_chunk partial[b][..][1][c] (gradient w.r.t. the demodulation
+ * radicand); nw_part[blk] = sum over the block's 32 channels of partial[..][2][..]
+ * (blk < cagc_act_bwd_finalize_blocks(pitch); the caller adds them up).  Any output may be NULL. */
+int cagc_act_bwd_finalize_blocks(int pitch);
+int cagc_act_bwd_finalize(cagc_stream_t stream, const float* partial, const float* d, float* g_bias, float* gq,
+                          float* nw_part, int B, int chunks, int pitch);
+
+/* g_s[b][i] = sum_chunk mpartial[b][chunk][i] + 2*s[b][i]*sum_o gq[b][o]*wsq_oi[o][i]   (gq NULL: first term only) */
+int cagc_style_grad_finalize(cagc_stream_t stream, const float* mpartial, const float* gq, const float* s,
+                             const float* wsq_oi, float* g_s, int B, int chunks, int pin, int O, int pout);
+
+/* W.grad in the parameter layout: out[o][i][t] = wscale * sum_split wpart[split][t][i][o]
+ *                                              + 2*wscale^2*W[o][i][t] * sum_b gq[b][o]*s[b][i]^2   (gq NULL: first term) */
+int cagc_wgrad_finalize(cagc_stream_t stream, const float* wpart, int nsplits, const float* w, float wscale,
+                        const float* gq, const float* s, int B, int O, int I, int ksize, int pin, int pout,
+                        float* out);
+
+/* ToRGB backward bookkeeping from the chunk partials of cagc_torgb_bwd (t[b][o][i] = sum_chunk partial):
+ *   g_w[o][i] = wscale * sum_b t[b][o][i]*s[b][i];   g_s[b][i] = wscale * sum_o t[b][o][i]*w[o][i]  (pad channels 0) */
+int cagc_torgb_bwd_finalize(cagc_stream_t stream, const float* partial, const float* s, const float* w,
+                            float wscale, float* g_w, float* g_s, int B, int chunks, int cin, int pin, int nout);
+
+/* EqualLinear epilogue (model.py:156-166): out = acc*acc_scale + bias*bias_scale, then (act != 0)
+ * leaky ReLU(alpha) * gain; acc/out [M][N].  Backward: g_acc = g*act'*acc_scale, g_bias[n] = bias_scale*sum_m g*act'. */
+int cagc_linear_bias_act(cagc_stream_t stream, const float* acc, const float* bias, float* out, int M, int N,
+                         float acc_scale, float bias_scale, int act, float alpha, float gain);
+int cagc_linear_bias_act_bwd(cagc_stream_t stream, const float* g, const float* out, float* g_acc, float* g_bias,
+                             int M, int N, float acc_scale, float bias_scale, int act, float alpha, float gain);
 
 /* NHWC-p FIR filter (up=down=1 case of upfirdn2d, used for the Blur after the
  * transposed conv, model.py:270) with the StyledConv epilogue fused:

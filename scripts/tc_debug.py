@@ -13,9 +13,8 @@ dev = 'cuda'
 
 def run(b, cin, cout, h, k, up=False, act=True):
     x = torch.randn(b, cin, h, h, device=dev)
-    s = torch.randn(b, cin, device=dev) * 0.5 + 1
+    s = torch.nn.functional.pad(torch.randn(b, cin, device=dev) * 0.5 + 1, (0, mc.pitch_of(cin) - cin))
     w = torch.randn(1, cout, cin, k, k, device=dev)
-    d = torch.rand(b, cout, device=dev) + 0.5
     ho = h * 2 if up else h
     noise = torch.randn(b, 1, ho, ho, device=dev)
     nw = torch.tensor([0.3], device=dev)
@@ -24,7 +23,7 @@ def run(b, cin, cout, h, k, up=False, act=True):
     outs = []
     for algo in (0, 1):
         with config.use_algo(algo):
-            y = mc.styled_conv(x, s, d, w, noise, nw, bias, 1.0 / (cin * k * k) ** 0.5, upsample=up, fir=fir, pad=(1, 1),
+            y = mc.styled_conv(x, s, w, noise, nw, bias, 1.0 / (cin * k * k) ** 0.5, upsample=up, fir=fir, pad=(1, 1),
                                act=act)
         torch.cuda.synchronize()
         outs.append(y.float().clone())

@@ -143,6 +143,18 @@ def test_flat_bucket_single_process():
     assert torch.equal(b.flat_grad[:6], torch.ones(6)) and torch.equal(b.flat_grad[8:10], torch.ones(2))
     b.zero_grad()
     assert float(b.flat_grad.abs().sum()) == 0.0 and net.weight.grad.data_ptr() == b.flat_grad.data_ptr()
+    # detached protocol: backward hands gradients over, one batched copy packs them into the bucket
+    b.detach_grads()
+    assert net.weight.grad is None
+    (2 * net(torch.ones(1, 3))).sum().backward()
+    assert net.weight.grad.data_ptr() != b.flat_grad.data_ptr()
+    b.pack_grads()
+    assert torch.equal(b.flat_grad[:6], 2 * torch.ones(6)) and torch.equal(b.flat_grad[8:10], 2 * torch.ones(2))
+    assert net.weight.grad.data_ptr() == b.flat_grad.data_ptr()
+    b.detach_grads()
+    net.weight.sum().backward()          # bias not reached: its segment must read zero after packing
+    b.pack_grads()
+    assert torch.equal(b.flat_grad[:6], torch.ones(6)) and float(b.flat_grad[8:10].abs().sum()) == 0.0
 
 
 @pytest.mark.gpu
