@@ -10,12 +10,13 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), 'lib', 'libcagc_b200.so')
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 _p = C.c_void_p
 _i = C.c_int
@@ -53,6 +54,7 @@ SIGNATURES = {
     'cagc_linear_bias_act': (_i, [_p, _p, _p, _p, _i, _i, _f, _f, _i, _f, _f]),
     'cagc_linear_bias_act_bwd': (_i, [_p, _p, _p, _p, _p, _i, _i, _f, _f, _i, _f, _f]),
     'cagc_fir_nhwc': (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _l, _i]),
+    'cagc_fir_nhwc_taps': (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _l, _i]),
     'cagc_act_bwd_chunks': (_i, [_i, _i]),
     'cagc_act_bwd': (_i, [_p, _p, _l, _l, _l, _l, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _l, _i]),
     'cagc_mod_bwd': (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i]),
@@ -115,3 +117,53 @@ def require_cuda(t: torch.Tensor, what: str):
 
 def launch_count() -> int:
     return int(lib.cagc_launch_count())
+
+
+class TensorCache:
+    """Values derived from long-lived tensors (FIR buffers, frozen parameters), keyed by tensor IDENTITY and
+    version counter.  A data pointer is not a safe key: the caching allocator hands the address of a freed
+    temporary to the next tensor of the same size.  Entries die with their tensor (weak references)."""
+
+    def __init__(self):
+        self._d = {}
+
+    def get(self, t: torch.Tensor, tag, make):
+        key = (id(t), tag)
+        hit = self._d.get(key)
+        if hit is not None and hit[0]() is t and hit[1] == t._version:
+            return hit[2]
+        val = make()
+        if val is None:
+            return None
+        d = self._d
+        if len(d) > 8192:
+            d.clear()
+        d[key] = (weakref.ref(t, lambda _r, k=key, d=d: d.pop(k, None)), t._version, val)
+        return val
+
+
+_taps_cache = TensorCache()
+
+
+def host_taps(fir: torch.Tensor):
+    """Host copy (ctypes float array) of a small constant FIR buffer, cached per tensor and version.  Returns
+    None while a CUDA graph is being captured and the buffer has not been seen before (a device->host copy is
+    not capturable): callers then use the entry point that reads the taps from device memory."""
+    def make():
+        if torch.cuda.is_current_stream_capturing():
+            return None
+        vals = fir.detach().float().cpu().reshape(-1).tolist()
+        return (C.c_float * len(vals))(*vals)
+    return _taps_cache.get(fir, 'taps', make)
+
+
+def fir_nhwc(st, x_ptr, fir: torch.Tensor, d, noise, nw, bias, out_ptr, b, h, w, pitch, valid, pads, nstride, act, what):
+    """cagc_fir_nhwc / cagc_fir_nhwc_taps on raw NHWC-p buffers (pads = (x0, x1, y0, y1))."""
+    kh, kw = fir.shape
+    taps = host_taps(fir) if kh * kw <= 16 else None
+    if taps is not None:
+        check(lib.cagc_fir_nhwc_taps(st, x_ptr, fir.data_ptr(), taps, ptr(d), ptr(noise), ptr(nw), ptr(bias), out_ptr,
+                                     b, h, w, pitch, valid, kh, kw, pads[0], pads[1], pads[2], pads[3], nstride, act), what)
+    else:
+        check(lib.cagc_fir_nhwc(st, x_ptr, fir.data_ptr(), ptr(d), ptr(noise), ptr(nw), ptr(bias), out_ptr,
+                                b, h, w, pitch, valid, kh, kw, pads[0], pads[1], pads[2], pads[3], nstride, act), what)

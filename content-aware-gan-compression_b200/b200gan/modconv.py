@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import weakref
 from typing import Optional
 
 import torch
@@ -23,7 +24,7 @@ import torch.nn.functional as F
 from torch.autograd import Function
 from torch.autograd.function import once_differentiable
 
-from ._lib import lib, check, stream_of, require_cuda, ptr
+from ._lib import lib, check, stream_of, require_cuda, ptr, fir_nhwc, TensorCache
 from . import config
 
 
@@ -53,7 +54,7 @@ def as_nhwc_buf(x: torch.Tensor) -> torch.Tensor:
     return buf
 
 
-_frozen = {}
+_frozen = TensorCache()
 
 
 def cached_frozen(param: torch.Tensor, tag, fn):
@@ -63,15 +64,11 @@ def cached_frozen(param: torch.Tensor, tag, fn):
     counter by the fused optimizer kernel)."""
     if param.requires_grad or torch.is_grad_enabled() and param.grad_fn is not None:
         return fn()
-    key = (param.data_ptr(), param._version, tuple(param.shape), tag)
-    hit = _frozen.get(key)
-    if hit is None:
-        if len(_frozen) > 4096:
-            _frozen.clear()
+
+    def make():
         with torch.no_grad():
-            hit = fn()
-        _frozen[key] = hit
-    return hit
+            return fn()
+    return _frozen.get(param, tag, make)
 
 
 def _timed(name, flops, nbytes, fn):
@@ -165,24 +162,18 @@ def _weight_prep(weight, bias, wscale, upsample, tc_fwd, tc_dgrad, pin, pout, wa
     return r
 
 
-_prep_cache = {}
-
-
 def _prepared(weight, bias, wscale, upsample, tc_fwd, tc_dgrad, pin, pout, want_wsq):
     """Frozen parameters (the teacher generator in the KD step): prepared once and reused.  A trainable
     parameter is re-derived every call (its storage may be updated behind torch's version counter by
     the fused optimizer kernel)."""
     if not (_is_frozen(weight) and _is_frozen(bias)):
         return _weight_prep(weight, bias, wscale, upsample, tc_fwd, tc_dgrad, pin, pout, want_wsq)
-    key = (weight.data_ptr(), weight._version, tuple(weight.shape),
-           None if bias is None else (bias.data_ptr(), bias._version), wscale, upsample, tc_fwd, tc_dgrad, want_wsq)
-    hit = _prep_cache.get(key)
-    if hit is None:
-        if len(_prep_cache) > 1024:
-            _prep_cache.clear()
-        hit = _weight_prep(weight, bias, wscale, upsample, tc_fwd, tc_dgrad, pin, pout, want_wsq)
-        _prep_cache[key] = hit
-    return hit
+    tag = ('prep', wscale, upsample, tc_fwd, tc_dgrad, want_wsq, None if bias is None else (id(bias), bias._version))
+    hit = _frozen.get(weight, tag, lambda: (_weight_prep(weight, bias, wscale, upsample, tc_fwd, tc_dgrad, pin, pout,
+                                                        want_wsq), None if bias is None else weakref.ref(bias)))
+    if hit[1] is not None and hit[1]() is not bias:      # the bias object that shared this id is gone: rebuild
+        return _weight_prep(weight, bias, wscale, upsample, tc_fwd, tc_dgrad, pin, pout, want_wsq)
+    return hit[0]
 
 
 class _StyledConvFn(Function):
@@ -258,10 +249,8 @@ class _StyledConvFn(Function):
                            lambda: check(lib.cagc_conv_up(st, x_in.data_ptr(), w_fwd.data_ptr(), s_arg,
                                                           ut.data_ptr(), b, h, w, pin, pout, k, falgo), 'conv_up'))
                     _timed('fir_nhwc', 0.0, 4.0 * b * cout * (hu * wu + ho * wo),
-                           lambda: check(lib.cagc_fir_nhwc(st, ut.data_ptr(), fir.data_ptr(), ptr(d_p), ptr(noise),
-                                                           ptr(nw), ptr(bias_p), out.data_ptr(), b, hu, wu, pout, cout,
-                                                           kh, kw, pad[0], pad[1], pad[0], pad[1], nstride, int(act)),
-                                         'fir_nhwc'))
+                           lambda: fir_nhwc(st, ut.data_ptr(), fir, d_p, noise, nw, bias_p, out.data_ptr(), b, hu, wu,
+                                            pout, cout, (pad[0], pad[1], pad[0], pad[1]), nstride, int(act), 'fir_nhwc'))
                 del ut
         xm = x_in if tc else None      # modulated, TF32-rounded input: A operand of the tensor-pipe wgrad
         ctx.save_for_backward(xb, s_p, d_p, weight, noise, nw, bias_p, out, fir if upsample else None, xm,
@@ -310,8 +299,9 @@ class _StyledConvFn(Function):
                 gp0, gp1 = kh - pad[0] - 1, hu - ho + pad[0]
                 g_t = torch.empty((b, hu, wu, pout), device=dev, dtype=torch.float32)
                 firf = _flipped(fir)
-                check(lib.cagc_fir_nhwc(st, gu.data_ptr(), firf.data_ptr(), None, None, None, None, g_t.data_ptr(),
-                                        b, ho, wo, pout, pout, kh, kw, gp0, gp1, gp0, gp1, 0, 0), 'fir_nhwc(bwd)')
+                _timed('fir_nhwc', 0.0, 4.0 * b * cout * (hu * wu + ho * wo),
+                       lambda: fir_nhwc(st, gu.data_ptr(), firf, None, None, None, None, g_t.data_ptr(), b, ho, wo, pout,
+                                        pout, (gp0, gp1, gp0, gp1), 0, 0, 'fir_nhwc(bwd)'))
                 g_conv = g_t
             else:
                 g_conv = gu
@@ -368,19 +358,9 @@ class _StyledConvFn(Function):
         return (g_x, g_s, g_w, None, g_nw, g_bias, None, None, None, None, None, None, None, None)
 
 
-_flip_cache = {}
-
-
 def _flipped(fir: torch.Tensor) -> torch.Tensor:
     """flip(fir) of a (constant) FIR buffer, computed once per buffer version."""
-    key = (fir.data_ptr(), fir._version, tuple(fir.shape))
-    hit = _flip_cache.get(key)
-    if hit is None:
-        if len(_flip_cache) > 256:
-            _flip_cache.clear()
-        hit = torch.flip(fir, [0, 1]).contiguous()
-        _flip_cache[key] = hit
-    return hit
+    return _frozen.get(fir, 'flip', lambda: torch.flip(fir.detach(), [0, 1]).contiguous())
 
 
 def styled_conv(x, s_p, weight, noise, noise_w, bias, wscale, demodulate=True, eps=1e-8, upsample=False, fir=None,

@@ -42,4 +42,5 @@ int cagc_tc_wgrad(cudaStream_t stream, const float* a, const float* g, float* pa
 // TMA-staged NHWC FIR; returns 1 when it handled the call (result code in *rc), 0 to use the plain kernel
 int cagc_tc_fir_nhwc(cudaStream_t stream, const float* in, const float* fir, const float* out_scale, const float* noise,
                      const float* noise_w, const float* bias, float* out, int B, int in_h, int in_w, int out_h, int out_w,
-                     int pitch, int valid, int pad_x0, int pad_y0, int64_t noise_bstride, int act, int* rc);
+                     int pitch, int valid, int pad_x0, int pad_y0, int64_t noise_bstride, int act, const float* taps_host,
+                     int* rc);

@@ -17,6 +17,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 
 #include "conv_params.cuh"
 
@@ -688,85 +689,298 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 
 
 // ================================================================================================
-// NHWC-p FIR (Blur) with TMA staging: one 4-D box load (32 channels x 35 x 11 pixels, zero fill for the
-// padding) per CTA lands the whole input window in shared memory; 256 threads = 32 pixels x 8 channel
-// quads produce 8 output rows from a register ring, conflict-free 128-bit shared loads, fused
-// demodulation / noise / bias / leaky-ReLU epilogue.  Four CTAs per SM keep loads and math overlapped.
+// Streaming NHWC-p FIR: a CTA owns a (pixel-column strip x channel chunk x row segment) of one sample and
+// marches down the rows.  A producer warp streams ONE input row per stage through a TMA/mbarrier ring
+// (box = chunk channels x (strip + KW - 1) pixels, padding = out-of-bounds zero fill); the 256 consumer
+// threads keep the last KH rows of their KW-pixel window in registers, so every input element is read from
+// shared memory KW times and from L2/HBM once (plus the 3-pixel strip halo).  No vertical halo re-read
+// inside a segment, loads run up to `stages` rows ahead of the math, stores are 128-bit and coalesced.
+// Channel pitches that are not multiples of 32 (the pruned widths 154/77/39 -> 160/80/40) are covered by
+// 32-channel chunks plus one narrower tail chunk with a proportionally longer pixel strip, so all 256
+// threads stay busy there too.
 // ================================================================================================
-constexpr int kFirTX = 32, kFirTR = 8, kFirCC = 32;
+constexpr int kFirMaxStages = 8;
 
-struct FirParams {
+struct FirSP {
     const float* fir;
     const float* out_scale;
     const float* noise;
     const float* noise_w;
     const float* bias;
     float* out;
-    int out_h, out_w, pitch, valid, c_chunks, pad_x0, pad_y0, act;
+    int out_h, out_w, pitch, valid, pad_x0, pad_y0, act;
+    int64_t noise_bstride;
+    int main_w, main_tx;         // channel width of a main chunk and its pixel strip (main_w * main_tx == PXT * 1024)
+    int n_main_chunks, n_main;   // full main chunks; CTAs (x) that work on them
+    int tail_w, tail_tx;         // width of the tail chunk (0: none) and its pixel strip
+    int rows_per_seg, stages, stage_stride;
+    float2 taps2[16];            // PTAPS: flipped taps, each duplicated (k, k) -- live in the constant bank / uniform registers
+};
+
+// two fp32 FMAs per issue slot (sm_100 FFMA2): a.xy += k.xy * v.xy
+__device__ __forceinline__ void fma2(float2& a, const float2 k, const float2 v) {
+    unsigned long long ua = *reinterpret_cast<unsigned long long*>(&a);
+    const unsigned long long uk = *reinterpret_cast<const unsigned long long*>(&k);
+    const unsigned long long uv = *reinterpret_cast<const unsigned long long*>(&v);
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(ua) : "l"(uk), "l"(uv));
+    a = *reinterpret_cast<float2*>(&ua);
+}
+
+// PXT: adjacent output pixels per thread (sliding window of PXT + KW - 1 shared-memory loads per row);
+// PTAPS: taps passed by value in the parameter block (uniform registers) instead of being read from `fir`.
+// 256 threads, all consumers; thread 0 also runs the TMA ring (it refills the stage of row r-1 with row
+// r+S-1 before it waits for row r), so two CTAs fit the register file of an SM.
+template <int KH, int KW, int PXT, bool PTAPS>
+__global__ void __launch_bounds__(256, 2) fir_nhwc_stream_kernel(const __grid_constant__ CUtensorMap map_main,
+                                                                 const __grid_constant__ CUtensorMap map_tail,
+                                                                 const __grid_constant__ FirSP p) {
+    static_assert(KH * KW <= 16 && KH == 4, "tap table holds 16 entries; the row loop is unrolled by KH == 4");
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[2 * kFirMaxStages];
+    __shared__ float skf[KH * KW];
+    const uint32_t base_u32 = (smem_u32(smem_raw) + 127u) & ~127u;
+    const uint8_t* base_ptr = smem_raw + (base_u32 - smem_u32(smem_raw));
+    const int S = p.stages;
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (kFirMaxStages + s); };
+
+    const bool tail = (int)blockIdx.x >= p.n_main;
+    int cw, tx_n, c0, x0;
+    if (!tail) {
+        cw = p.main_w; tx_n = p.main_tx;
+        c0 = ((int)blockIdx.x % p.n_main_chunks) * cw;
+        x0 = ((int)blockIdx.x / p.n_main_chunks) * tx_n;
+    } else {
+        cw = p.tail_w; tx_n = p.tail_tx;
+        c0 = p.n_main_chunks * p.main_w;
+        x0 = ((int)blockIdx.x - p.n_main) * tx_n;
+    }
+    const CUtensorMap* map = tail ? &map_tail : &map_main;
+    const int y0 = blockIdx.y * p.rows_per_seg;
+    const int rows_out = min(p.rows_per_seg, p.out_h - y0);
+    const int rows_in = rows_out + KH - 1;
+    const int b = blockIdx.z;
+    const uint32_t stage_bytes = (uint32_t)(tx_n + KW - 1) * cw * 4;
+    const int tx_c = x0 - p.pad_x0, ty_c = y0 - p.pad_y0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 8);      // one arrival per warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const int pre = min(S - 1, rows_in);
+        for (int r = 0; r < pre; ++r) {      // fill the ring: rows 0 .. S-2
+            mbar_expect_tx(full_bar(r), stage_bytes);
+            tma_load_4d(base_u32 + (uint32_t)r * p.stage_stride, map, full_bar(r), c0, tx_c, ty_c + r, b);
+        }
+    }
+    if (!PTAPS && threadIdx.x < KH * KW) {
+        const int ky = threadIdx.x / KW, kx = threadIdx.x % KW;
+        skf[threadIdx.x] = p.fir[(KH - 1 - ky) * KW + (KW - 1 - kx)];
+    }
+    __syncthreads();
+
+    float2 kf2[KH * KW];
+#pragma unroll
+    for (int i = 0; i < KH * KW; ++i) kf2[i] = PTAPS ? p.taps2[i] : make_float2(skf[i], skf[i]);
+    const int q4 = cw >> 2;
+    const int g = threadIdx.x / q4, c4 = threadIdx.x - g * q4;
+    const int px0 = g * PXT;
+    const bool active = px0 < tx_n;
+    const int c = c0 + c4 * 4;
+    const int lane = threadIdx.x & 31;
+    float4 scale4 = make_float4(1.f, 1.f, 1.f, 1.f), bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float nw = 0.f;
+    if (active) {
+        if (p.out_scale) scale4 = ldg4(p.out_scale + (int64_t)b * p.pitch + c);
+        if (p.bias) bias4 = ldg4(p.bias + c);
+        if (p.noise) nw = __ldg(p.noise_w);
+    }
+    bool ok[PXT];
+#pragma unroll
+    for (int pp = 0; pp < PXT; ++pp) ok[pp] = active && (px0 + pp < tx_n) && (x0 + px0 + pp < p.out_w);
+    const bool edge = c + 3 >= p.valid;
+    const float* sbase = reinterpret_cast<const float*>(base_ptr) + (active ? (px0 * cw + c4 * 4) : 0);
+    const int sstride = p.stage_stride >> 2;
+    // running output / noise pointers of this thread's first pixel (advanced one image row per emitted row)
+    float* optr = p.out + (((int64_t)b * p.out_h + y0) * p.out_w + (x0 + px0)) * p.pitch + c;
+    const int64_t orow = (int64_t)p.out_w * p.pitch;
+    const float* nptr = p.noise ? p.noise + (int64_t)b * p.noise_bstride + (int64_t)y0 * p.out_w + (x0 + px0) : nullptr;
+
+    // acc[k][pp] = output row (k mod KH), pixel pp, in flight: input row r adds its vertical tap i = r - oy to
+    // rows oy = r-KH+1 .. r (same fma order per output as a plain (i, j) double loop)
+    float2 acc[KH][PXT][2];
+#pragma unroll
+    for (int i = 0; i < KH; ++i)
+#pragma unroll
+        for (int pp = 0; pp < PXT; ++pp) acc[i][pp][0] = acc[i][pp][1] = make_float2(0.f, 0.f);
+    int s = 0, prev_s = 0;
+    uint32_t ph = 0, prev_ph = 0;
+
+    // one input row; Q = r mod KH (compile time), FIRST = the first KH rows of the segment (r == Q)
+    auto row = [&](int r, auto qc, auto firstc) {
+        constexpr int Q = decltype(qc)::value;
+        constexpr bool FIRST = decltype(firstc)::value;
+        if (threadIdx.x == 0 && r + S - 1 < rows_in) {
+            const int st = FIRST && Q == 0 ? S - 1 : prev_s;
+            if (!(FIRST && Q == 0)) mbar_wait(empty_bar(st), prev_ph);     // every warp is done with row r-1
+            mbar_expect_tx(full_bar(st), stage_bytes);
+            tma_load_4d(base_u32 + (uint32_t)st * p.stage_stride, map, full_bar(st), c0, tx_c, ty_c + r + S - 1, b);
+        }
+        mbar_wait(full_bar(s), ph);
+        const float* src = sbase + s * sstride;
+        float4 win[PXT + KW - 1];
+#pragma unroll
+        for (int j = 0; j < PXT + KW - 1; ++j) win[j] = ld4(src + j * cw);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty_bar(s));
+        prev_s = s; prev_ph = ph;
+        if (++s == S) { s = 0; ph ^= 1u; }
+#pragma unroll
+        for (int i = 0; i < KH; ++i) {
+            if (FIRST && Q - i < 0) continue;           // output row above this segment
+#pragma unroll
+            for (int pp = 0; pp < PXT; ++pp)
+#pragma unroll
+                for (int j = 0; j < KW; ++j) {
+                    const float4 v = win[pp + j];
+                    fma2(acc[(Q - i + KH) % KH][pp][0], kf2[i * KW + j], make_float2(v.x, v.y));
+                    fma2(acc[(Q - i + KH) % KH][pp][1], kf2[i * KW + j], make_float2(v.z, v.w));
+                }
+        }
+        if (!FIRST || Q == KH - 1) {
+            float nz[PXT];
+#pragma unroll
+            for (int pp = 0; pp < PXT; ++pp) nz[pp] = 0.f;
+            if (p.noise) {
+#pragma unroll
+                for (int pp = 0; pp < PXT; ++pp)
+                    if (ok[pp]) nz[pp] = nw * __ldg(nptr + pp);
+                nptr += p.out_w;
+            }
+#pragma unroll
+            for (int pp = 0; pp < PXT; ++pp) {
+                const float2 a0 = acc[(Q + 1) % KH][pp][0], a1 = acc[(Q + 1) % KH][pp][1];
+                acc[(Q + 1) % KH][pp][0] = acc[(Q + 1) % KH][pp][1] = make_float2(0.f, 0.f);
+                float v[4] = {fmaf(a0.x, scale4.x, nz[pp] + bias4.x), fmaf(a0.y, scale4.y, nz[pp] + bias4.y),
+                              fmaf(a1.x, scale4.z, nz[pp] + bias4.z), fmaf(a1.y, scale4.w, nz[pp] + bias4.w)};
+                if (p.act) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) v[j] = lrelu_sqrt2(v[j]);
+                }
+                if (edge) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (c + j >= p.valid) v[j] = 0.f;
+                }
+                if (ok[pp]) st4(optr + (int64_t)pp * p.pitch, make_float4(v[0], v[1], v[2], v[3]));
+            }
+            optr += orow;
+        }
+    };
+    using std::integral_constant;
+    row(0, integral_constant<int, 0>{}, integral_constant<bool, true>{});      // rows_in >= KH always
+    row(1, integral_constant<int, 1>{}, integral_constant<bool, true>{});
+    row(2, integral_constant<int, 2>{}, integral_constant<bool, true>{});
+    row(3, integral_constant<int, 3>{}, integral_constant<bool, true>{});
+    for (int r0 = KH; r0 < rows_in; r0 += KH) {
+        row(r0, integral_constant<int, 0>{}, integral_constant<bool, false>{});
+        if (r0 + 1 >= rows_in) break;
+        row(r0 + 1, integral_constant<int, 1>{}, integral_constant<bool, false>{});
+        if (r0 + 2 >= rows_in) break;
+        row(r0 + 2, integral_constant<int, 2>{}, integral_constant<bool, false>{});
+        if (r0 + 3 >= rows_in) break;
+        row(r0 + 3, integral_constant<int, 3>{}, integral_constant<bool, false>{});
+    }
+}
+
+// ================================================================================================
+// Register-streaming NHWC-p FIR without shared memory: one thread per float4 of the flattened (x, c) output
+// row, marching down a row segment.  The KW-pixel window of the next input row is loaded (128-bit,
+// read-only path; the KW-fold horizontal overlap is served by L1) while the current row is accumulated
+// into the KH output rows it contributes to.  A warp touches 512 contiguous bytes per load.
+// ================================================================================================
+struct FirLP {
+    const float* in;
+    const float* fir;
+    const float* out_scale;
+    const float* noise;
+    const float* noise_w;
+    const float* bias;
+    float* out;
+    int in_h, in_w, out_h, out_w, pitch, valid, pad_x0, pad_y0, act, rows_per_seg;
     int64_t noise_bstride;
 };
 
 template <int KH, int KW>
-__global__ void __launch_bounds__(256, 3) fir_nhwc_tma_kernel(const __grid_constant__ CUtensorMap map_in,
-                                                              const FirParams p) {
-    constexpr int BW = kFirTX + KW - 1, BH = kFirTR + KH - 1;
-    extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bar;
+__global__ void __launch_bounds__(256, 2) fir_nhwc_ldg_kernel(const FirLP p) {
     __shared__ float skf[KH * KW];
-    const uint32_t tile = (smem_u32(smem_raw) + 127u) & ~127u;
-    const float* tile_ptr = reinterpret_cast<const float*>(smem_raw + (tile - smem_u32(smem_raw)));
-    const int cchunk = blockIdx.x % p.c_chunks, xt = blockIdx.x / p.c_chunks;
-    const int x0 = xt * kFirTX, y0 = blockIdx.y * kFirTR, b = blockIdx.z, c0 = cchunk * kFirCC;
-    const uint32_t bar_a = smem_u32(&bar);
-    if (threadIdx.x == 0) {
-        mbar_init(bar_a, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        mbar_expect_tx(bar_a, BW * BH * kFirCC * 4);
-        tma_load_4d(tile, &map_in, bar_a, c0, x0 - p.pad_x0, y0 - p.pad_y0, b);
-    }
     if (threadIdx.x < KH * KW) {
         const int ky = threadIdx.x / KW, kx = threadIdx.x % KW;
         skf[threadIdx.x] = p.fir[(KH - 1 - ky) * KW + (KW - 1 - kx)];
     }
     __syncthreads();
+    const int c4n = p.pitch >> 2;
+    const int pos = blockIdx.x * 256 + threadIdx.x;
+    if (pos >= p.out_w * c4n) return;
+    const int ox = pos / c4n, c = (pos - ox * c4n) * 4;
+    const int b = blockIdx.z;
+    const int y0 = blockIdx.y * p.rows_per_seg;
+    const int rows_out = min(p.rows_per_seg, p.out_h - y0);
+    const int rows_in = rows_out + KH - 1;
     float kf[KH * KW];
 #pragma unroll
     for (int i = 0; i < KH * KW; ++i) kf[i] = skf[i];
-
-    const int c4 = threadIdx.x & 7, tx = threadIdx.x >> 3;
-    const int c = c0 + c4 * 4, ox = x0 + tx;
-    const bool live = (ox < p.out_w) && (c < p.pitch);
     float4 scale4 = make_float4(1.f, 1.f, 1.f, 1.f), bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    float nw = 0.f;
-    if (live) {
-        if (p.out_scale) scale4 = ldg4(p.out_scale + (int64_t)b * p.pitch + c);
-        if (p.bias) bias4 = ldg4(p.bias + c);
-        if (p.noise) nw = __ldg(p.noise_w);
-    }
-    mbar_wait(bar_a, 0);
-
-    const float* base = tile_ptr + tx * kFirCC + c4 * 4;
-    float4 ring[KH][KW];
+    if (p.out_scale) scale4 = ldg4(p.out_scale + (int64_t)b * p.pitch + c);
+    if (p.bias) bias4 = ldg4(p.bias + c);
+    const float nw = p.noise ? __ldg(p.noise_w) : 0.f;
+    const int ix0 = ox - p.pad_x0;
+    const float* src = p.in + (int64_t)b * p.in_h * p.in_w * p.pitch + (int64_t)ix0 * p.pitch + c;
+    bool xok[KW];
 #pragma unroll
-    for (int r = 0; r < BH; ++r) {
+    for (int j = 0; j < KW; ++j) xok[j] = (ix0 + j >= 0) && (ix0 + j < p.in_w);
+    auto load_row = [&](int r, float4* w) {
+        const int iy = y0 - p.pad_y0 + r;
+        const bool rowok = (r < rows_in) && iy >= 0 && iy < p.in_h;
+        const float* rp = src + (int64_t)iy * p.in_w * p.pitch;
 #pragma unroll
-        for (int j = 0; j < KW; ++j) ring[r % KH][j] = ld4(base + (r * BW + j) * kFirCC);
-        if (r >= KH - 1) {
-            const int q = r - (KH - 1);
-            const int oy = y0 + q;
-            if (live && oy < p.out_h) {
-                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < KW; ++j)
+            w[j] = (rowok && xok[j]) ? ldg4(rp + (int64_t)j * p.pitch) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    float4 acc4[KH];
 #pragma unroll
-                for (int i = 0; i < KH; ++i)
+    for (int i = 0; i < KH; ++i) acc4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 nxt[KW];
+    load_row(0, nxt);
+    for (int r0 = 0; r0 < rows_in; r0 += KH) {
 #pragma unroll
-                    for (int j = 0; j < KW; ++j) {
-                        const float k = kf[i * KW + j];
-                        const float4 v = ring[(q + i) % KH][j];
-                        acc.x = fmaf(k, v.x, acc.x);
-                        acc.y = fmaf(k, v.y, acc.y);
-                        acc.z = fmaf(k, v.z, acc.z);
-                        acc.w = fmaf(k, v.w, acc.w);
-                    }
+        for (int q = 0; q < KH; ++q) {
+            const int r = r0 + q;
+            if (r >= rows_in) break;
+            float4 win[KW];
+#pragma unroll
+            for (int j = 0; j < KW; ++j) win[j] = nxt[j];
+            load_row(r + 1, nxt);
+#pragma unroll
+            for (int i = 0; i < KH; ++i) {
+                if (r - i < 0) continue;
+                float4& a = acc4[(q - i + KH) % KH];
+#pragma unroll
+                for (int j = 0; j < KW; ++j) {
+                    const float k = kf[i * KW + j];
+                    a.x = fmaf(k, win[j].x, a.x);
+                    a.y = fmaf(k, win[j].y, a.y);
+                    a.z = fmaf(k, win[j].z, a.z);
+                    a.w = fmaf(k, win[j].w, a.w);
+                }
+            }
+            if (r >= KH - 1) {
+                const int oy = y0 + r - (KH - 1);
+                const float4 acc = acc4[(q + 1) % KH];
+                acc4[(q + 1) % KH] = make_float4(0.f, 0.f, 0.f, 0.f);
                 float v[4] = {acc.x * scale4.x, acc.y * scale4.y, acc.z * scale4.z, acc.w * scale4.w};
                 if (p.noise) {
                     const float nz = nw * __ldg(p.noise + (int64_t)b * p.noise_bstride + (int64_t)oy * p.out_w + ox);
@@ -991,35 +1205,105 @@ int cagc_tc_wgrad(cudaStream_t stream, const float* a, const float* g, float* pa
 // returns 1 if the TMA path took the call, 0 if the caller should use the plain kernel, <0 / >1 on error
 int cagc_tc_fir_nhwc(cudaStream_t stream, const float* in, const float* fir, const float* out_scale, const float* noise,
                      const float* noise_w, const float* bias, float* out, int B, int in_h, int in_w, int out_h, int out_w,
-                     int pitch, int valid, int pad_x0, int pad_y0, int64_t noise_bstride, int act, int* rc) {
+                     int pitch, int valid, int pad_x0, int pad_y0, int64_t noise_bstride, int act, const float* taps_host,
+                     int* rc) {
     using namespace cagc::tc;
     *rc = 0;
-    if (pitch < 32 || B > 65535) return 0;
+    if (pitch % 4 != 0 || B > 65535) return 0;
+    const char* impl = getenv("CAGC_FIR_IMPL");          // tuning knobs (development)
+    const bool use_ldg = (impl && impl[0] == 'l') || pitch % 8 != 0;
+    auto pick_segs = [&](int64_t per_seg, int min_rows) {
+        // enough CTAs for ~4 waves of 2 CTAs per SM, but at least `min_rows` output rows per segment (3 halo rows each)
+        int want = 8 * kNumSMs;
+        if (const char* e = getenv("CAGC_FIR_CTAS")) want = atoi(e);
+        int sg = (int)std::min<int64_t>(ceil_div<int64_t>(want, per_seg), std::max(1, out_h / min_rows));
+        return sg < 1 ? 1 : sg;
+    };
+    if (use_ldg) {
+        FirLP q{};
+        q.in = in; q.fir = fir; q.out_scale = out_scale; q.noise = noise; q.noise_w = noise_w; q.bias = bias; q.out = out;
+        q.in_h = in_h; q.in_w = in_w; q.out_h = out_h; q.out_w = out_w; q.pitch = pitch; q.valid = valid;
+        q.pad_x0 = pad_x0; q.pad_y0 = pad_y0; q.act = act; q.noise_bstride = noise_bstride;
+        const int gx = ceil_div(out_w * (pitch / 4), 256);
+        int segs = pick_segs((int64_t)gx * B, 16);
+        q.rows_per_seg = ceil_div(out_h, segs);
+        segs = ceil_div(out_h, q.rows_per_seg);
+        if (segs > 65535) return 0;
+        fir_nhwc_ldg_kernel<4, 4><<<dim3(gx, segs, B), 256, 0, stream>>>(q);
+        *rc = launched("fir_nhwc_ldg_kernel");
+        return 1;
+    }
     EncodeTiledFn encode = get_encode();
     if (!encode) return 0;
-    CUtensorMap map;
+    FirSP p{};
+    p.fir = fir; p.out_scale = out_scale; p.noise = noise; p.noise_w = noise_w; p.bias = bias; p.out = out;
+    p.out_h = out_h; p.out_w = out_w; p.pitch = pitch; p.valid = valid;
+    p.pad_x0 = pad_x0; p.pad_y0 = pad_y0; p.act = act; p.noise_bstride = noise_bstride;
+    constexpr int PXT = 2;
+    // chunk width: the widest of 128 / 64 / 32 channels that divides the pitch (measured: +5..40% on 256..512
+    // channel tensors, longer contiguous runs per TMA row); ragged pitches use 32 + a tail chunk
+    p.main_w = pitch % 128 == 0 ? 128 : pitch % 64 == 0 ? 64 : 32;
+    if (const char* e = getenv("CAGC_FIR_CW")) p.main_w = atoi(e);
+    p.main_tx = PXT * 1024 / p.main_w;
+    p.n_main_chunks = pitch / p.main_w;
+    p.tail_w = pitch % p.main_w;
+    p.tail_tx = p.tail_w ? std::min(252, PXT * 1024 / p.tail_w) / PXT * PXT : 0;   // TMA box <= 256 pixels
+    p.n_main = p.n_main_chunks * ceil_div(out_w, p.main_tx);
+    const int n_tail = p.tail_w ? ceil_div(out_w, p.tail_tx) : 0;
+    int segs = pick_segs((int64_t)(p.n_main + n_tail) * B, 16);
+    p.rows_per_seg = ceil_div(out_h, segs);
+    segs = ceil_div(out_h, p.rows_per_seg);
+    if (segs > 65535) return 0;
+    p.stages = std::min(6, p.rows_per_seg + 3);        // 6 x 8.5 KB: two or three CTAs per SM
+    if (const char* e = getenv("CAGC_FIR_STAGES")) p.stages = std::max(2, std::min(kFirMaxStages, atoi(e)));
+    int sbytes = p.n_main_chunks ? (p.main_tx + 3) * p.main_w * 4 : 0;
+    if (p.tail_w) sbytes = std::max(sbytes, (p.tail_tx + 3) * p.tail_w * 4);
+    p.stage_stride = (sbytes + 127) & ~127;
+    if (taps_host)
+        for (int i = 0; i < 16; ++i) {
+            const float k = taps_host[15 - i];            // flipped: true convolution
+            p.taps2[i] = make_float2(k, k);
+        }
+
+    CUtensorMap map_main, map_tail;
     cuuint64_t dims[4] = {(cuuint64_t)pitch, (cuuint64_t)in_w, (cuuint64_t)in_h, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)pitch * 4, (cuuint64_t)in_w * pitch * 4, (cuuint64_t)in_h * in_w * pitch * 4};
-    cuuint32_t box[4] = {(cuuint32_t)kFirCC, (cuuint32_t)(kFirTX + 3), (cuuint32_t)(kFirTR + 3), 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
-    if (encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(in), dims, strides, box, es,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-        return 0;
-    FirParams p{};
-    p.fir = fir; p.out_scale = out_scale; p.noise = noise; p.noise_w = noise_w; p.bias = bias; p.out = out;
-    p.out_h = out_h; p.out_w = out_w; p.pitch = pitch; p.valid = valid; p.c_chunks = ceil_div(pitch, kFirCC);
-    p.pad_x0 = pad_x0; p.pad_y0 = pad_y0; p.act = act; p.noise_bstride = noise_bstride;
-    const size_t smem = (size_t)(kFirTX + 3) * (kFirTR + 3) * kFirCC * 4 + 128;
+    auto enc = [&](CUtensorMap* m, int cw, int tx) {
+        cuuint32_t box[4] = {(cuuint32_t)cw, (cuuint32_t)(tx + 3), 1, 1};
+        return encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(in), dims, strides, box, es,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    };
+    if (p.n_main_chunks && !enc(&map_main, p.main_w, p.main_tx)) return 0;
+    if (p.tail_w && !enc(&map_tail, p.tail_w, p.tail_tx)) return 0;
+    if (!p.n_main_chunks) map_main = map_tail;
+    if (!p.tail_w) map_tail = map_main;
+    const size_t smem = (size_t)p.stages * p.stage_stride + 128;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(fir_nhwc_tma_kernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) { *rc = fail((int)e, "fir_nhwc[tma]: cudaFuncSetAttribute failed"); return 1; }
+        cudaError_t e = cudaFuncSetAttribute(fir_nhwc_stream_kernel<4, 4, PXT, true>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(fir_nhwc_stream_kernel<4, 4, PXT, false>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        // ask for the largest shared-memory carve-out: the default heuristic sized it for ONE resident CTA
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(fir_nhwc_stream_kernel<4, 4, PXT, true>,
+                                     cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(fir_nhwc_stream_kernel<4, 4, PXT, false>,
+                                     cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) { *rc = fail((int)e, "fir_nhwc[stream]: cudaFuncSetAttribute failed"); return 1; }
         attr_set = true;
     }
-    dim3 grid(ceil_div(out_w, kFirTX) * p.c_chunks, ceil_div(out_h, kFirTR), B);
-    fir_nhwc_tma_kernel<4, 4><<<grid, 256, smem, stream>>>(map, p);
-    *rc = launched("fir_nhwc_tma_kernel");
+    if (smem > 100 * 1024) return 0;
+    dim3 grid(p.n_main + n_tail, segs, B);
+    if (taps_host)
+        fir_nhwc_stream_kernel<4, 4, PXT, true><<<grid, 256, smem, stream>>>(map_main, map_tail, p);
+    else
+        fir_nhwc_stream_kernel<4, 4, PXT, false><<<grid, 256, smem, stream>>>(map_main, map_tail, p);
+    *rc = launched("fir_nhwc_stream_kernel");
     return 1;
 }
 

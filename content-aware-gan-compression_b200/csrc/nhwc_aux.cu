@@ -419,9 +419,10 @@ using namespace cagc;
 
 extern "C" {
 
-int cagc_fir_nhwc(cagc_stream_t stream_, const float* in, const float* fir, const float* out_scale, const float* noise,
-                  const float* noise_w, const float* bias, float* out, int B, int in_h, int in_w, int pitch, int valid,
-                  int kh, int kw, int pad_x0, int pad_x1, int pad_y0, int pad_y1, int64_t noise_bstride, int act) {
+static int fir_nhwc_impl(cagc_stream_t stream_, const float* in, const float* fir, const float* taps_host,
+                         const float* out_scale, const float* noise, const float* noise_w, const float* bias, float* out,
+                         int B, int in_h, int in_w, int pitch, int valid, int kh, int kw, int pad_x0, int pad_x1,
+                         int pad_y0, int pad_y1, int64_t noise_bstride, int act) {
     cudaStream_t stream = (cudaStream_t)stream_;
     CAGC_REQUIRE(in && fir && out, "fir_nhwc: null pointer");
     CAGC_REQUIRE(pitch > 0 && pitch % 4 == 0, "fir_nhwc: pitch must be a positive multiple of 4");
@@ -433,7 +434,7 @@ int cagc_fir_nhwc(cagc_stream_t stream_, const float* in, const float* fir, cons
     {
         int rc = 0;
         if (cagc_tc_fir_nhwc(stream, in, fir, out_scale, noise, noise_w, bias, out, B, in_h, in_w, out_h, out_w, pitch,
-                             valid, pad_x0, pad_y0, noise_bstride, act, &rc))
+                             valid, pad_x0, pad_y0, noise_bstride, act, taps_host, &rc))
             return rc;
     }
     CAGC_REQUIRE(B <= 65535, "fir_nhwc: batch too large");
@@ -442,6 +443,22 @@ int cagc_fir_nhwc(cagc_stream_t stream_, const float* in, const float* fir, cons
     fir_nhwc_kernel<4, 4, TR><<<grid, 256, 0, stream>>>(in, fir, out_scale, noise, noise_w, bias, out, in_h, in_w, out_h,
                                                        out_w, pitch, valid, pad_x0, pad_y0, noise_bstride, act);
     return launched("fir_nhwc_kernel");
+}
+
+int cagc_fir_nhwc(cagc_stream_t stream, const float* in, const float* fir, const float* out_scale, const float* noise,
+                  const float* noise_w, const float* bias, float* out, int B, int in_h, int in_w, int pitch, int valid,
+                  int kh, int kw, int pad_x0, int pad_x1, int pad_y0, int pad_y1, int64_t noise_bstride, int act) {
+    return fir_nhwc_impl(stream, in, fir, nullptr, out_scale, noise, noise_w, bias, out, B, in_h, in_w, pitch, valid, kh,
+                         kw, pad_x0, pad_x1, pad_y0, pad_y1, noise_bstride, act);
+}
+
+int cagc_fir_nhwc_taps(cagc_stream_t stream, const float* in, const float* fir, const float* taps_host,
+                       const float* out_scale, const float* noise, const float* noise_w, const float* bias, float* out,
+                       int B, int in_h, int in_w, int pitch, int valid, int kh, int kw, int pad_x0, int pad_x1,
+                       int pad_y0, int pad_y1, int64_t noise_bstride, int act) {
+    CAGC_REQUIRE(taps_host, "fir_nhwc_taps: null host taps");
+    return fir_nhwc_impl(stream, in, fir, taps_host, out_scale, noise, noise_w, bias, out, B, in_h, in_w, pitch, valid, kh,
+                         kw, pad_x0, pad_x1, pad_y0, pad_y1, noise_bstride, act);
 }
 
 int cagc_act_bwd_chunks(int H, int W) { return pixel_chunks(H * W); }

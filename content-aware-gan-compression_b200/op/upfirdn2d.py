@@ -7,7 +7,7 @@ kernel, up and down swapped and the pads of op/upfirdn2d.py:111-116.
 import torch
 from torch.autograd import Function
 
-from b200gan._lib import lib, check, stream_of, require_cuda
+from b200gan._lib import lib, check, stream_of, require_cuda, fir_nhwc
 
 
 def _is_nhwc(x):
@@ -45,9 +45,8 @@ def _launch(x4, kernel, up, down, pad):
     if nhwc:
         # channels-last storage is exactly the NHWC-p layout with pitch == C
         with torch.cuda.device(x4.device):
-            check(lib.cagc_fir_nhwc(stream_of(x4), x4.data_ptr(), kernel.data_ptr(), None, None, None, None,
-                                    out.data_ptr(), n, in_h, in_w, c, c, kh, kw, pad_x0, pad_x1, pad_y0, pad_y1, 0, 0),
-                  'upfirdn2d(nhwc)')
+            fir_nhwc(stream_of(x4), x4.data_ptr(), kernel, None, None, None, None, out.data_ptr(), n, in_h, in_w, c, c,
+                     (pad_x0, pad_x1, pad_y0, pad_y1), 0, 0, 'upfirdn2d(nhwc)')
         return out
     with torch.cuda.device(x4.device):
         check(lib.cagc_upfirdn2d(stream_of(x4), x4.data_ptr(), kernel.data_ptr(), out.data_ptr(),

@@ -37,7 +37,7 @@ typedef void* cagc_stream_t; /* cudaStream_t */
 #define CAGC_E_UNSUPPORTED (-2) /* shape outside what the kernels implement */
 
 /* bump when a signature changes; the Python loader checks it */
-#define CAGC_ABI_VERSION 11
+#define CAGC_ABI_VERSION 12
 
 int cagc_abi_version(void);
 const char* cagc_last_error(void);
@@ -219,6 +219,14 @@ int cagc_fir_nhwc(cagc_stream_t stream, const float* in, const float* fir, const
                   const float* noise, const float* noise_w, const float* bias, float* out,
                   int B, int in_h, int in_w, int pitch, int valid, int kh, int kw,
                   int pad_x0, int pad_x1, int pad_y0, int pad_y1, int64_t noise_bstride, int act);
+
+/* Same with the kh*kw taps ALSO given on the host (row-major, as in `fir`): they travel in the kernel
+ * parameter block (uniform registers) instead of being re-read from device memory by every thread.
+ * `fir` must hold the same values (the fallback kernels read it). */
+int cagc_fir_nhwc_taps(cagc_stream_t stream, const float* in, const float* fir, const float* taps_host,
+                       const float* out_scale, const float* noise, const float* noise_w, const float* bias,
+                       float* out, int B, int in_h, int in_w, int pitch, int valid, int kh, int kw,
+                       int pad_x0, int pad_x1, int pad_y0, int pad_y1, int64_t noise_bstride, int act);
 
 /* Backward of the StyledConv epilogue a = lrelu(d*u + nw*noise + bias)*sqrt2 (or of the bare
  * demodulation y = d*u when act == 0) on NHWC-p tensors:

@@ -510,6 +510,25 @@ def test_tcgen05_generator_vs_golden(golden_dir, mods):
     close(img, ref, 1e-2, 'tc generator image')
 
 
+@pytest.mark.parametrize('c,h,w,pad', [(8, 19, 23, (2, 2)), (24, 33, 70, (1, 1)), (40, 257, 257, (1, 1)),
+                                       (80, 129, 129, (1, 1)), (160, 65, 65, (2, 2)), (32, 300, 40, (2, 2)),
+                                       (128, 64, 64, (1, 1)), (12, 20, 20, (1, 1)), (72, 5, 3, (2, 2))])
+def test_fir_nhwc_streaming_kernel(mods, c, h, w, pad):
+    """Channels-last 4x4 FIR (the row-streaming TMA kernel: 32-channel chunks + narrower tail chunk, row
+    segments, strip halos) against the oracle for the pitches the pruned generator produces."""
+    op, O = mods['op'], mods['O']
+    torch.manual_seed(c * 1000 + h)
+    b = 2 if h * w * c < 2000000 else 1
+    x = torch.randn(b, c, h, w)
+    k = O.fir_kernel_2d([1, 3, 3, 1]) * 4
+    k[0, 1] += 0.03                     # not symmetric: catches flips / transposes
+    k[2, 3] -= 0.02
+    ref = O.upfirdn2d(x.double(), k, pad=pad)
+    xc = x.cuda().contiguous(memory_format=torch.channels_last)
+    y = op.upfirdn2d(xc, k.float().cuda(), pad=pad)
+    close(y, ref, TOL_BW, f'nhwc stream fir c={c}')
+
+
 def test_upfirdn2d_channels_last_and_discriminator(mods):
     """Channels-last storage goes through the NHWC FIR kernel; a channels-last Discriminator equals the
     oracle (its convolutions are library calls; fp32 forced for the comparison)."""
