@@ -124,6 +124,43 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, float* v) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// One elected lane of a converged warp.  The TMA / MMA warps keep their control flow warp-uniform and put only
+// the asynchronous instruction itself under the election: every address / descriptor computation then stays on
+// the uniform datapath, and the single-thread issue loop (the real bound of narrow-N tcgen05 tiles: ~150 cycles
+// per MMA when the descriptors were rebuilt in vector registers by a lone lane) shrinks to a few instructions.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+// low / high words of the K-major SWIZZLE_128B descriptor (see make_desc_sw128): only the 14-bit start-address
+// field of the low word changes between MMAs, so stepping along K (+32 bytes) or M (+128 rows) is a 32-bit add
+constexpr uint32_t kDescHiSw128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t desc_lo_sw128(uint32_t saddr) { return ((saddr >> 4) & 0x3fffu) | (1u << 16); }
+__device__ __forceinline__ void tc_mma_tf32_lh(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                               uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// the (up to) four K = 8 steps of one 32-channel stage for one (A tile, B tile) pair
+__device__ __forceinline__ void mma_stage_k(uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, int kk, bool fresh) {
+    if (kk == 4) {
+        tc_mma_tf32_lh(d, a_lo, kDescHiSw128, b_lo, kDescHiSw128, idesc, fresh ? 0u : 1u);
+        tc_mma_tf32_lh(d, a_lo + 2, kDescHiSw128, b_lo + 2, kDescHiSw128, idesc, 1u);
+        tc_mma_tf32_lh(d, a_lo + 4, kDescHiSw128, b_lo + 4, kDescHiSw128, idesc, 1u);
+        tc_mma_tf32_lh(d, a_lo + 6, kDescHiSw128, b_lo + 6, kDescHiSw128, idesc, 1u);
+    } else {
+        for (int k = 0; k < kk; ++k)
+            tc_mma_tf32_lh(d, a_lo + 2 * k, kDescHiSw128, b_lo + 2 * k, kDescHiSw128, idesc, (fresh && k == 0) ? 0u : 1u);
+    }
+}
+
 // K-major, 128-byte swizzle shared-memory matrix descriptor: 8-row groups of 1024 bytes
 // (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout [61,64))
 __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
@@ -202,46 +239,42 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
     if (warp == 0) {
         // =============================== TMA producer ===============================
-        if (lane == 0) {
-            for (int it = 0; it < total; ++it) {
-                const int s = it % S;
-                const uint32_t ph = (uint32_t)(it / S) & 1u;
-                mbar_wait(empty_bar(s), ph ^ 1u);
-                const int tap = it / nk, kc = it - tap * nk;
-                const Tap tp = p.taps[tap];
+        for (int it = 0; it < total; ++it) {
+            const int s = it % S;
+            const uint32_t ph = (uint32_t)(it / S) & 1u;
+            mbar_wait(empty_bar(s), ph ^ 1u);
+            const int tap = it / nk, kc = it - tap * nk;
+            const Tap tp = p.taps[tap];
+            if (elect_one()) {
                 mbar_expect_tx(full_bar(s), stage_bytes);
                 for (int j = 0; j < MT; ++j)
                     tma_load_4d(a_addr(s, j), &map_a, full_bar(s), kc * kChunkK, x0s[j] * p.in_stride + tp.dx,
                                 y0s[j] * p.in_stride + tp.dy, b0s[j]);
                 tma_load_3d(b_addr(s), &map_b, full_bar(s), kc * kChunkK, n0, tp.slab);
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
         // =============================== MMA issuer =================================
-        if (lane == 0) {
-            // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32, K-major both, N>>3, M>>4
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n_mma >> 3) << 17) |
-                                   ((uint32_t)(kTileM >> 4) << 24);
-            for (int it = 0; it < total; ++it) {
-                const int s = it % S;
-                const uint32_t ph = (uint32_t)(it / S) & 1u;
-                mbar_wait(full_bar(s), ph);
-                tc_fence_after();
-                const int kc = it % nk;
-                int kk = (p.k_valid - kc * kChunkK + 7) >> 3;   // 8-wide tf32 MMAs with real data
-                if (kk > 4) kk = 4;
-                const uint64_t bd = make_desc_sw128(b_addr(s));
-                for (int j = 0; j < MT; ++j) {
-                    const uint64_t ad = make_desc_sw128(a_addr(s, j));
-                    for (int k = 0; k < kk; ++k) {
-                        // advance 8 tf32 = 32 bytes along K inside the swizzle row: +2 in 16-byte units
-                        tc_mma_tf32(tmem_acc + (uint32_t)(j * n_mma), ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k),
-                                    idesc, (it > 0 || k > 0) ? 1u : 0u);
-                    }
-                }
+        // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32, K-major both, N>>3, M>>4
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n_mma >> 3) << 17) |
+                               ((uint32_t)(kTileM >> 4) << 24);
+        for (int it = 0; it < total; ++it) {
+            const int s = it % S;
+            const uint32_t ph = (uint32_t)(it / S) & 1u;
+            mbar_wait(full_bar(s), ph);
+            tc_fence_after();
+            const int kc = it % nk;
+            int kk = (p.k_valid - kc * kChunkK + 7) >> 3;   // 8-wide tf32 MMAs with real data
+            if (kk > 4) kk = 4;
+            const uint32_t b_lo = desc_lo_sw128(b_addr(s));
+            if (elect_one()) {
+                for (int j = 0; j < MT; ++j)
+                    mma_stage_k(tmem_acc + (uint32_t)(j * n_mma), desc_lo_sw128(a_addr(s, j)), b_lo, idesc, kk, it == 0);
                 tc_commit(empty_bar(s));   // frees the smem stage once these MMAs have read it
+                if (it == total - 1) tc_commit(acc_bar);            // accumulator complete
             }
-            tc_commit(acc_bar);            // accumulator complete
+            __syncwarp();
         }
     } else {
         // =============================== epilogue ===================================
@@ -384,56 +417,54 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     };
 
     if (warp == 0) {
-        if (lane == 0) {
-            int s = 0;
-            uint32_t ph = 0;
-            for (int item = blockIdx.x; item < items; item += gridDim.x) {
-                int x0s[2], y0s[2], b0s[2], n0, n_mma;
-                decode(item, x0s, y0s, b0s, n0, n_mma);
-                for (int it = 0; it < per_item; ++it) {
-                    mbar_wait(empty_bar(s), ph ^ 1u);
-                    const int tap = it / nk, kc = it - tap * nk;
-                    const Tap tp = p.taps[tap];
+        int s = 0;
+        uint32_t ph = 0;
+        for (int item = blockIdx.x; item < items; item += gridDim.x) {
+            int x0s[2], y0s[2], b0s[2], n0, n_mma;
+            decode(item, x0s, y0s, b0s, n0, n_mma);
+            for (int it = 0; it < per_item; ++it) {
+                mbar_wait(empty_bar(s), ph ^ 1u);
+                const int tap = it / nk, kc = it - tap * nk;
+                const Tap tp = p.taps[tap];
+                if (elect_one()) {
                     mbar_expect_tx(full_bar(s), stage_bytes);
                     for (int j = 0; j < MT; ++j)
                         tma_load_4d(a_addr(s, j), &map_a, full_bar(s), kc * kChunkK, x0s[j] * p.in_stride + tp.dx,
                                     y0s[j] * p.in_stride + tp.dy, b0s[j]);
                     tma_load_3d(b_addr(s), &map_b, full_bar(s), kc * kChunkK, n0, tp.slab);
-                    if (++s == S) { s = 0; ph ^= 1u; }
                 }
+                __syncwarp();
+                if (++s == S) { s = 0; ph ^= 1u; }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            int s = 0, acc = 0;
-            uint32_t ph = 0, aph = 0;
-            for (int item = blockIdx.x; item < items; item += gridDim.x) {
-                int x0s[2], y0s[2], b0s[2], n0, n_mma;
-                decode(item, x0s, y0s, b0s, n0, n_mma);
-                const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n_mma >> 3) << 17) |
-                                       ((uint32_t)(kTileM >> 4) << 24);
-                mbar_wait(tempty_bar(acc), aph ^ 1u);        // epilogue has drained this accumulator buffer
+        int s = 0, acc = 0;
+        uint32_t ph = 0, aph = 0;
+        for (int item = blockIdx.x; item < items; item += gridDim.x) {
+            int x0s[2], y0s[2], b0s[2], n0, n_mma;
+            decode(item, x0s, y0s, b0s, n0, n_mma);
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n_mma >> 3) << 17) |
+                                   ((uint32_t)(kTileM >> 4) << 24);
+            mbar_wait(tempty_bar(acc), aph ^ 1u);        // epilogue has drained this accumulator buffer
+            tc_fence_after();
+            const uint32_t d0 = tmem_acc + (uint32_t)(acc * acc_stride);
+            for (int it = 0; it < per_item; ++it) {
+                mbar_wait(full_bar(s), ph);
                 tc_fence_after();
-                const uint32_t d0 = tmem_acc + (uint32_t)(acc * acc_stride);
-                for (int it = 0; it < per_item; ++it) {
-                    mbar_wait(full_bar(s), ph);
-                    tc_fence_after();
-                    const int kc = it % nk;
-                    int kk = (p.k_valid - kc * kChunkK + 7) >> 3;
-                    if (kk > 4) kk = 4;
-                    const uint64_t bd = make_desc_sw128(b_addr(s));
-                    for (int j = 0; j < MT; ++j) {
-                        const uint64_t ad = make_desc_sw128(a_addr(s, j));
-                        for (int k = 0; k < kk; ++k)
-                            tc_mma_tf32(d0 + (uint32_t)(j * p.n_tile), ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc,
-                                        (it > 0 || k > 0) ? 1u : 0u);
-                    }
+                const int kc = it % nk;
+                int kk = (p.k_valid - kc * kChunkK + 7) >> 3;
+                if (kk > 4) kk = 4;
+                const uint32_t b_lo = desc_lo_sw128(b_addr(s));
+                if (elect_one()) {
+                    for (int j = 0; j < MT; ++j)
+                        mma_stage_k(d0 + (uint32_t)(j * p.n_tile), desc_lo_sw128(a_addr(s, j)), b_lo, idesc, kk, it == 0);
                     tc_commit(empty_bar(s));
-                    if (++s == S) { s = 0; ph ^= 1u; }
+                    if (it == per_item - 1) tc_commit(tfull_bar(acc));
                 }
-                tc_commit(tfull_bar(acc));
-                if (++acc == 2) { acc = 0; aph ^= 1u; }
+                __syncwarp();
+                if (++s == S) { s = 0; ph ^= 1u; }
             }
+            if (++acc == 2) { acc = 0; aph ^= 1u; }
         }
     } else {
         const int q = warp & 3;
@@ -492,6 +523,236 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(acc));
             if (++acc == 2) { acc = 0; aph ^= 1u; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(tmem_cols) : "memory");
+    }
+}
+
+// ================================================================================================
+// Halo-tile variant: the activation window of a (R rows x TW pixels) output tile -- including the halo the
+// taps reach into -- is loaded ONCE per 32-channel chunk as a single TMA box of (R + dyspan) x (TW + dxspan)
+// pixels; its pixels sit in shared memory in raster order, one 128-byte swizzled row each.  Every tap is then
+// the SAME tile seen through a descriptor whose start address is shifted by (dy*Wt + dx) rows: tcgen05 derives
+// the 128-byte swizzle from absolute shared-memory address bits, so a start row that is not aligned to the
+// 8-row swizzle atom is legal (measured: scripts/probe/umma_shift_probe.cu, exact for every shift).  The M
+// dimension of the GEMM is the raster range of the tile (Wt = TW + dxspan positions per row; the dxspan
+// positions per row that fall on halo columns produce accumulator rows nobody stores).
+// Operand traffic per output pixel drops from ntaps x (once per tap) to (R+dyspan)(TW+dxspan)/(R*TW) ~ 1.3x,
+// which is what bounds the narrow, HBM-class student layers (K = 9 taps x 2..5 chunks).
+// Weights stream per (chunk, tap) through their own ring.  Persistent, one CTA per SM, TMEM accumulator
+// double buffered when 2*MT*N <= 512 columns.  Warp roles as above.
+// ================================================================================================
+struct HaloParams {
+    const float* out_scale;
+    const float* noise;
+    const float* noise_w;
+    const float* bias;
+    float* out;
+    int B, Ho, Wo;                  // iteration domain (output pixels of this launch)
+    int TW, R, Wt, rows_box;        // tile width / rows, raster pitch, box rows (R + dyspan)
+    int dx_min, dy_min;
+    int strips, ytiles;             // tiles per sample
+    int mt;                         // 128-row M sub-tiles per tile: ceil(R*Wt / 128)
+    int k_valid, n_pitch, out_valid, n_tile, n_rows;
+    int Hout, Wout, out_stride, out_oy, out_ox;
+    int64_t noise_bstride;
+    int act, ntaps, b_stages, acc_bufs;
+    uint32_t a_bytes, a_stride, b_bytes;   // box bytes, A buffer stride, bytes of one B stage
+    int tap_row[kMaxTaps];          // row shift of tap t inside the halo tile
+    int tap_slab[kMaxTaps];
+};
+
+constexpr int kHaloMaxB = 8;
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    const __grid_constant__ HaloParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[2 * kHaloMaxB + 8];
+    __shared__ uint32_t tmem_base_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t b_base = smem_base + 2u * p.a_stride;
+    const int SB = p.b_stages, MT = p.mt;
+    const uint32_t bar0 = smem_u32(bars);
+    auto bfull = [&](int s) { return bar0 + 8u * s; };
+    auto bempty = [&](int s) { return bar0 + 8u * (kHaloMaxB + s); };
+    auto afull = [&](int a) { return bar0 + 8u * (2 * kHaloMaxB + a); };
+    auto aempty = [&](int a) { return bar0 + 8u * (2 * kHaloMaxB + 2 + a); };
+    auto tfull = [&](int a) { return bar0 + 8u * (2 * kHaloMaxB + 4 + a); };
+    auto tempty = [&](int a) { return bar0 + 8u * (2 * kHaloMaxB + 6 + a); };
+
+    const int acc_stride = MT * p.n_tile;
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < p.acc_bufs * acc_stride) tmem_cols <<= 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < SB; ++s) { mbar_init(bfull(s), 1); mbar_init(bempty(s), 1); }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(afull(a), 1); mbar_init(aempty(a), 1);
+            mbar_init(tfull(a), 1); mbar_init(tempty(a), 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                     "r"(tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_acc = tmem_base_slot;
+
+    const int nk = (p.k_valid + kChunkK - 1) / kChunkK;
+    const int tiles_per_sample = p.strips * p.ytiles;
+    const int m_tiles = tiles_per_sample * p.B;
+    const int n_tiles = (p.n_rows + p.n_tile - 1) / p.n_tile;
+    const int items = m_tiles * n_tiles;
+
+    auto decode = [&](int item, int& x0, int& y0, int& b, int& n0, int& n_mma) {
+        const int n_idx = item / m_tiles;
+        int t = item - n_idx * m_tiles;
+        n0 = n_idx * p.n_tile;
+        n_mma = p.n_tile;
+        const int rem = ((p.n_pitch - n0) + 15) & ~15;
+        if (rem < n_mma) n_mma = rem;
+        b = t / tiles_per_sample;
+        t -= b * tiles_per_sample;
+        y0 = (t / p.strips) * p.R;
+        x0 = (t % p.strips) * p.TW;
+    };
+
+    if (warp == 0) {
+        int s = 0, ab = 0;
+        uint32_t ph = 0, aph = 0;
+        for (int item = blockIdx.x; item < items; item += gridDim.x) {
+            int x0, y0, b, n0, n_mma;
+            decode(item, x0, y0, b, n0, n_mma);
+            for (int kc = 0; kc < nk; ++kc) {
+                mbar_wait(aempty(ab), aph ^ 1u);
+                // one TMA op per image row of the window (a single large box is no faster, and the row ops can
+                // overlap); destinations are 128-byte aligned, which is all the absolute-address swizzle needs
+                if (elect_one()) {
+                    mbar_expect_tx(afull(ab), p.a_bytes);
+                    for (int r = 0; r < p.rows_box; ++r)
+                        tma_load_4d(smem_base + (uint32_t)ab * p.a_stride + (uint32_t)(r * p.Wt) * 128u, &map_a, afull(ab),
+                                    kc * kChunkK, x0 + p.dx_min, y0 + p.dy_min + r, b);
+                }
+                __syncwarp();
+                if (++ab == 2) { ab = 0; aph ^= 1u; }
+                for (int tap = 0; tap < p.ntaps; ++tap) {
+                    mbar_wait(bempty(s), ph ^ 1u);
+                    if (elect_one()) {
+                        mbar_expect_tx(bfull(s), p.b_bytes);
+                        tma_load_3d(b_base + (uint32_t)s * p.b_bytes, &map_b, bfull(s), kc * kChunkK, n0, p.tap_slab[tap]);
+                    }
+                    __syncwarp();
+                    if (++s == SB) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        int s = 0, ab = 0, acc = 0;
+        uint32_t ph = 0, aph = 0, tph = 0;
+        for (int item = blockIdx.x; item < items; item += gridDim.x) {
+            int x0, y0, b, n0, n_mma;
+            decode(item, x0, y0, b, n0, n_mma);
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n_mma >> 3) << 17) |
+                                   ((uint32_t)(kTileM >> 4) << 24);
+            mbar_wait(tempty(acc), tph ^ 1u);
+            tc_fence_after();
+            const uint32_t d0 = tmem_acc + (uint32_t)(acc * acc_stride);
+            for (int kc = 0; kc < nk; ++kc) {
+                mbar_wait(afull(ab), aph);
+                tc_fence_after();
+                int kk = (p.k_valid - kc * kChunkK + 7) >> 3;
+                if (kk > 4) kk = 4;
+                const uint32_t a_buf = smem_base + (uint32_t)ab * p.a_stride;
+                for (int tap = 0; tap < p.ntaps; ++tap) {
+                    mbar_wait(bfull(s), ph);
+                    tc_fence_after();
+                    const uint32_t b_lo = desc_lo_sw128(b_base + (uint32_t)s * p.b_bytes);
+                    const uint32_t a_lo = desc_lo_sw128(a_buf + (uint32_t)p.tap_row[tap] * 128u);
+                    if (elect_one()) {
+                        for (int j = 0; j < MT; ++j)     // next 128 raster rows: +128*128 bytes = +1024 in the address field
+                            mma_stage_k(d0 + (uint32_t)(j * p.n_tile), a_lo + (uint32_t)j * (kTileM * 128u >> 4), b_lo, idesc,
+                                        kk, kc == 0 && tap == 0);
+                        tc_commit(bempty(s));
+                        if (tap == p.ntaps - 1) {
+                            tc_commit(aempty(ab));
+                            if (kc == nk - 1) tc_commit(tfull(acc));
+                        }
+                    }
+                    __syncwarp();
+                    if (++s == SB) { s = 0; ph ^= 1u; }
+                }
+                if (++ab == 2) { ab = 0; aph ^= 1u; }
+            }
+            if (++acc == p.acc_bufs) { acc = 0; tph ^= 1u; }
+        }
+    } else {
+        const int q = warp & 3;
+        const int m = q * 32 + lane;
+        const float nwv = p.noise ? __ldg(p.noise_w) : 0.f;
+        int acc = 0;
+        uint32_t tph = 0;
+        for (int item = blockIdx.x; item < items; item += gridDim.x) {
+            int x0, y0, b, n0, n_mma;
+            decode(item, x0, y0, b, n0, n_mma);
+            mbar_wait(tfull(acc), tph);
+            tc_fence_after();
+            const uint32_t d0 = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * acc_stride);
+            const float* sc = p.out_scale ? p.out_scale + (int64_t)b * p.n_pitch : nullptr;
+            for (int j = 0; j < MT; ++j) {
+                const int pos = j * kTileM + m;              // raster position inside the tile
+                const int ry = pos / p.Wt, rx = pos - ry * p.Wt;
+                const int ox = x0 + rx, oy = y0 + ry;
+                const bool pvalid = (rx < p.TW) && (ry < p.R) && (ox < p.Wo) && (oy < p.Ho);
+                const int yy = oy * p.out_stride + p.out_oy, xx = ox * p.out_stride + p.out_ox;
+                float nz = 0.f;
+                if (p.noise && pvalid) nz = nwv * __ldg(p.noise + (int64_t)b * p.noise_bstride + (int64_t)yy * p.Wout + xx);
+                float* dst = p.out + (((int64_t)b * p.Hout + yy) * p.Wout + xx) * p.n_pitch;
+                for (int c = 0; c < n_mma; c += 16) {
+                    float v[16];
+                    tc_ld16(d0 + (uint32_t)(j * p.n_tile + c), v);
+                    if (!pvalid) continue;
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const int n = n0 + c + g * 4;
+                        if (n >= p.n_pitch) break;
+                        float o[4] = {v[g * 4 + 0], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]};
+                        if (sc) {
+                            const float4 s4 = ldg4(sc + n);
+                            o[0] *= s4.x; o[1] *= s4.y; o[2] *= s4.z; o[3] *= s4.w;
+                        }
+                        if (p.noise) { o[0] += nz; o[1] += nz; o[2] += nz; o[3] += nz; }
+                        if (p.bias) {
+                            const float4 b4 = ldg4(p.bias + n);
+                            o[0] += b4.x; o[1] += b4.y; o[2] += b4.z; o[3] += b4.w;
+                        }
+                        if (p.act) {
+#pragma unroll
+                            for (int jj = 0; jj < 4; ++jj) o[jj] = lrelu_sqrt2(o[jj]);
+                        }
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj)
+                            if (n + jj >= p.out_valid) o[jj] = 0.f;
+                        st4(dst + n, make_float4(o[0], o[1], o[2], o[3]));
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty(acc));
+            if (++acc == p.acc_bufs) { acc = 0; tph ^= 1u; }
         }
     }
 
@@ -620,21 +881,21 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const uint32_t tmem_acc = tmem_base_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
-            const int dya = p.dya[tap], dxa = p.dxa[tap], dyg = p.dyg[tap], dxg = p.dxg[tap];
-            const int a_boxes = min(4, (p.a_pitch - i0 + 31) / 32);
-            for (int it = 0; it < total; ++it) {
-                const int s = it % S;
-                const uint32_t ph = (uint32_t)(it / S) & 1u;
-                mbar_wait(empty_bar(s), ph ^ 1u);
-                int t = t_lo + it;
-                const int tx = t % p.tiles_x;
-                t /= p.tiles_x;
-                const int ty = t % p.tiles_y;
-                const int tb = t / p.tiles_y;
-                const int x0 = tx * p.bw, y0 = ty * p.bh, b0 = tb * p.bb;
-                // only the 32-channel boxes that hold real input channels are loaded; accumulator rows fed
-                // from the untouched shared memory are never stored
+        const int dya = p.dya[tap], dxa = p.dxa[tap], dyg = p.dyg[tap], dxg = p.dxg[tap];
+        const int a_boxes = min(4, (p.a_pitch - i0 + 31) / 32);
+        for (int it = 0; it < total; ++it) {
+            const int s = it % S;
+            const uint32_t ph = (uint32_t)(it / S) & 1u;
+            mbar_wait(empty_bar(s), ph ^ 1u);
+            int t = t_lo + it;
+            const int tx = t % p.tiles_x;
+            t /= p.tiles_x;
+            const int ty = t % p.tiles_y;
+            const int tb = t / p.tiles_y;
+            const int x0 = tx * p.bw, y0 = ty * p.bh, b0 = tb * p.bb;
+            // only the 32-channel boxes that hold real input channels are loaded; accumulator rows fed
+            // from the untouched shared memory are never stored
+            if (elect_one()) {
                 mbar_expect_tx(full_bar(s), (uint32_t)(a_boxes + p.b_boxes) * kBoxBytes);
                 for (int c = 0; c < a_boxes; ++c)
                     tma_load_4d(a_addr(s) + c * kBoxBytes, &map_a, full_bar(s), i0 + 32 * c, x0 + dxa, y0 + dya, b0);
@@ -642,26 +903,31 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     tma_load_4d(b_addr(s) + c * kBoxBytes, &map_g, full_bar(s), 32 * c, x0 * p.g_stride + dxg,
                                 y0 * p.g_stride + dyg, b0);
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // D=f32, A=B=tf32, both MN-major (bits 15, 16), N>>3, M>>4
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
-                                   ((uint32_t)(p.n_mma >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-            for (int it = 0; it < total; ++it) {
-                const int s = it % S;
-                const uint32_t ph = (uint32_t)(it / S) & 1u;
-                mbar_wait(full_bar(s), ph);
-                tc_fence_after();
-#pragma unroll
-                for (int j = 0; j < kWgPix / 8; ++j) {
-                    const uint64_t ad = make_desc_mn_sw128(a_addr(s) + j * 1024);
-                    const uint64_t bd = make_desc_mn_sw128(b_addr(s) + j * 1024);
-                    tc_mma_tf32(tmem_acc, ad, bd, idesc, (it > 0 || j > 0) ? 1u : 0u);
-                }
+        // D=f32, A=B=tf32, both MN-major (bits 15, 16), N>>3, M>>4
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                               ((uint32_t)(p.n_mma >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+        // MN-major descriptor (make_desc_mn_sw128) split in words: LBO = 4 KB box pitch, SBO = 512, 32B-atom swizzle
+        constexpr uint32_t kHi = (512u >> 4) | (1u << 14) | (1u << 29);
+        constexpr uint32_t kLoFlags = (uint32_t)(kBoxBytes >> 4) << 16;
+        for (int it = 0; it < total; ++it) {
+            const int s = it % S;
+            const uint32_t ph = (uint32_t)(it / S) & 1u;
+            mbar_wait(full_bar(s), ph);
+            tc_fence_after();
+            const uint32_t a_lo = ((a_addr(s) >> 4) & 0x3fffu) | kLoFlags, b_lo = ((b_addr(s) >> 4) & 0x3fffu) | kLoFlags;
+            if (elect_one()) {
+                // 8 pixels (K) per MMA = 1024 bytes = +64 in the 16-byte address field
+                tc_mma_tf32_lh(tmem_acc, a_lo, kHi, b_lo, kHi, idesc, it > 0 ? 1u : 0u);
+                tc_mma_tf32_lh(tmem_acc, a_lo + 64, kHi, b_lo + 64, kHi, idesc, 1u);
+                tc_mma_tf32_lh(tmem_acc, a_lo + 128, kHi, b_lo + 128, kHi, idesc, 1u);
+                tc_mma_tf32_lh(tmem_acc, a_lo + 192, kHi, b_lo + 192, kHi, idesc, 1u);
                 tc_commit(empty_bar(s));
+                if (it == total - 1) tc_commit(acc_bar);
             }
-            tc_commit(acc_bar);
+            __syncwarp();
         }
     } else {
         const int q = warp & 3;
@@ -1023,6 +1289,116 @@ static int next_pow2(int v) {
 
 using namespace cagc;
 
+// Halo-tile launch (see conv_tc_halo_kernel).  Returns 1 when it took the call (result in *rc).
+static int try_halo_conv(cudaStream_t stream, const ConvP& c, const char* what, cagc::tc::EncodeTiledFn encode, int* rc) {
+    using namespace cagc::tc;
+    static const int halo_env = [] { const char* e = getenv("CAGC_TC_HALO"); return e ? atoi(e) : 1; }();
+    if (!halo_env || c.in_stride != 1 || c.ntaps < 2 || c.B > 65535) return 0;
+    // default: the narrow (operand-traffic-bound) layers; CAGC_TC_HALO=2 forces every eligible shape
+    // (measured per layer, scripts/layer_times.py: wins for N <= 80 -- 39/77-channel layers and their up-conv phases;
+    //  at N >= 128 the plain kernels' larger MMAs and two-CTA overlap are faster)
+    if (halo_env == 1 && c.n_cols > 80) return 0;
+    const int min_w = [] { const char* e = getenv("CAGC_TC_HALO_MINW"); return e ? atoi(e) : 32; }();
+    if (c.Wo < min_w) return 0;
+    int dxmin = 0, dxmax = 0, dymin = 0, dymax = 0;
+    for (int i = 0; i < c.ntaps; ++i) {
+        dxmin = std::min(dxmin, c.taps[i].dx); dxmax = std::max(dxmax, c.taps[i].dx);
+        dymin = std::min(dymin, c.taps[i].dy); dymax = std::max(dymax, c.taps[i].dy);
+    }
+    const int dxs = dxmax - dxmin, dys = dymax - dymin;
+    HaloParams p{};
+    p.n_rows = (c.n_cols + 15) & ~15;
+    p.n_tile = std::min(256, p.n_rows);
+    const int n_tiles = ceil_div(p.n_rows, p.n_tile);
+    p.TW = std::min(c.Wo, 64);
+    if (const char* e = getenv("CAGC_TC_HALO_TW")) p.TW = std::min(c.Wo, std::max(8, atoi(e)));
+    p.Wt = p.TW + dxs;
+    p.strips = ceil_div(c.Wo, p.TW);
+    const int mt_max = std::min(8, 512 / p.n_tile);
+    p.b_bytes = (uint32_t)p.n_tile * kChunkK * 4;
+    // choose the tile height: best MMA-row / operand-byte efficiency that fits shared memory and TMEM
+    const int smem_budget = 222 * 1024;
+    double best = 0;
+    int bestR = 0;
+    for (int R = 1; R <= std::min(c.Ho, 32); ++R) {
+        const int mt = ceil_div(R * p.Wt, kTileM);
+        if (mt > mt_max) break;
+        const int rows = std::max((R + dys) * p.Wt, mt * kTileM + dys * p.Wt + dxs);
+        const uint32_t a_stride = ((uint32_t)rows * 128u + 1023u) & ~1023u;
+        // the weight ring must be deep enough to cover the TMA round trip of its small per-tap stages
+        if (2 * (int64_t)a_stride + (int64_t)std::min(kHaloMaxB, c.ntaps) * p.b_bytes + 1024 > smem_budget) break;
+        const int ytiles = ceil_div(c.Ho, R);
+        // cost per useful output pixel: MMA rows + (weighted) operand rows, including the ragged last row tile
+        const double useful = (double)c.Ho * c.Wo;
+        const double mma = (double)ytiles * p.strips * mt * kTileM;
+        const double load = (double)ytiles * p.strips * (R + dys) * p.Wt;
+        const bool dbl = 2 * mt * p.n_tile <= 512;
+        const double score = useful / (mma * (dbl ? 1.0 : 1.15) + 0.5 * load);
+        if (score > best) { best = score; bestR = R; }
+    }
+    if (const char* e = getenv("CAGC_TC_HALO_R")) bestR = std::min(bestR ? 32 : 0, atoi(e));
+    if (bestR <= 0) return 0;
+    p.R = bestR;
+    p.mt = ceil_div(p.R * p.Wt, kTileM);
+    if (p.mt > mt_max) return 0;
+    p.rows_box = p.R + dys;
+    p.ytiles = ceil_div(c.Ho, p.R);
+    p.acc_bufs = (2 * p.mt * p.n_tile <= 512) ? 2 : 1;
+    p.a_bytes = (uint32_t)p.rows_box * p.Wt * 128u;
+    const int rows = std::max(p.rows_box * p.Wt, p.mt * kTileM + dys * p.Wt + dxs);
+    p.a_stride = ((uint32_t)rows * 128u + 1023u) & ~1023u;
+    const int64_t left = smem_budget - 1024 - 2 * (int64_t)p.a_stride;
+    p.b_stages = (int)std::min<int64_t>(kHaloMaxB, left / p.b_bytes);
+    if (p.b_stages < 2) return 0;
+    p.out_scale = c.out_scale; p.noise = c.noise; p.noise_w = c.noise_w; p.bias = c.bias; p.out = c.out;
+    p.B = c.B; p.Ho = c.Ho; p.Wo = c.Wo;
+    p.dx_min = dxmin; p.dy_min = dymin;
+    p.k_valid = c.in_pitch; p.n_pitch = c.n_cols; p.out_valid = c.out_valid;
+    p.Hout = c.Hout; p.Wout = c.Wout; p.out_stride = c.out_stride; p.out_oy = c.out_oy; p.out_ox = c.out_ox;
+    p.noise_bstride = c.noise_bstride; p.act = c.act; p.ntaps = c.ntaps;
+    int max_slab = 0;
+    for (int i = 0; i < c.ntaps; ++i) {
+        p.tap_row[i] = (c.taps[i].dy - dymin) * p.Wt + (c.taps[i].dx - dxmin);
+        p.tap_slab[i] = c.taps[i].slab;
+        max_slab = std::max(max_slab, c.taps[i].slab);
+    }
+    CUtensorMap map_a, map_b;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)c.in_pitch, (cuuint64_t)c.Win, (cuuint64_t)c.Hin, (cuuint64_t)c.B};
+        cuuint64_t strides[3] = {(cuuint64_t)c.in_pitch * 4, (cuuint64_t)c.Win * c.in_pitch * 4,
+                                 (cuuint64_t)c.Hin * c.Win * c.in_pitch * 4};
+        cuuint32_t box[4] = {(cuuint32_t)kChunkK, (cuuint32_t)p.Wt, 1, 1};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        if (p.Wt > 256) return 0;
+        CUresult r = encode(&map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(c.in), dims, strides, box, es,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { *rc = fail(CAGC_E_INVALID, "%s: cuTensorMapEncodeTiled(A, halo) failed with %d", what, (int)r); return 1; }
+    }
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)c.in_pitch, (cuuint64_t)p.n_rows, (cuuint64_t)(max_slab + 1)};
+        cuuint64_t strides[2] = {(cuuint64_t)c.in_pitch * 4, (cuuint64_t)p.n_rows * c.in_pitch * 4};
+        cuuint32_t box[3] = {(cuuint32_t)kChunkK, (cuuint32_t)p.n_tile, 1};
+        cuuint32_t es[3] = {1, 1, 1};
+        CUresult r = encode(&map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(c.w), dims, strides, box, es,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { *rc = fail(CAGC_E_INVALID, "%s: cuTensorMapEncodeTiled(B, halo) failed with %d", what, (int)r); return 1; }
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_budget);
+        if (e != cudaSuccess) { *rc = fail((int)e, "%s: cudaFuncSetAttribute failed: %s", what, cudaGetErrorString(e)); return 1; }
+        attr_set = true;
+    }
+    const size_t smem = 2 * (size_t)p.a_stride + (size_t)p.b_stages * p.b_bytes + 1024;
+    const int64_t items = (int64_t)p.strips * p.ytiles * c.B * n_tiles;
+    const unsigned grid = (unsigned)std::min<int64_t>(items, kNumSMs);
+    conv_tc_halo_kernel<<<grid, kThreads, smem, stream>>>(map_a, map_b, p);
+    *rc = launched(what);
+    return 1;
+}
+
 int cagc_tc_conv(cudaStream_t stream, const ConvP& c, const char* what) {
     using namespace cagc::tc;
     CAGC_REQUIRE(c.in_scale == nullptr, "%s: the tcgen05 path takes a pre-modulated input (cagc_modulate)", what);
@@ -1033,6 +1409,10 @@ int cagc_tc_conv(cudaStream_t stream, const ConvP& c, const char* what) {
     if (!encode) return fail(CAGC_E_UNSUPPORTED, "%s: cuTensorMapEncodeTiled not available from the driver", what);
     if ((int64_t)c.B * c.Ho * c.Wo == 0) return 0;
 
+    {
+        int rc = 0;
+        if (try_halo_conv(stream, c, what, encode, &rc)) return rc;
+    }
     TcParams p{};
     p.out_scale = c.out_scale; p.noise = c.noise; p.noise_w = c.noise_w; p.bias = c.bias; p.out = c.out;
     p.B = c.B; p.Ho = c.Ho; p.Wo = c.Wo;
