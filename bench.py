@@ -26,8 +26,8 @@ for p in (PKG, ROOT):
     if p not in sys.path:
         sys.path.insert(0, p)
 
-if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
-    os.environ['NCCL_DEBUG'] = 'WARN'      # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+if os.environ.get('NCCL_DEBUG', '').upper() in ('VERSION', 'WARN'):
+    del os.environ['NCCL_DEBUG']           # both print NCCL's version banner on stdout: rank 0 prints ONE JSON line
 
 import torch  # noqa: E402
 
@@ -245,6 +245,7 @@ def main():
 
     # ---------------- per-kernel CUDA events (roofline): eager steps, events on the launching stream
     prof = config.KernelProfiler()
+    overlap_stream, kd.teacher_stream = kd.teacher_stream, None   # one stream: a kernel's events bracket only itself
     kd.step(lat[0], inject)
     barrier_sync()
     config.set_profiler(prof)
@@ -253,6 +254,7 @@ def main():
         kd.step(lat[i], inject)
     barrier_sync()
     config.set_profiler(None)
+    kd.teacher_stream = overlap_stream
 
     # ---------------- generator slice alone (student f+b, teacher f) for the Amdahl picture
     def slice_step(z):
@@ -347,7 +349,7 @@ def main():
                    'global_batch': B * world, 'parallelism': f'dp{world}',
                    'l2': 'per-step working set (>=4 GB of activations) exceeds the 126 MB L2; no explicit flush',
                    'conv_algo': 'tcgen05-tf32' if algo == config.ALGO_TCGEN05_TF32 else 'simt-fp32',
-                   'launch': 'one CUDA graph per step' if use_graph else 'eager launches',
+                   'launch': ('one CUDA graph per step' if use_graph else 'eager launches') + (', teacher forward on a parallel graph branch' if kd.teacher_stream is not None else ''),
                    'kernel_timing': f'CUDA events around each native launch over {prof_steps} eager steps in this run'},
         'e2e': {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': 2 * B * 512 * 4,
                 'd2h_bytes_per_step': 4},

@@ -8,6 +8,7 @@ LPIPS (VGG16) and the BiSeNet face parser are third-party networks outside the h
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional
 
 import torch
@@ -37,13 +38,29 @@ class KDStep:
         self.device = self.bucket.flat_param.device
         self.t_dev = torch.zeros(1, device=self.device)      # Adam step count, device-resident (graph-safe)
         self.graph = None
+        self.teacher_stream = torch.cuda.Stream(device=self.device) \
+            if (self.device.type == 'cuda' and os.environ.get('CAGC_KD_OVERLAP', '1') != '0') else None
 
     def losses(self, z: List[torch.Tensor], inject_index: int, s_noise=None, t_noise=None):
         """GAN + KD losses; per-layer noise is drawn fresh (train.py:291,151) unless given explicitly."""
+        # The frozen teacher does not depend on the student: its forward runs on a side stream (a parallel
+        # branch of the captured graph) that only waits for the latents, and fills the SMs that the student's
+        # small low-resolution launches leave idle.  Program order stays student -> teacher, so the per-layer
+        # noise draws consume the RNG stream in the reference's order (train.py:291, then :151).
+        main = torch.cuda.current_stream(self.device)
+        ready = main.record_event() if self.teacher_stream is not None else None
         fake = self.student(z, return_rgb_list=True, inject_index=inject_index, noise=s_noise)
+        if self.teacher_stream is not None:
+            self.teacher_stream.wait_event(ready)
+            with torch.cuda.stream(self.teacher_stream), torch.no_grad():
+                real = self.teacher(z, return_rgb_list=True, inject_index=inject_index, noise=t_noise)
+                real[-1].record_stream(main)
+        else:
+            with torch.no_grad():
+                real = self.teacher(z, return_rgb_list=True, inject_index=inject_index, noise=t_noise)
         g_loss = F.softplus(-self.disc(fake[-1].contiguous(memory_format=torch.channels_last))).mean()
-        with torch.no_grad():
-            real = self.teacher(z, return_rgb_list=True, inject_index=inject_index, noise=t_noise)
+        if self.teacher_stream is not None:
+            main.wait_stream(self.teacher_stream)
         s_img, t_img = fake[-1], real[-1]
         if self.mask is not None:
             s_img, t_img = s_img * self.mask, t_img * self.mask

@@ -129,10 +129,11 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const float* __restrict__ 
     constexpr float kInvPos = 0.70710678118654752440f;            // 1/sqrt2
     constexpr float kInvNeg = 0.70710678118654752440f / 0.2f;     // 1/(0.2*sqrt2)
 
+#pragma unroll 2
     for (int p = p_lo + py; p < p_hi; p += PY) {
         const int y = p / W, x = p - y * W;
         const int64_t off = ((int64_t)b * HW + p) * pitch + c;
-        const float4 a4 = ld4(a + off);
+        const float4 a4 = ldg4(a + off);
         float gav[4];
         const float* gp = ga + b * sb + y * sh + x * sw + (int64_t)c * sc;
         if (ga_vec) {
@@ -190,10 +191,11 @@ __global__ void __launch_bounds__(256) mod_bwd_kernel(float* __restrict__ gxt, c
     const int p_lo = chunk * per, p_hi = min(HW, p_lo + per);
     const float4 s4 = ldg4(s + (int64_t)b * pitch + c);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
     for (int p = p_lo + py; p < p_hi; p += PY) {
         const int64_t off = ((int64_t)b * HW + p) * pitch + c;
         float4 g = ld4(gxt + off);
-        const float4 xv = ld4(x + off);
+        const float4 xv = ldg4(x + off);
         acc.x = fmaf(g.x, xv.x, acc.x);
         acc.y = fmaf(g.y, xv.y, acc.y);
         acc.z = fmaf(g.z, xv.z, acc.z);
@@ -249,6 +251,7 @@ __global__ void __launch_bounds__(256) torgb_fwd_kernel(const float* __restrict_
         const bool pvalid = p < p_hi;
         const float* xp = x + ((int64_t)b * HW + (pvalid ? p : p_lo)) * pitch;
         float acc[kRgbMaxOut] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
         for (int c4 = lane8; c4 < c4n; c4 += 8) {
             const float4 xv = ldg4(xp + c4 * 4);
 #pragma unroll
@@ -372,9 +375,10 @@ __global__ void __launch_bounds__(256) bias_act_bwd_rows_kernel(const float* __r
     const int64_t per = ceil_div<int64_t>(rows, chunks);
     const int64_t r_lo = chunk * per, r_hi = min(rows, r_lo + per);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
     for (int64_t r = r_lo + py; r < r_hi; r += PY) {
         const int64_t off = r * C + c;
-        const float4 gv = ld4(g + off), rv = ld4(refer + off);
+        const float4 gv = ldg4(g + off), rv = ldg4(refer + off);
         float4 o;
         o.x = (rv.x > 0.f ? gv.x : gv.x * alpha) * scale;
         o.y = (rv.y > 0.f ? gv.y : gv.y * alpha) * scale;
@@ -466,7 +470,7 @@ int cagc_act_bwd_chunks(int H, int W) { return pixel_chunks(H * W); }
 int cagc_bias_grad_rows_chunks(int64_t rows, int C) {
     if (C % 4 != 0 || C > 1024 || rows < 64) return 0;   // caller reduces grad_in itself
     int64_t c = ceil_div<int64_t>(rows, 512);
-    if (c > 4 * kNumSMs) c = 4 * kNumSMs;
+    if (c > 8 * kNumSMs) c = 8 * kNumSMs;
     return (int)c;
 }
 
