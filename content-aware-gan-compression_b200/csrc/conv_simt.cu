@@ -309,9 +309,12 @@ int cagc_conv_up(cagc_stream_t stream_, const float* in, const float* w_slabs, c
     CAGC_REQUIRE(in && w_slabs && out_t, "conv_up: null pointer");
     CAGC_REQUIRE(ksize >= 2, "conv_up: kernel size must be >= 2");
     const int Hu = 2 * H + ksize - 2, Wu = 2 * W + ksize - 2;
+    ConvP phases[4];
+    int nph = 0;
     for (int py = 0; py < 2; ++py)
         for (int px = 0; px < 2; ++px) {
-            ConvP p{};
+            ConvP& p = phases[nph++];
+            p = ConvP{};
             p.in = in; p.w = w_slabs; p.in_scale = in_scale; p.out = out_t;
             p.B = B; p.Hin = H; p.Win = W; p.in_pitch = in_pitch; p.in_stride = 1;
             p.Ho = (Hu - py + 1) / 2; p.Wo = (Wu - px + 1) / 2;
@@ -320,12 +323,21 @@ int cagc_conv_up(cagc_stream_t stream_, const float* in, const float* w_slabs, c
             for (int ky = py; ky < ksize; ky += 2)
                 for (int kx = px; kx < ksize; kx += 2)
                     p.taps[p.ntaps++] = Tap{-(ky - py) / 2, -(kx - px) / 2, ky * ksize + kx};
-            if (algo == 1) {
-                CAGC_TRY(cagc_tc_conv(stream, p, "conv_up[tc]"));
-            } else {
-                CAGC_TRY(launch_conv(stream, p, "conv_up[simt]"));
-            }
         }
+    // wide layers on the tensor pipe: all four phases as one persistent launch; narrow ones (halo-tile kernel) and
+    // the SIMT engine: phase by phase
+    if (algo == 1 && out_pitch > 80) {
+        int rc = 0;
+        if (cagc_tc_conv_multi(stream, phases, nph, "conv_up[tc,multi]", &rc)) return rc;
+    }
+    for (int i = 0; i < nph; ++i) {
+        if (phases[i].ntaps == 0) continue;
+        if (algo == 1) {
+            CAGC_TRY(cagc_tc_conv(stream, phases[i], "conv_up[tc]"));
+        } else {
+            CAGC_TRY(launch_conv(stream, phases[i], "conv_up[simt]"));
+        }
+    }
     return 0;
 }
 

@@ -29,6 +29,7 @@ constexpr int kTileM = 128;
 constexpr int kChunkK = 32;                      // fp32 elements per 128-byte swizzle row
 constexpr int kABytes = kTileM * kChunkK * 4;    // 16 KB
 constexpr int kMaxStages = 8;
+constexpr int kMaxPhases = 4;
 constexpr int kSmemBudget = 110 * 1024;          // two CTAs per SM
 constexpr int kSmemBudget1 = 220 * 1024;         // one CTA per SM (two M sub-tiles, > 256 TMEM columns)
 
@@ -51,6 +52,13 @@ struct TcParams {
     int mt, tiles_total;        // M sub-tiles (128 pixels each) per CTA sharing one weight tile; number of pixel tiles
     uint32_t b_bytes;           // bytes of one B stage
     Tap taps[kMaxTaps];
+    // persistent kernel only: several "phases" (the four output parities of the stride-2 transposed convolution)
+    // in ONE launch; a phase has its own taps, output lattice and pixel-tile grid.  Work items are enumerated
+    // phase-major (most taps first) and dealt round-robin to the CTAs, which balances the mixed costs.
+    int nphase;
+    int ph_item0[kMaxPhases + 1], ph_tap0[kMaxPhases], ph_ntaps[kMaxPhases];
+    int ph_Ho[kMaxPhases], ph_Wo[kMaxPhases], ph_oy[kMaxPhases], ph_ox[kMaxPhases];
+    int ph_tx[kMaxPhases], ph_ty[kMaxPhases], ph_tiles[kMaxPhases];
 };
 
 // ---------------------------------------------------------------- PTX helpers
@@ -390,14 +398,15 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     const uint32_t tmem_acc = tmem_base_slot;
 
     const int nk = (p.k_valid + kChunkK - 1) / kChunkK;
-    const int per_item = p.ntaps * nk;
-    const int m_super = (p.tiles_total + MT - 1) / MT;
-    const int n_tiles = (p.n_rows + p.n_tile - 1) / p.n_tile;
-    const int items = m_super * n_tiles;
+    const int items = p.ph_item0[p.nphase];
 
-    // sub-tile coordinates of work item `item`
+    // phase, weight tile and sub-tile coordinates of work item `item`
     auto decode = [&](int item, int* x0s, int* y0s, int* b0s, int& n0, int& n_mma) {
-        const int n_idx = item / m_super, m_idx = item - n_idx * m_super;
+        int f = 0;
+        while (f + 1 < p.nphase && item >= p.ph_item0[f + 1]) ++f;
+        const int local = item - p.ph_item0[f];
+        const int m_super = (p.ph_tiles[f] + MT - 1) / MT;
+        const int n_idx = local / m_super, m_idx = local - n_idx * m_super;
         n0 = n_idx * p.n_tile;
         n_mma = p.n_tile;
         const int rem = ((p.n_pitch - n0) + 15) & ~15;
@@ -405,15 +414,16 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             int t = m_idx * MT + j;
-            if (j < MT && t < p.tiles_total) {
-                x0s[j] = (t % p.tiles_x) * p.bw;
-                t /= p.tiles_x;
-                y0s[j] = (t % p.tiles_y) * p.bh;
-                b0s[j] = (t / p.tiles_y) * p.bb;
+            if (j < MT && t < p.ph_tiles[f]) {
+                x0s[j] = (t % p.ph_tx[f]) * p.bw;
+                t /= p.ph_tx[f];
+                y0s[j] = (t % p.ph_ty[f]) * p.bh;
+                b0s[j] = (t / p.ph_ty[f]) * p.bb;
             } else {
                 x0s[j] = 0; y0s[j] = 0; b0s[j] = p.B;
             }
         }
+        return f;
     };
 
     if (warp == 0) {
@@ -421,11 +431,12 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         uint32_t ph = 0;
         for (int item = blockIdx.x; item < items; item += gridDim.x) {
             int x0s[2], y0s[2], b0s[2], n0, n_mma;
-            decode(item, x0s, y0s, b0s, n0, n_mma);
+            const int f = decode(item, x0s, y0s, b0s, n0, n_mma);
+            const int per_item = p.ph_ntaps[f] * nk;
             for (int it = 0; it < per_item; ++it) {
                 mbar_wait(empty_bar(s), ph ^ 1u);
                 const int tap = it / nk, kc = it - tap * nk;
-                const Tap tp = p.taps[tap];
+                const Tap tp = p.taps[p.ph_tap0[f] + tap];
                 if (elect_one()) {
                     mbar_expect_tx(full_bar(s), stage_bytes);
                     for (int j = 0; j < MT; ++j)
@@ -442,7 +453,8 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         uint32_t ph = 0, aph = 0;
         for (int item = blockIdx.x; item < items; item += gridDim.x) {
             int x0s[2], y0s[2], b0s[2], n0, n_mma;
-            decode(item, x0s, y0s, b0s, n0, n_mma);
+            const int f = decode(item, x0s, y0s, b0s, n0, n_mma);
+            const int per_item = p.ph_ntaps[f] * nk;
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n_mma >> 3) << 17) |
                                    ((uint32_t)(kTileM >> 4) << 24);
             mbar_wait(tempty_bar(acc), aph ^ 1u);        // epilogue has drained this accumulator buffer
@@ -477,14 +489,14 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         uint32_t aph = 0;
         for (int item = blockIdx.x; item < items; item += gridDim.x) {
             int x0s[2], y0s[2], b0s[2], n0, n_mma;
-            decode(item, x0s, y0s, b0s, n0, n_mma);
+            const int f = decode(item, x0s, y0s, b0s, n0, n_mma);
             mbar_wait(tfull_bar(acc), aph);
             tc_fence_after();
             const uint32_t d0 = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * acc_stride);
             for (int j = 0; j < MT; ++j) {
                 const int ox = x0s[j] + lx, oy = y0s[j] + ly, b = b0s[j] + lb;
-                const bool pvalid = (ox < p.Wo) && (oy < p.Ho) && (b < p.B);
-                const int yy = oy * p.out_stride + p.out_oy, xx = ox * p.out_stride + p.out_ox;
+                const bool pvalid = (ox < p.ph_Wo[f]) && (oy < p.ph_Ho[f]) && (b < p.B);
+                const int yy = oy * p.out_stride + p.ph_oy[f], xx = ox * p.out_stride + p.ph_ox[f];
                 float nz = 0.f;
                 if (p.noise && pvalid) nz = nwv * __ldg(p.noise + (int64_t)b * p.noise_bstride + (int64_t)yy * p.Wout + xx);
                 float* dst = p.out + (((int64_t)b * p.Hout + yy) * p.Wout + xx) * p.n_pitch;
@@ -1502,6 +1514,11 @@ int cagc_tc_conv(cudaStream_t stream, const ConvP& c, const char* what) {
     const int64_t items = ceil_div<int64_t>(p.tiles_total, p.mt) * ceil_div(p.n_rows, p.n_tile);
     if (persist_env && p.mt * p.n_tile <= 256 && (items >= 6 * kNumSMs || persist_env == 2)) {
         TcParams q = p;
+        q.nphase = 1;
+        q.ph_item0[0] = 0; q.ph_item0[1] = (int)items;
+        q.ph_tap0[0] = 0; q.ph_ntaps[0] = p.ntaps;
+        q.ph_Ho[0] = p.Ho; q.ph_Wo[0] = p.Wo; q.ph_oy[0] = p.out_oy; q.ph_ox[0] = p.out_ox;
+        q.ph_tx[0] = p.tiles_x; q.ph_ty[0] = p.tiles_y; q.ph_tiles[0] = p.tiles_total;
         const uint32_t sb = (uint32_t)q.mt * kABytes + q.b_bytes;
         q.stages = std::max(2, std::min(kMaxStages, (int)((kSmemBudget1 - 1024) / sb)));
         const size_t smem_p = (size_t)q.stages * sb + 1024;
@@ -1516,6 +1533,101 @@ int cagc_tc_conv(cudaStream_t stream, const ConvP& c, const char* what) {
     return launched(what);
 }
 
+
+// All phases of the stride-2 transposed convolution in ONE persistent launch (see TcParams::nphase).  Phases must
+// share input, weights, pitches and output tensor; they differ in taps, output lattice offset and extent.
+// Returns 1 when it took the call (result in *rc), 0 when the caller should launch the phases one by one.
+int cagc_tc_conv_multi(cudaStream_t stream, const ConvP* ph, int nphase, const char* what, int* rc) {
+    using namespace cagc::tc;
+    *rc = 0;
+    static const int multi_env = [] { const char* e = getenv("CAGC_TC_MULTI"); return e ? atoi(e) : 1; }();
+    if (!multi_env || nphase < 2 || nphase > kMaxPhases) return 0;
+    const ConvP& c = ph[0];
+    if (c.in_scale != nullptr || c.in_stride != 1 || c.in_pitch % 8 != 0 || c.n_cols % 8 != 0) return 0;
+    EncodeTiledFn encode = get_encode();
+    if (!encode) return 0;
+    int Hmax = 0, Wmax = 0, taps_total = 0;
+    for (int f = 0; f < nphase; ++f) {
+        Hmax = std::max(Hmax, ph[f].Ho); Wmax = std::max(Wmax, ph[f].Wo);
+        taps_total += ph[f].ntaps;
+    }
+    if ((int64_t)c.B * Hmax * Wmax == 0 || taps_total > kMaxTaps) return 0;
+    TcParams p{};
+    p.out_scale = c.out_scale; p.noise = c.noise; p.noise_w = c.noise_w; p.bias = c.bias; p.out = c.out;
+    p.B = c.B; p.Ho = Hmax; p.Wo = Wmax;
+    p.bw = std::min(16, next_pow2(Wmax));
+    p.bh = std::min(kTileM / p.bw, next_pow2(Hmax));
+    p.bb = kTileM / (p.bw * p.bh);
+    const int tiles_b = ceil_div(c.B, p.bb);
+    p.k_valid = c.in_pitch;
+    p.n_pitch = c.n_cols; p.out_valid = c.out_valid;
+    p.n_rows = (c.n_cols + 15) & ~15;
+    p.n_tile = std::min(256, p.n_rows);
+    const int n_tiles = ceil_div(p.n_rows, p.n_tile);
+    p.mt = (p.n_tile <= 128) ? 2 : 1;
+    if (p.mt * p.n_tile > 256) return 0;                 // needs a double-buffered TMEM accumulator
+    p.Hout = c.Hout; p.Wout = c.Wout; p.out_stride = c.out_stride;
+    p.noise_bstride = c.noise_bstride; p.act = c.act; p.in_stride = 1;
+    p.b_bytes = (uint32_t)p.n_tile * kChunkK * 4;
+    // phases in order of decreasing tap count (round-robin dealing then balances the CTAs)
+    int order[kMaxPhases];
+    for (int f = 0; f < nphase; ++f) order[f] = f;
+    std::sort(order, order + nphase, [&](int a, int b) { return ph[a].ntaps > ph[b].ntaps; });
+    int64_t items = 0;
+    int tap0 = 0, max_slab = 0;
+    p.nphase = nphase;
+    for (int k = 0; k < nphase; ++k) {
+        const ConvP& q = ph[order[k]];
+        p.ph_item0[k] = (int)items;
+        p.ph_tap0[k] = tap0; p.ph_ntaps[k] = q.ntaps;
+        for (int i = 0; i < q.ntaps; ++i) {
+            p.taps[tap0 + i] = q.taps[i];
+            max_slab = std::max(max_slab, q.taps[i].slab);
+        }
+        tap0 += q.ntaps;
+        p.ph_Ho[k] = q.Ho; p.ph_Wo[k] = q.Wo; p.ph_oy[k] = q.out_oy; p.ph_ox[k] = q.out_ox;
+        p.ph_tx[k] = ceil_div(q.Wo, p.bw); p.ph_ty[k] = ceil_div(q.Ho, p.bh);
+        p.ph_tiles[k] = p.ph_tx[k] * p.ph_ty[k] * tiles_b;
+        items += (int64_t)ceil_div(p.ph_tiles[k], p.mt) * n_tiles;
+    }
+    p.ph_item0[nphase] = (int)items;
+    p.ntaps = taps_total;
+    if (items < 2 * kNumSMs || items > 0x7fffffff) return 0;   // tiny layers: the per-phase launches are latency-bound anyway
+    const uint32_t sb = (uint32_t)p.mt * kABytes + p.b_bytes;
+    p.stages = std::max(2, std::min(kMaxStages, (int)((kSmemBudget1 - 1024) / sb)));
+    const size_t smem = (size_t)p.stages * sb + 1024;
+    CUtensorMap map_a, map_b;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)c.in_pitch, (cuuint64_t)c.Win, (cuuint64_t)c.Hin, (cuuint64_t)c.B};
+        cuuint64_t strides[3] = {(cuuint64_t)c.in_pitch * 4, (cuuint64_t)c.Win * c.in_pitch * 4,
+                                 (cuuint64_t)c.Hin * c.Win * c.in_pitch * 4};
+        cuuint32_t box[4] = {(cuuint32_t)kChunkK, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bb};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        CUresult r = encode(&map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(c.in), dims, strides, box, es,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { *rc = fail(CAGC_E_INVALID, "%s: cuTensorMapEncodeTiled(A) failed with %d", what, (int)r); return 1; }
+    }
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)c.in_pitch, (cuuint64_t)p.n_rows, (cuuint64_t)(max_slab + 1)};
+        cuuint64_t strides[2] = {(cuuint64_t)c.in_pitch * 4, (cuuint64_t)p.n_rows * c.in_pitch * 4};
+        cuuint32_t box[3] = {(cuuint32_t)kChunkK, (cuuint32_t)p.n_tile, 1};
+        cuuint32_t es[3] = {1, 1, 1};
+        CUresult r = encode(&map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(c.w), dims, strides, box, es,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { *rc = fail(CAGC_E_INVALID, "%s: cuTensorMapEncodeTiled(B) failed with %d", what, (int)r); return 1; }
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget1);
+        if (e != cudaSuccess) { *rc = fail((int)e, "%s: cudaFuncSetAttribute failed: %s", what, cudaGetErrorString(e)); return 1; }
+        attr_set = true;
+    }
+    conv_tc_persist_kernel<<<kNumSMs, kThreads, smem, stream>>>(map_a, map_b, p);
+    *rc = launched(what);
+    return 1;
+}
 
 int cagc_tc_wgrad_splits(int B, int H, int W, int a_pitch, int g_pitch, int ksize) {
     using namespace cagc::tc;
