@@ -16,7 +16,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), 'lib', 'libcagc_b200.so')
-ABI_VERSION = 12
+ABI_VERSION = 13
 
 _p = C.c_void_p
 _i = C.c_int
@@ -59,7 +59,7 @@ SIGNATURES = {
     'cagc_act_bwd': (_i, [_p, _p, _l, _l, _l, _l, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _l, _i]),
     'cagc_mod_bwd': (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i]),
     'cagc_torgb_fwd': (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _i, _i, _i, _i]),
-    'cagc_torgb_bwd': (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f]),
+    'cagc_torgb_bwd': (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f]),
     'cagc_to_nhwc': (_i, [_p, _p, _l, _l, _l, _l, _p, _i, _i, _i, _i, _i]),
     'cagc_adam_step': (_i, [_p, _p, _p, _p, _p, _l, _f, _f, _f, _f, _f, _f, _f, _p]),
 }

@@ -373,7 +373,7 @@ class _ToRGBFn(Function):
     """rgb = conv1x1(s*x, c*W) + bias + Upsample(skip), output NCHW [B,3,H,W] (model.py:380-395)."""
 
     @staticmethod
-    def forward(ctx, x, s_p, weight, bias, skip, wscale, fir, pad):
+    def forward(ctx, x, s_p, weight, bias, skip, wscale, fir, pad, passthrough=False):
         require_cuda(x, 'ToRGB')
         b, cin, h, w = x.shape
         nout = weight.shape[1]
@@ -402,22 +402,29 @@ class _ToRGBFn(Function):
                                          wscale, fh, fw, pad[0], pad[1]), 'torgb_fwd')
         ctx.save_for_backward(xb, s_p, w2, fir if skip is not None else None)
         ctx.cfg = (b, cin, nout, h, w, pin, wscale, pad, bias is not None, skip is not None)
+        if passthrough:
+            # the activation is handed on to its other consumer THROUGH this node: both of its gradients then
+            # arrive here and are summed inside torgb_bwd instead of by a separate accumulation kernel
+            return out, x
         return out
 
     @staticmethod
     @once_differentiable
-    def backward(ctx, g):
+    def backward(ctx, g, g_through=None):
         xb, s_p, w2, fir = ctx.saved_tensors
         b, cin, nout, h, w, pin, wscale, pad, has_bias, has_skip = ctx.cfg
         dev = xb.device
+        if g is None:       # only the pass-through branch reached the loss
+            return g_through, None, None, None, None, None, None, None, None
         g = g.contiguous()
         with torch.cuda.device(dev):
             st = stream_of(xb)
             gx = torch.empty((b, h, w, pin), device=dev, dtype=torch.float32)
             chunks = lib.cagc_act_bwd_chunks(h, w)
             partial = torch.empty((b, chunks, nout, pin), device=dev, dtype=torch.float32)
-            check(lib.cagc_torgb_bwd(st, g.data_ptr(), xb.data_ptr(), w2.data_ptr(), s_p.data_ptr(), gx.data_ptr(),
-                                     partial.data_ptr(), b, h, w, pin, cin, nout, wscale), 'torgb_bwd')
+            g_add = as_nhwc_buf(g_through) if g_through is not None else None
+            check(lib.cagc_torgb_bwd(st, g.data_ptr(), xb.data_ptr(), w2.data_ptr(), s_p.data_ptr(), ptr(g_add),
+                                     gx.data_ptr(), partial.data_ptr(), b, h, w, pin, cin, nout, wscale), 'torgb_bwd')
             g_w = g_s = g_bias = g_skip = None
             need_s, need_w = ctx.needs_input_grad[1], ctx.needs_input_grad[2]
             if need_s or need_w:
@@ -435,11 +442,12 @@ class _ToRGBFn(Function):
                 gp1 = (h // 2) * 2 - h + pad[0] - 2 + 1
                 g_skip = _launch(g, _flipped(fir), (1, 1), (2, 2), (gp0, gp1, gp0, gp1))
             g_x = nhwc_view(gx, cin) if ctx.needs_input_grad[0] else None
-        return g_x, g_s, g_w, g_bias, g_skip, None, None, None
+        return g_x, g_s, g_w, g_bias, g_skip, None, None, None, None
 
 
-def to_rgb(x, s_p, weight, bias, skip, wscale, fir=None, pad=(0, 0)):
-    return _ToRGBFn.apply(x, s_p, weight, bias, skip, wscale, fir, pad)
+def to_rgb(x, s_p, weight, bias, skip, wscale, fir=None, pad=(0, 0), passthrough=False):
+    """passthrough=True returns (rgb, x'): x' aliases x and carries its gradient back through this node."""
+    return _ToRGBFn.apply(x, s_p, weight, bias, skip, wscale, fir, pad, passthrough)
 
 
 # ------------------------------------------------------------------------------------------------

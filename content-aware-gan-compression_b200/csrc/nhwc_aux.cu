@@ -7,6 +7,8 @@
 // All of them are HBM-bound: one 128-bit access per thread per tensor element, threads contiguous
 // along (pixel, channel), per-thread channel ownership so that the per-channel reductions live in
 // registers, fixed-order (deterministic) partial sums.
+#include <cstdlib>
+
 #include "conv_params.cuh"
 
 namespace cagc {
@@ -225,7 +227,7 @@ __global__ void __launch_bounds__(256) torgb_fwd_kernel(const float* __restrict_
                                                         const float* __restrict__ s, const float* __restrict__ bias,
                                                         const float* __restrict__ skip, const float* __restrict__ fir,
                                                         float* __restrict__ out, int H, int W, int pitch, int cin,
-                                                        int nout, float wscale, int fh, int fw, int pad0) {
+                                                        int nout, float wscale, int fh, int fw, int pad0, int chunk) {
     extern __shared__ __align__(16) float weff[];  // [nout][pitch]
     __shared__ float sfir[64];
     const int b = blockIdx.y;
@@ -243,8 +245,8 @@ __global__ void __launch_bounds__(256) torgb_fwd_kernel(const float* __restrict_
     const int lane8 = threadIdx.x & 7;
     const int grp = threadIdx.x >> 3;  // 32 pixel groups per CTA
     const int c4n = pitch >> 2;
-    const int p_lo = blockIdx.x * kRgbChunk;
-    const int p_hi = min(HW, p_lo + kRgbChunk);
+    const int p_lo = blockIdx.x * chunk;
+    const int p_hi = min(HW, p_lo + chunk);
     const int Hs = H >> 1, Ws = W >> 1;
     for (int pbase = p_lo; pbase < p_hi; pbase += 32) {  // warp-uniform trip count (shuffles below)
         const int p = pbase + grp;
@@ -306,7 +308,8 @@ __global__ void __launch_bounds__(256) torgb_fwd_kernel(const float* __restrict_
 // ToRGB backward: block = (c4n, PY); gx written, per-sample T[o][c] partials
 __global__ void __launch_bounds__(256) torgb_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x,
                                                         const float* __restrict__ w, const float* __restrict__ s,
-                                                        float* __restrict__ gx, float* __restrict__ partial, int HW,
+                                                        const float* __restrict__ gx_add, float* __restrict__ gx,
+                                                        float* __restrict__ partial, int HW,
                                                         int pitch, int cin, int nout, float wscale, int chunks) {
     extern __shared__ float4 red[];  // [PY][nout][c4n]
     const int c4n = blockDim.x, PY = blockDim.y;
@@ -346,6 +349,10 @@ __global__ void __launch_bounds__(256) torgb_bwd_kernel(const float* __restrict_
                 T[o].w = fmaf(gv, xv.w, T[o].w);
             }
         }
+        if (gx_add) {   // gradient that reached the same activation through its other consumer (the next conv)
+            const float4 e = ld4(gx_add + off);
+            o4.x += e.x; o4.y += e.y; o4.z += e.z; o4.w += e.w;
+        }
         st4(gx + off, o4);
     }
 #pragma unroll
@@ -372,12 +379,12 @@ __global__ void __launch_bounds__(256) bias_act_bwd_rows_kernel(const float* __r
     const int c4n = blockDim.x, PY = blockDim.y;
     const int cx = threadIdx.x, py = threadIdx.y, c = cx * 4;
     const int chunk = blockIdx.x;
+    // each block owns a contiguous run of rows (an interleaved / grid-stride deal of the rows was measured 20% SLOWER)
     const int64_t per = ceil_div<int64_t>(rows, chunks);
     const int64_t r_lo = chunk * per, r_hi = min(rows, r_lo + per);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
-    for (int64_t r = r_lo + py; r < r_hi; r += PY) {
-        const int64_t off = r * C + c;
+    for (int64_t r = r_lo + py; r < r_hi; r += PY) {        const int64_t off = r * C + c;
         const float4 gv = ldg4(g + off), rv = ldg4(refer + off);
         float4 o;
         o.x = (rv.x > 0.f ? gv.x : gv.x * alpha) * scale;
@@ -538,14 +545,19 @@ int cagc_torgb_fwd(cagc_stream_t stream_, const float* x, const float* w, const 
     CAGC_REQUIRE(B <= 65535, "torgb_fwd: batch too large");
     const size_t smem = sizeof(float) * nout * pitch;
     CAGC_REQUIRE(smem <= 48 * 1024, "torgb_fwd: pitch too large");
-    dim3 grid(ceil_div(H * W, kRgbChunk), B);
+    // pixels per CTA: enough to amortise the per-CTA effective-weight set-up, while keeping >= ~4 CTAs per SM
+    int chunk = kRgbChunk;
+    static const int max_chunk = [] { const char* e = getenv("CAGC_RGB_CHUNK"); return e ? atoi(e) : 2048; }();
+    while (chunk < max_chunk && (int64_t)ceil_div(H * W, chunk * 2) * B >= 4 * kNumSMs) chunk *= 2;
+    dim3 grid(ceil_div(H * W, chunk), B);
     torgb_fwd_kernel<<<grid, 256, smem, stream>>>(x, w, s, bias, skip, fir, out, H, W, pitch, cin, nout, wscale, fh, fw,
-                                                  pad0);
+                                                  pad0, chunk);
     return launched("torgb_fwd_kernel");
 }
 
-int cagc_torgb_bwd(cagc_stream_t stream_, const float* g, const float* x, const float* w, const float* s, float* gx,
-                   float* partial, int B, int H, int W, int pitch, int cin, int nout, float wscale) {
+int cagc_torgb_bwd(cagc_stream_t stream_, const float* g, const float* x, const float* w, const float* s,
+                   const float* gx_add, float* gx, float* partial, int B, int H, int W, int pitch, int cin, int nout,
+                   float wscale) {
     cudaStream_t stream = (cudaStream_t)stream_;
     CAGC_REQUIRE(g && x && w && s && gx && partial, "torgb_bwd: null pointer");
     CAGC_REQUIRE(pitch > 0 && pitch % 4 == 0 && cin <= pitch, "torgb_bwd: bad pitch");
@@ -556,7 +568,7 @@ int cagc_torgb_bwd(cagc_stream_t stream_, const float* g, const float* x, const 
     const int chunks = pixel_chunks(H * W);
     dim3 grid(chunks, B);
     const size_t smem = sizeof(float4) * blk.y * nout * blk.x;
-    torgb_bwd_kernel<<<grid, blk, smem, stream>>>(g, x, w, s, gx, partial, H * W, pitch, cin, nout, wscale, chunks);
+    torgb_bwd_kernel<<<grid, blk, smem, stream>>>(g, x, w, s, gx_add, gx, partial, H * W, pitch, cin, nout, wscale, chunks);
     return launched("torgb_bwd_kernel");
 }
 

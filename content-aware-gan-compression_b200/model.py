@@ -22,6 +22,10 @@ from b200gan import config as _cfg
 from b200gan import modconv as _mc
 
 
+import os as _os
+_THROUGH = _os.environ.get('CAGC_TORGB_THROUGH', '1') != '0'   # tuning knob (development)
+
+
 class PixelNorm(nn.Module):
     """x * rsqrt(mean(x^2, dim=1) + 1e-8)   (reference model.py:14-24)."""
 
@@ -290,7 +294,9 @@ class ToRGB(nn.Module):
         self.conv = ModulatedConv2d(in_channel, 3, 1, style_dim, demodulate=False)
         self.bias = nn.Parameter(torch.zeros(1, 3, 1, 1))
 
-    def forward(self, input, style, skip=None, return_style_scalars=False, _s=None):
+    def forward(self, input, style, skip=None, return_style_scalars=False, _s=None, _through=False):
+        """_through (private, first-order fused path only): also return the input activation routed through this
+        node, so that the gradients of its two consumers are summed inside the ToRGB backward kernel."""
         conv = self.conv
         if skip is not None:
             up = self.upsample
@@ -304,8 +310,14 @@ class ToRGB(nn.Module):
             out = _mc.to_rgb_composite(input, s, conv.weight, self.bias, skip, conv.scale, fir=fir, pad=pad)
         else:
             s_p = _s if _s is not None else _mc.style_affine(style.unsqueeze(1), [conv.modulation], [0])[0]
-            out = _mc.to_rgb(input, s_p, conv.weight, self.bias, skip, conv.scale, fir=fir, pad=pad)
+            out = _mc.to_rgb(input, s_p, conv.weight, self.bias, skip, conv.scale, fir=fir, pad=pad,
+                             passthrough=_through)
             s = s_p[:, :conv.in_channel]
+            if _through:
+                rgb, x_through = out
+                if return_style_scalars:
+                    return rgb, s.reshape(s.shape[0], 1, conv.in_channel, 1, 1), x_through
+                return rgb, x_through
         if return_style_scalars:
             return out, s.reshape(s.shape[0], 1, conv.in_channel, 1, 1)
         return out
@@ -432,18 +444,31 @@ class Generator(nn.Module):
                 return y
             return layer(x, w_lat, noise=nz, _s=s_of.get(id(layer.conv)))
 
+        # first-order fused path: an activation that feeds both a ToRGB and the next block travels THROUGH the ToRGB
+        # node, which sums the two gradients in its backward kernel (no separate accumulation pass)
+        through = not _cfg.is_second_order() and torch.is_grad_enabled() and _THROUGH
         out = self.input(latent)
         out = styled(self.conv1, out, latent[:, 0], noise[0])
-        skip = self.to_rgb1(out, latent[:, 1], _s=s_of.get(id(self.to_rgb1.conv)))
+        if through and len(self.to_rgbs) > 0:
+            skip, out = self.to_rgb1(out, latent[:, 1], _s=s_of.get(id(self.to_rgb1.conv)), _through=True)
+        else:
+            skip = self.to_rgb1(out, latent[:, 1], _s=s_of.get(id(self.to_rgb1.conv)))
         rgbs = [skip]
 
         i = 1
+        n_blocks = len(self.to_rgbs)
         for blk, to_rgb in enumerate(self.to_rgbs):
             out = styled(self.convs[2 * blk], out, latent[:, i], noise[1 + 2 * blk])
             out = styled(self.convs[2 * blk + 1], out, latent[:, i + 1], noise[2 + 2 * blk])
+            thr = through and blk + 1 < n_blocks
             if return_style_scalars and (i + 3) == latent.shape[1]:   # only the last ToRGB reports (model.py:636-638)
-                skip, sc = to_rgb(out, latent[:, i + 2], skip, True, _s=s_of.get(id(to_rgb.conv)))
+                res = to_rgb(out, latent[:, i + 2], skip, True, _s=s_of.get(id(to_rgb.conv)), _through=thr)
+                skip, sc = res[0], res[1]
                 scalars.append(sc)
+                if thr:
+                    out = res[2]
+            elif thr:
+                skip, out = to_rgb(out, latent[:, i + 2], skip, _s=s_of.get(id(to_rgb.conv)), _through=True)
             else:
                 skip = to_rgb(out, latent[:, i + 2], skip, _s=s_of.get(id(to_rgb.conv)))
             rgbs.append(skip)

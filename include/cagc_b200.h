@@ -37,7 +37,7 @@ typedef void* cagc_stream_t; /* cudaStream_t */
 #define CAGC_E_UNSUPPORTED (-2) /* shape outside what the kernels implement */
 
 /* bump when a signature changes; the Python loader checks it */
-#define CAGC_ABI_VERSION 12
+#define CAGC_ABI_VERSION 13
 
 int cagc_abi_version(void);
 const char* cagc_last_error(void);
@@ -252,10 +252,12 @@ int cagc_mod_bwd(cagc_stream_t stream, float* gxt, const float* x, const float* 
 int cagc_torgb_fwd(cagc_stream_t stream, const float* x, const float* w, const float* s, const float* bias,
                    const float* skip, const float* fir, float* out, int B, int H, int W, int pitch,
                    int cin, int nout, float wscale, int fh, int fw, int pad0, int pad1);
-/* gx[b,p,i] = sum_o weff[b,o,i]*g[b,o,p] (NHWC-p, pad channels zero);
- * partial[b][chunk][o][pitch] = sum_p g[b,o,p]*x[b,p,i]  (caller reduces over chunk) */
+/* gx[b,p,i] = sum_o weff[b,o,i]*g[b,o,p] (+ gx_add[b,p,i] when given: the gradient that reached the same
+ * activation through the next convolution, so autograd needs no separate accumulation pass) (NHWC-p, pad
+ * channels zero);  partial[b][chunk][o][pitch] = sum_p g[b,o,p]*x[b,p,i]  (caller reduces over chunk) */
 int cagc_torgb_bwd(cagc_stream_t stream, const float* g, const float* x, const float* w, const float* s,
-                   float* gx, float* partial, int B, int H, int W, int pitch, int cin, int nout, float wscale);
+                   const float* gx_add, float* gx, float* partial, int B, int H, int W, int pitch, int cin, int nout,
+                   float wscale);
 
 /* NCHW (arbitrary strides) <-> NHWC-p conversion; pad channels zeroed. */
 int cagc_to_nhwc(cagc_stream_t stream, const float* src, int64_t sb, int64_t sc, int64_t sh, int64_t sw,
