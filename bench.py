@@ -293,7 +293,14 @@ def main():
         return
     peaks = load_peaks()
     summ = prof.summary()
-    kernels = {}
+    kernels, layers = {}, {}
+    for name, r in summ.items():
+        if '@' in name:     # per-layer records: kept apart from the per-kernel aggregates
+            layers[name] = {'launches_per_step': r['launches'] / prof_steps,
+                            'avg_launch_us': r['ms'] / max(r['launches'], 1) * 1e3,
+                            'tflops': (r['flops'] / (r['ms'] / 1e3) / 1e12) if r['flops'] and r['ms'] else None,
+                            'gbs': (r['bytes'] / (r['ms'] / 1e3) / 1e9) if r['bytes'] and r['ms'] else None}
+    summ = {k: v for k, v in summ.items() if '@' not in k}
     for name, r in summ.items():
         per = r['ms'] / max(r['launches'], 1)
         kernels[name] = {'launches_per_step': r['launches'] / prof_steps, 'ms_per_step': r['ms'] / prof_steps,
@@ -328,7 +335,17 @@ def main():
         if n in summ and summ[n]['ms']:
             g = summ[n]['bytes'] / (summ[n]['ms'] / 1e3) / 1e9
             hbm[n] = {'bound': 'hbm', 'achieved': g, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
-                      'frac': g / peaks['hbm_gbs']}
+                      'frac': g / peaks['hbm_gbs'],
+                      'note': 'all generator FIR launches of a step, 9x9 .. 257x257 (the small ones are launch-latency bound)'}
+    # the largest FIR call of the step (Blur after the last up-conv) and the heaviest conv layers, each alone
+    fl = {k: v for k, v in layers.items() if k.startswith('fir_nhwc@') and v['gbs']}
+    if fl:
+        k = max(fl, key=lambda k: fl[k]['avg_launch_us'])
+        hbm['fir_nhwc[largest]'] = {'bound': 'hbm', 'layer': k.split('@')[1], 'achieved': fl[k]['gbs'],
+                                    'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': fl[k]['gbs'] / peaks['hbm_gbs'],
+                                    'avg_launch_us': fl[k]['avg_launch_us']}
+    cl = {k: v for k, v in layers.items() if k.startswith('conv_') and v['tflops']}
+    top_layers = {k: cl[k] for k in sorted(cl, key=lambda k: -cl[k]['avg_launch_us'] * cl[k]['launches_per_step'])[:6]}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -362,6 +379,7 @@ def main():
                             'tflops': B * (3 * gf['student'] + gf['teacher']) / slice_ms,
                             'note': 'student f+b + teacher f only, rank 0'},
         'kernels': kernels,
+        'top_conv_layers': top_layers,
     }
     print(json.dumps(line))
 

@@ -71,8 +71,10 @@ def cached_frozen(param: torch.Tensor, tag, fn):
     return _frozen.get(param, tag, make)
 
 
-def _timed(name, flops, nbytes, fn):
-    """Run a native launch, bracketing it with CUDA events when bench.py installed a profiler."""
+def _timed(name, flops, nbytes, fn, shape=None):
+    """Run a native launch, bracketing it with CUDA events when bench.py installed a profiler.  `shape`
+    additionally files the launch under a per-shape key (the roofline of the dominant LAYER, next to the
+    aggregate over all launches of the kernel)."""
     prof = config.profiler()
     if prof is None:
         return fn()
@@ -81,6 +83,8 @@ def _timed(name, flops, nbytes, fn):
     r = fn()
     e1.record()
     prof.add(name, flops, nbytes, e0, e1)
+    if shape is not None:
+        prof.add(f'{name}@{shape}', flops, nbytes, e0, e1)
     return r
 
 
@@ -235,7 +239,7 @@ class _StyledConvFn(Function):
                            lambda: check(lib.cagc_conv_same(st, x_in.data_ptr(), w_fwd.data_ptr(), s_arg,
                                                             ptr(d_p), ptr(noise), ptr(nw), ptr(bias_p), out.data_ptr(),
                                                             b, h, w, pin, pout, cout, k, nstride, int(act), falgo),
-                                         'conv_same'))
+                                         'conv_same'), shape=f'{cin}->{cout}x{h}x{w}')
             else:
                 hu, wu = 2 * h + k - 2, 2 * w + k - 2
                 ut = torch.empty((b, hu, wu, pout), device=dev, dtype=torch.float32)
@@ -247,10 +251,12 @@ class _StyledConvFn(Function):
                     flops = 2.0 * b * h * w * cin * cout * k * k          # transposed conv counted at input res
                     _timed(f'conv_up[algo{falgo}]', flops, 4.0 * b * (h * w * cin + hu * wu * cout),
                            lambda: check(lib.cagc_conv_up(st, x_in.data_ptr(), w_fwd.data_ptr(), s_arg,
-                                                          ut.data_ptr(), b, h, w, pin, pout, k, falgo), 'conv_up'))
+                                                          ut.data_ptr(), b, h, w, pin, pout, k, falgo), 'conv_up'),
+                           shape=f'{cin}->{cout}x{h}x{w}')
                     _timed('fir_nhwc', 0.0, 4.0 * b * cout * (hu * wu + ho * wo),
                            lambda: fir_nhwc(st, ut.data_ptr(), fir, d_p, noise, nw, bias_p, out.data_ptr(), b, hu, wu,
-                                            pout, cout, (pad[0], pad[1], pad[0], pad[1]), nstride, int(act), 'fir_nhwc'))
+                                            pout, cout, (pad[0], pad[1], pad[0], pad[1]), nstride, int(act), 'fir_nhwc'),
+                           shape=f'{cout}x{hu}x{wu}')
                 del ut
         xm = x_in if tc else None      # modulated, TF32-rounded input: A operand of the tensor-pipe wgrad
         ctx.save_for_backward(xb, s_p, d_p, weight, noise, nw, bias_p, out, fir if upsample else None, xm,

@@ -1076,6 +1076,13 @@ __global__ void __launch_bounds__(256, 2) fir_nhwc_stream_kernel(const __grid_co
         if (p.bias) bias4 = ldg4(p.bias + c);
         if (p.noise) nw = __ldg(p.noise_w);
     }
+    // epilogue in 3 instructions per element: lrelu(v)*sqrt2 == max(v', 0.2 v') with v' = sqrt2*v, and the gain is
+    // folded into the demodulation scale, the bias and the noise weight once per thread
+    if (p.act) {
+        scale4.x *= kSqrt2; scale4.y *= kSqrt2; scale4.z *= kSqrt2; scale4.w *= kSqrt2;
+        bias4.x *= kSqrt2; bias4.y *= kSqrt2; bias4.z *= kSqrt2; bias4.w *= kSqrt2;
+        nw *= kSqrt2;
+    }
     bool ok[PXT];
 #pragma unroll
     for (int pp = 0; pp < PXT; ++pp) ok[pp] = active && (px0 + pp < tx_n) && (x0 + px0 + pp < p.out_w);
@@ -1107,6 +1114,16 @@ __global__ void __launch_bounds__(256, 2) fir_nhwc_stream_kernel(const __grid_co
             mbar_expect_tx(full_bar(st), stage_bytes);
             tma_load_4d(base_u32 + (uint32_t)st * p.stage_stride, map, full_bar(st), c0, tx_c, ty_c + r + S - 1, b);
         }
+        // noise of the output row this input row completes: requested before the wait, consumed after the FMAs
+        float nz[PXT];
+#pragma unroll
+        for (int pp = 0; pp < PXT; ++pp) nz[pp] = 0.f;
+        if ((!FIRST || Q == KH - 1) && p.noise) {
+#pragma unroll
+            for (int pp = 0; pp < PXT; ++pp)
+                if (ok[pp]) nz[pp] = __ldg(nptr + pp);
+            nptr += p.out_w;
+        }
         mbar_wait(full_bar(s), ph);
         const float* src = sbase + s * sstride;
         float4 win[PXT + KW - 1];
@@ -1129,24 +1146,15 @@ __global__ void __launch_bounds__(256, 2) fir_nhwc_stream_kernel(const __grid_co
                 }
         }
         if (!FIRST || Q == KH - 1) {
-            float nz[PXT];
-#pragma unroll
-            for (int pp = 0; pp < PXT; ++pp) nz[pp] = 0.f;
-            if (p.noise) {
-#pragma unroll
-                for (int pp = 0; pp < PXT; ++pp)
-                    if (ok[pp]) nz[pp] = nw * __ldg(nptr + pp);
-                nptr += p.out_w;
-            }
 #pragma unroll
             for (int pp = 0; pp < PXT; ++pp) {
                 const float2 a0 = acc[(Q + 1) % KH][pp][0], a1 = acc[(Q + 1) % KH][pp][1];
                 acc[(Q + 1) % KH][pp][0] = acc[(Q + 1) % KH][pp][1] = make_float2(0.f, 0.f);
-                float v[4] = {fmaf(a0.x, scale4.x, nz[pp] + bias4.x), fmaf(a0.y, scale4.y, nz[pp] + bias4.y),
-                              fmaf(a1.x, scale4.z, nz[pp] + bias4.z), fmaf(a1.y, scale4.w, nz[pp] + bias4.w)};
+                float v[4] = {fmaf(a0.x, scale4.x, fmaf(nz[pp], nw, bias4.x)), fmaf(a0.y, scale4.y, fmaf(nz[pp], nw, bias4.y)),
+                              fmaf(a1.x, scale4.z, fmaf(nz[pp], nw, bias4.z)), fmaf(a1.y, scale4.w, fmaf(nz[pp], nw, bias4.w))};
                 if (p.act) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) v[j] = lrelu_sqrt2(v[j]);
+                    for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], kLreluSlope * v[j]);
                 }
                 if (edge) {
 #pragma unroll
