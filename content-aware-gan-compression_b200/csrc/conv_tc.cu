@@ -28,7 +28,7 @@ constexpr int kThreads = 192;
 constexpr int kTileM = 128;
 constexpr int kChunkK = 32;                      // fp32 elements per 128-byte swizzle row
 constexpr int kABytes = kTileM * kChunkK * 4;    // 16 KB
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 12;
 constexpr int kMaxPhases = 4;
 constexpr int kSmemBudget = 110 * 1024;          // two CTAs per SM
 constexpr int kSmemBudget1 = 220 * 1024;         // one CTA per SM (two M sub-tiles, > 256 TMEM columns)
@@ -967,6 +967,151 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 
 
 // ================================================================================================
+// Weight gradient, all taps of a 3x3 same-resolution convolution in ONE CTA: per 32-pixel stage the gradient tile
+// g[32 px][N] is loaded once and the layer-input window a[3 rows][34 px][M] once; tap (dy, dx) is the SAME window
+// seen through an MN-major descriptor shifted by (dy+1)*36 + (dx+1) K rows (absolute-address swizzle, see the
+// probe), accumulating into its own TMEM tile.  Operand traffic per stage: 3*a_boxes + b_boxes TMA boxes instead
+// of 9*(a_boxes + b_boxes) -- the one-tap-per-CTA kernel above is L2-bandwidth bound on exactly that re-read.
+// One CTA per SM (taps_per * n_mma <= 512 TMEM columns), persistent over its split of the pixel tiles.
+// ================================================================================================
+constexpr int kWgRowPitch = 36;                                  // K rows reserved per image row (34 used): 9 x 512 B
+constexpr int kWgABoxBytes = 3 * kWgRowPitch * 128;              // 13824: one 32-channel box of the 3-row window
+
+struct WgAllParams {
+    float* partial;
+    int a_pitch, g_pitch, n_mma, a_boxes, b_boxes;
+    int taps_per, nsplits, tiles_total, tiles_per_split;
+    int tiles_x, tiles_y, stages;
+    uint32_t stage_bytes;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_tc_alltaps_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_g,
+                        const __grid_constant__ WgAllParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 1];
+    __shared__ uint32_t tmem_base_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int S = p.stages;
+    const uint32_t a_bytes = (uint32_t)p.a_boxes * kWgABoxBytes;
+    auto a_addr = [&](int s) { return smem_base + (uint32_t)s * p.stage_bytes; };
+    auto b_addr = [&](int s) { return smem_base + (uint32_t)s * p.stage_bytes + a_bytes; };
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (kMaxStages + s); };
+    const uint32_t acc_bar = bar0 + 8u * (2 * kMaxStages);
+
+    const int i0 = blockIdx.x * kTileM;
+    const int tap0 = blockIdx.y * p.taps_per;
+    const int ntap = min(p.taps_per, 9 - tap0);
+    const int split = blockIdx.z;
+    const int t_lo = split * p.tiles_per_split;
+    const int t_hi = min(p.tiles_total, t_lo + p.tiles_per_split);
+    const int total = t_hi - t_lo;            // host guarantees >= 1
+
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < p.taps_per * p.n_mma) tmem_cols <<= 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        mbar_init(acc_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                     "r"(tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_acc = tmem_base_slot;
+
+    if (warp == 0) {
+        const int a_ld = min(p.a_boxes, (p.a_pitch - i0 + 31) / 32);      // boxes that hold real input channels
+        const uint32_t tx_bytes = (uint32_t)a_ld * 3u * 34u * 128u + (uint32_t)p.b_boxes * kBoxBytes;
+        for (int it = 0; it < total; ++it) {
+            const int s = it % S;
+            const uint32_t ph = (uint32_t)(it / S) & 1u;
+            mbar_wait(empty_bar(s), ph ^ 1u);
+            int t = t_lo + it;
+            const int tx = t % p.tiles_x;
+            t /= p.tiles_x;
+            const int y0 = t % p.tiles_y;
+            const int b0 = t / p.tiles_y;
+            const int x0 = tx * kWgPix;
+            if (elect_one()) {
+                mbar_expect_tx(full_bar(s), tx_bytes);
+                for (int c = 0; c < a_ld; ++c)
+                    for (int r = 0; r < 3; ++r)
+                        tma_load_4d(a_addr(s) + c * kWgABoxBytes + r * (kWgRowPitch * 128), &map_a, full_bar(s), i0 + 32 * c,
+                                    x0 - 1, y0 + r - 1, b0);
+                for (int c = 0; c < p.b_boxes; ++c)
+                    tma_load_4d(b_addr(s) + c * kBoxBytes, &map_g, full_bar(s), 32 * c, x0, y0, b0);
+            }
+            __syncwarp();
+        }
+    } else if (warp == 1) {
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                               ((uint32_t)(p.n_mma >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+        constexpr uint32_t kHi = (512u >> 4) | (1u << 14) | (1u << 29);
+        constexpr uint32_t kLoA = (uint32_t)(kWgABoxBytes >> 4) << 16, kLoB = (uint32_t)(kBoxBytes >> 4) << 16;
+        for (int it = 0; it < total; ++it) {
+            const int s = it % S;
+            const uint32_t ph = (uint32_t)(it / S) & 1u;
+            mbar_wait(full_bar(s), ph);
+            tc_fence_after();
+            const uint32_t a_lo = ((a_addr(s) >> 4) & 0x3fffu) | kLoA, b_lo = ((b_addr(s) >> 4) & 0x3fffu) | kLoB;
+            if (elect_one()) {
+                for (int tl = 0; tl < ntap; ++tl) {
+                    const int tap = tap0 + tl;
+                    const int dy = tap / 3, dx = tap - dy * 3;                    // (dy+1, dx+1) of the conv tap
+                    const uint32_t a_t = a_lo + (uint32_t)((dy * kWgRowPitch + dx) * 8);   // K rows are 128 B = 8 address units
+                    const uint32_t d = tmem_acc + (uint32_t)(tl * p.n_mma);
+                    const uint32_t acc = it > 0 ? 1u : 0u;
+                    tc_mma_tf32_lh(d, a_t, kHi, b_lo, kHi, idesc, acc);
+                    tc_mma_tf32_lh(d, a_t + 64, kHi, b_lo + 64, kHi, idesc, 1u);
+                    tc_mma_tf32_lh(d, a_t + 128, kHi, b_lo + 128, kHi, idesc, 1u);
+                    tc_mma_tf32_lh(d, a_t + 192, kHi, b_lo + 192, kHi, idesc, 1u);
+                }
+                tc_commit(empty_bar(s));
+                if (it == total - 1) tc_commit(acc_bar);
+            }
+            __syncwarp();
+        }
+    } else {
+        const int q = warp & 3;
+        const int ii = i0 + q * 32 + lane;     // accumulator row = input channel
+        mbar_wait(acc_bar, 0);
+        tc_fence_after();
+        for (int tl = 0; tl < ntap; ++tl) {
+            float* dst = p.partial + (((int64_t)split * 9 + tap0 + tl) * p.a_pitch + ii) * p.g_pitch;
+            for (int c = 0; c < p.n_mma; c += 16) {
+                float v[16];
+                tc_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(tl * p.n_mma + c), v);
+                if (ii >= p.a_pitch) continue;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const int o = c + g * 4;
+                    if (o < p.g_pitch) st4(dst + o, make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(tmem_cols) : "memory");
+    }
+}
+
+// ================================================================================================
 // Streaming NHWC-p FIR: a CTA owns a (pixel-column strip x channel chunk x row segment) of one sample and
 // marches down the rows.  A producer warp streams ONE input row per stage through a TMA/mbarrier ring
 // (box = chunk channels x (strip + KW - 1) pixels, padding = out-of-bounds zero fill); the 256 consumer
@@ -1473,7 +1618,10 @@ int cagc_tc_conv(cudaStream_t stream, const ConvP& c, const char* what) {
     const uint32_t stage_bytes = (uint32_t)p.mt * kABytes + p.b_bytes;
     int tmem_need = 32;
     while (tmem_need < p.mt * p.n_tile) tmem_need <<= 1;
-    const int budget = (tmem_need <= 256 && 2 * stage_bytes + 1024 <= (uint32_t)kSmemBudget) ? kSmemBudget : kSmemBudget1;
+    int budget = (tmem_need <= 256 && 2 * stage_bytes + 1024 <= (uint32_t)kSmemBudget) ? kSmemBudget : kSmemBudget1;
+    // grids smaller than the machine (4x4 .. 32x32 layers): one CTA per SM anyway, and the launch is bound by the
+    // serial K loop's TMA latency -- give each CTA the whole shared memory for a deeper ring
+    if ((int64_t)ceil_div(p.tiles_total, p.mt) * ceil_div(p.n_rows, p.n_tile) <= kNumSMs) budget = kSmemBudget1;
     p.stages = std::max(2, std::min(kMaxStages, (int)((budget - 1024) / stage_bytes)));
     const size_t smem = (size_t)p.stages * stage_bytes + 1024;
 
@@ -1637,7 +1785,33 @@ int cagc_tc_conv_multi(cudaStream_t stream, const ConvP* ph, int nphase, const c
     return 1;
 }
 
+// all-taps plan (wgrad_tc_alltaps_kernel): taps per CTA, tap groups, splits; returns false when not applicable
+static bool wgrad_alltaps_plan(int B, int H, int W, int a_pitch, int g_pitch, int ksize, int mode, int* taps_per,
+                               int* groups, int* nsplits) {
+    using namespace cagc::tc;
+    static const int env = [] { const char* e = getenv("CAGC_TC_WGRAD_ALL"); return e ? atoi(e) : 1; }();
+    if (!env || mode != 0 || ksize != 3 || W < kWgPix || W % kWgPix != 0) return false;
+    const int n_mma = (g_pitch + 15) & ~15;
+    const int tp = std::min(9, 512 / n_mma);
+    if (tp < 3) return false;
+    const int gr = ceil_div(9, tp);
+    const int64_t tiles = (int64_t)(W / kWgPix) * H * B;
+    const int64_t fixed = (int64_t)ceil_div(a_pitch, kTileM) * gr;
+    int64_t sp = std::max<int64_t>(1, kNumSMs / fixed);
+    sp = std::min(sp, std::max<int64_t>(1, tiles / 8));
+    *taps_per = tp; *groups = gr; *nsplits = (int)sp;
+    return true;
+}
+
+static int wgrad_onetap_splits(int B, int H, int W, int a_pitch, int g_pitch, int ksize);
+
 int cagc_tc_wgrad_splits(int B, int H, int W, int a_pitch, int g_pitch, int ksize) {
+    int all_sp = 0, tp, gr, sp;   // the caller sizes its partial buffer before it knows the mode: cover both kernels
+    if (wgrad_alltaps_plan(B, H, W, a_pitch, g_pitch, ksize, 0, &tp, &gr, &sp)) all_sp = sp;
+    return std::max(all_sp, wgrad_onetap_splits(B, H, W, a_pitch, g_pitch, ksize));
+}
+
+static int wgrad_onetap_splits(int B, int H, int W, int a_pitch, int g_pitch, int ksize) {
     using namespace cagc::tc;
     const int bw = std::min(kWgPix, next_pow2(W)), bh = std::min(kWgPix / bw, next_pow2(H)), bb = kWgPix / (bw * bh);
     const int64_t tiles = (int64_t)ceil_div(W, bw) * ceil_div(H, bh) * ceil_div(B, bb);
@@ -1659,6 +1833,52 @@ int cagc_tc_wgrad(cudaStream_t stream, const float* a, const float* g, float* pa
     CAGC_REQUIRE(g_pitch <= 256, "%s: more than 256 gradient channels per call (caller splits)", what);
     EncodeTiledFn encode = get_encode();
     if (!encode) return fail(CAGC_E_UNSUPPORTED, "%s: cuTensorMapEncodeTiled not available from the driver", what);
+    {
+        int tp, gr, sp;
+        if (wgrad_alltaps_plan(B, H, W, a_pitch, g_pitch, ksize, mode, &tp, &gr, &sp) && sp <= nsplits) {
+            WgAllParams q{};
+            q.partial = partial; q.a_pitch = a_pitch; q.g_pitch = g_pitch;
+            q.n_mma = (g_pitch + 15) & ~15;
+            q.b_boxes = ceil_div(q.n_mma, 32);
+            q.a_boxes = std::min(4, ceil_div(a_pitch, 32));
+            q.taps_per = tp;
+            q.tiles_x = W / kWgPix; q.tiles_y = H;
+            q.tiles_total = q.tiles_x * H * B;
+            q.tiles_per_split = ceil_div(q.tiles_total, sp);
+            sp = ceil_div(q.tiles_total, q.tiles_per_split);
+            q.nsplits = sp;
+            q.stage_bytes = (uint32_t)q.a_boxes * kWgABoxBytes + (uint32_t)q.b_boxes * kBoxBytes;
+            // M = 128 always addresses four channel boxes: the last stage's reads may run into the tail padding
+            const int tail = (4 - q.a_boxes) * kWgABoxBytes;
+            q.stages = std::max(2, std::min(kMaxStages, (int)((kSmemBudget1 - 1024 - tail) / q.stage_bytes)));
+            const size_t smem_all = (size_t)q.stages * q.stage_bytes + tail + 1024;
+            CUtensorMap map_a, map_g;
+            {
+                cuuint64_t dims[4] = {(cuuint64_t)a_pitch, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+                cuuint64_t strides[3] = {(cuuint64_t)a_pitch * 4, (cuuint64_t)W * a_pitch * 4, (cuuint64_t)H * W * a_pitch * 4};
+                cuuint32_t box[4] = {32, 34, 1, 1};
+                cuuint32_t es[4] = {1, 1, 1, 1};
+                if (encode(&map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(a), dims, strides, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                    return fail(CAGC_E_INVALID, "%s: cuTensorMapEncodeTiled(a, all taps) failed", what);
+            }
+            if (encode_act_map(encode, &map_g, g, B, H, W, g_pitch, kWgPix, 1, 1, 1) != 0)
+                return fail(CAGC_E_INVALID, "%s: cuTensorMapEncodeTiled(g, all taps) failed", what);
+            static bool attr_all = false;
+            if (!attr_all) {
+                cudaError_t e = cudaFuncSetAttribute(wgrad_tc_alltaps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     kSmemBudget1);
+                if (e != cudaSuccess) return fail((int)e, "%s: cudaFuncSetAttribute failed: %s", what, cudaGetErrorString(e));
+                attr_all = true;
+            }
+            *nsplits_io = sp;
+            dim3 grid(ceil_div(a_pitch, kTileM), gr, sp);
+            wgrad_tc_alltaps_kernel<<<grid, kThreads, smem_all, stream>>>(map_a, map_g, q);
+            return launched(what);
+        }
+    }
+    nsplits = std::min(nsplits, wgrad_onetap_splits(B, H, W, a_pitch, g_pitch, ksize));
     WgTcParams p{};
     p.partial = partial; p.a_pitch = a_pitch; p.g_pitch = g_pitch;
     p.n_mma = (g_pitch + 15) & ~15;
