@@ -514,8 +514,19 @@ class ResBlock(nn.Module):
         self.skip = ConvLayer(in_channel, out_channel, 1, downsample=True, activate=False, bias=False)
 
     def forward(self, input):
-        out = self.conv2(self.conv1(input))
-        return (out + self.skip(input)) / math.sqrt(2)
+        out = self.conv1(input)
+        c2, sk = self.conv2, self.skip
+        if isinstance(c2[-1], FusedLeakyReLU) and len(c2) == 3 and len(sk) == 2 and sk[1].bias is None:
+            # (conv2(x) + skip(x)) / sqrt2 with the 1/sqrt2 folded into the activation gain of conv2 and into
+            # the (linear, bias-free) skip convolution's weight scale: one add instead of add + scale, forward
+            # and backward (reference model.py:731-737 computes the same quantity)
+            r = 1 / math.sqrt(2)
+            act = c2[2]
+            out = fused_leaky_relu(c2[1](c2[0](out)), act.bias, act.negative_slope, act.scale * r)
+            conv = sk[1]
+            w = _mc.cached_frozen(conv.weight, ('eqconv', conv.scale * r), lambda: conv.weight * (conv.scale * r))
+            return out + F.conv2d(sk[0](input), w, stride=conv.stride, padding=conv.padding)
+        return (self.conv2(out) + self.skip(input)) / math.sqrt(2)
 
 
 class Discriminator(nn.Module):
