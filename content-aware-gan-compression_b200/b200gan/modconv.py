@@ -434,10 +434,11 @@ class _ToRGBFn(Function):
             g_w = g_s = g_bias = g_skip = None
             need_s, need_w = ctx.needs_input_grad[1], ctx.needs_input_grad[2]
             if need_s or need_w:
-                g_w = torch.empty((1, nout, cin, 1, 1), device=dev, dtype=torch.float32) if need_w else None
+                gw_part = torch.empty((b, nout, cin), device=dev, dtype=torch.float32) if need_w else None
                 g_s = torch.empty((b, pin), device=dev, dtype=torch.float32) if need_s else None
                 check(lib.cagc_torgb_bwd_finalize(st, partial.data_ptr(), s_p.data_ptr(), w2.data_ptr(), wscale,
-                                                  ptr(g_w), ptr(g_s), b, chunks, cin, pin, nout), 'torgb_bwd_finalize')
+                                                  ptr(gw_part), ptr(g_s), b, chunks, cin, pin, nout), 'torgb_bwd_finalize')
+                g_w = gw_part.sum(0).reshape(1, nout, cin, 1, 1) if need_w else None   # fixed-order sum over the batch
             if has_bias and ctx.needs_input_grad[3]:
                 g_bias = g.sum(dim=(0, 2, 3)).reshape(1, nout, 1, 1)
             if has_skip and ctx.needs_input_grad[4]:

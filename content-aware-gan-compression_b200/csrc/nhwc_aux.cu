@@ -284,16 +284,17 @@ __global__ void __launch_bounds__(256) torgb_fwd_kernel(const float* __restrict_
             if (skip) {
                 // Upsample(skip): zero-insert x2, pad (pad0, .), true convolution with fir (model.py:38-56)
                 const float* sp = skip + ((int64_t)b * nout + o) * Hs * Ws;
+                // only every other tap meets a non-zero sample of the zero-inserted signal: start at the first
+                // tap index of the right parity and step by 2 (fh x fw = 4 x 4 -> 2 x 2 loads per output)
                 float u = 0.f;
-                for (int i = 0; i < fh; ++i) {
-                    const int ay = y + i - pad0;
-                    if (ay < 0 || (ay & 1)) continue;
-                    const int sy = ay >> 1;
+                const int i0 = (pad0 - y) & 1, j0 = (pad0 - xx) & 1;
+                for (int i = i0; i < fh; i += 2) {
+                    const int sy = (y + i - pad0) >> 1;          // arithmetic shift: negative stays negative
+                    if (sy < 0) continue;
                     if (sy >= Hs) break;
-                    for (int j = 0; j < fw; ++j) {
-                        const int ax = xx + j - pad0;
-                        if (ax < 0 || (ax & 1)) continue;
-                        const int sx = ax >> 1;
+                    for (int j = j0; j < fw; j += 2) {
+                        const int sx = (xx + j - pad0) >> 1;
+                        if (sx < 0) continue;
                         if (sx >= Ws) break;
                         u = fmaf(sfir[i * fw + j], __ldg(sp + sy * Ws + sx), u);
                     }
@@ -476,7 +477,9 @@ int cagc_act_bwd_chunks(int H, int W) { return pixel_chunks(H * W); }
 
 int cagc_bias_grad_rows_chunks(int64_t rows, int C) {
     if (C % 4 != 0 || C > 1024 || rows < 64) return 0;   // caller reduces grad_in itself
-    int64_t c = ceil_div<int64_t>(rows, 512);
+    // ~16 rows per block (a block covers PY >= 1 rows per step), capped at one resident wave.  (One block per
+    // 512 rows left the low-resolution layers of the discriminator to a handful of blocks: 60-130 us each.)
+    int64_t c = ceil_div<int64_t>(rows, 16);
     if (c > 8 * kNumSMs) c = 8 * kNumSMs;
     return (int)c;
 }

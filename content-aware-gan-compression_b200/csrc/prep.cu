@@ -350,39 +350,37 @@ __global__ void __launch_bounds__(256) wgrad_finalize_kernel(const float* __rest
     }
 }
 
-// ToRGB: t[b][o][i] = sum_ch partial[b][ch][o][i];  g_s[b][i] = c sum_o t w[o][i];  g_w[o][i] = c sum_b t s[b][i]
-// block = (32 channels, 8 batch lanes)
+// ToRGB: t[b][o][i] = sum_ch partial[b][ch][o][i];  g_s[b][i] = c sum_o t w[o][i];  gw_part[b][o][i] = c t s[b][i]
+// (the caller adds gw_part over b).  block = (32 channels, 8 chunk lanes); grid = (ceil(pin/32), B)
 __global__ void __launch_bounds__(256) torgb_bwd_finalize_kernel(const float* __restrict__ partial,
                                                                  const float* __restrict__ s,
                                                                  const float* __restrict__ w, float wscale,
-                                                                 float* __restrict__ g_w, float* __restrict__ g_s,
-                                                                 int B, int chunks, int cin, int pin, int nout) {
+                                                                 float* __restrict__ gw_part, float* __restrict__ g_s,
+                                                                 int chunks, int cin, int pin, int nout) {
     __shared__ float red[4][8][32];
     const int cx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int i = blockIdx.x * 32 + cx;
-    float gw[4] = {0.f, 0.f, 0.f, 0.f};
+    const int i = blockIdx.x * 32 + cx, b = blockIdx.y;
+    float t[4] = {0.f, 0.f, 0.f, 0.f};
     if (i < pin) {
-        for (int b = ty; b < B; b += 8) {
-            float gs = 0.f;
-            const float sv = s[(int64_t)b * pin + i];
-            for (int o = 0; o < nout; ++o) {
-                const float* pp = partial + ((int64_t)b * chunks * nout + o) * pin + i;
-                float t = 0.f;
-                for (int ch = 0; ch < chunks; ++ch) t += pp[(int64_t)ch * nout * pin];
-                if (i < cin) gs = fmaf(t, __ldg(w + o * cin + i), gs);
-                gw[o] = fmaf(t, sv, gw[o]);
-            }
-            if (g_s) g_s[(int64_t)b * pin + i] = gs * wscale;
+        for (int ch = ty; ch < chunks; ch += 8) {
+            const float* pp = partial + (((int64_t)b * chunks + ch) * nout) * pin + i;
+            for (int o = 0; o < nout; ++o) t[o] += pp[(int64_t)o * pin];
         }
     }
-    for (int o = 0; o < 4; ++o) red[o][ty][cx] = gw[o];
+    for (int o = 0; o < 4; ++o) red[o][ty][cx] = t[o];
     __syncthreads();
-    if (ty == 0 && g_w && i < cin) {
+    if (ty == 0 && i < pin) {
+        const float sv = s[(int64_t)b * pin + i];
+        float gs = 0.f;
         for (int o = 0; o < nout; ++o) {
-            float t = 0.f;
-            for (int k = 0; k < 8; ++k) t += red[o][k][cx];
-            g_w[o * cin + i] = t * wscale;
+            float v = 0.f;
+            for (int k = 0; k < 8; ++k) v += red[o][k][cx];
+            if (i < cin) {
+                gs = fmaf(v, __ldg(w + o * cin + i), gs);
+                if (gw_part) gw_part[((int64_t)b * nout + o) * cin + i] = v * sv * wscale;
+            }
         }
+        if (g_s) g_s[(int64_t)b * pin + i] = gs * wscale;
     }
 }
 
@@ -577,8 +575,10 @@ int cagc_torgb_bwd_finalize(cagc_stream_t stream_, const float* partial, const f
                             float* g_w, float* g_s, int B, int chunks, int cin, int pin, int nout) {
     cudaStream_t stream = (cudaStream_t)stream_;
     CAGC_REQUIRE(partial && s && w && chunks >= 1 && pin >= cin && nout >= 1 && nout <= 4, "torgb_bwd_finalize: bad arguments");
-    torgb_bwd_finalize_kernel<<<ceil_div(pin, 32), 256, 0, stream>>>(partial, s, w, wscale, g_w, g_s, B, chunks, cin, pin,
-                                                                    nout);
+    if (B == 0) return 0;
+    CAGC_REQUIRE(B <= 65535, "torgb_bwd_finalize: batch too large");
+    torgb_bwd_finalize_kernel<<<dim3(ceil_div(pin, 32), B), 256, 0, stream>>>(partial, s, w, wscale, g_w, g_s, chunks, cin,
+                                                                             pin, nout);
     return launched("torgb_bwd_finalize_kernel");
 }
 

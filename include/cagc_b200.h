@@ -37,7 +37,7 @@ typedef void* cagc_stream_t; /* cudaStream_t */
 #define CAGC_E_UNSUPPORTED (-2) /* shape outside what the kernels implement */
 
 /* bump when a signature changes; the Python loader checks it */
-#define CAGC_ABI_VERSION 13
+#define CAGC_ABI_VERSION 14
 
 int cagc_abi_version(void);
 const char* cagc_last_error(void);
@@ -199,7 +199,8 @@ int cagc_wgrad_finalize(cagc_stream_t stream, const float* wpart, int nsplits, c
                         float* out);
 
 /* ToRGB backward bookkeeping from the chunk partials of cagc_torgb_bwd (t[b][o][i] = sum_chunk partial):
- *   g_w[o][i] = wscale * sum_b t[b][o][i]*s[b][i];   g_s[b][i] = wscale * sum_o t[b][o][i]*w[o][i]  (pad channels 0) */
+ *   g_w[b][o][i] = wscale * t[b][o][i]*s[b][i]  (per-sample contributions [B][nout][cin]; the caller adds them over b);
+ *   g_s[b][i] = wscale * sum_o t[b][o][i]*w[o][i]  (pad channels 0) */
 int cagc_torgb_bwd_finalize(cagc_stream_t stream, const float* partial, const float* s, const float* w,
                             float wscale, float* g_w, float* g_s, int B, int chunks, int cin, int pin, int nout);
 

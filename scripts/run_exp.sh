@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
-(timeout 600 python -m pytest tests -m gpu -q -x 2>&1 | tail -12) > gpurun_out/tests.log
+(timeout 600 python -m pytest tests -m gpu -q -x 2>&1 | tail -6) > gpurun_out/tests.log
 (timeout 200 python bench.py --no-cpu-baseline 2>&1 | tail -1) > gpurun_out/bench.log

@@ -358,6 +358,40 @@ def test_generator_vs_oracle_pruned_widths(mods, size, shape):
         assert relerr(gr.cpu().numpy(), rr.numpy()) <= 5e-4, f'grad {n}: {relerr(gr.cpu().numpy(), rr.numpy()):.3e}'
 
 
+@pytest.mark.parametrize('shape,b,grads', [([154] * 10 + [77, 77, 39, 39], 4, True), (None, 2, False)])
+def test_full_size_256px_tensor_path_vs_exact_fp32(mods, shape, b, grads):
+    """BASELINE's full sizes (256px; 70%-pruned student 154/77/39 and the full 512/256/128 teacher): the tcgen05
+    path -- halo-tile kernel, multi-phase up-conv, persistent kernels, all-taps weight gradient at their real
+    tile / split configurations -- against the exact-fp32 SIMT engines of the same library on the same inputs
+    (the SIMT engines are pinned to the oracle by the small-size tests above).  TF32 tolerance; gradients of a
+    network with 13 leaky-ReLU layers are compared in L2 (sign flips of near-zero activations)."""
+    model, config = mods['model'], mods['config']
+    torch.manual_seed(11)
+    gen = model.Generator(256, 512, 8, generator_net_shape=shape).cuda()
+    _rand_small_params(gen, 5)
+    z = [torch.randn(b, 512, device='cuda'), torch.randn(b, 512, device='cuda')]
+    noise = [torch.randn(b, 1, n.shape[2], n.shape[3], device='cuda') for n in gen.make_noise()]
+    cot = torch.randn(b, 3, 256, 256, device='cuda')
+    res = {}
+    for name, algo in (('fp32', config.ALGO_SIMT_FP32), ('tc', config.ALGO_TCGEN05_TF32)):
+        gen.zero_grad()
+        with config.use_algo(algo), torch.set_grad_enabled(grads):
+            out = gen(z, inject_index=5, noise=noise, return_rgb_list=True)
+            if grads:
+                ((out[-1] * cot).abs().mean() * 3 + sum(r.mean() for r in out[:-1])).backward()
+        res[name] = ([o.detach().clone() for o in out],
+                     {n: p.grad.detach().clone() for n, p in gen.named_parameters()} if grads else {})
+    for i, (a, c) in enumerate(zip(res['tc'][0], res['fp32'][0])):
+        close(a, c, 1e-2, f'256px rgb {i} (tcgen05 vs fp32)')
+    # scalar gradients (noise weights) are sums with heavy cancellation: measure them against the largest of their kind
+    scal = max([float(g.abs().max()) for n, g in res['fp32'][1].items() if g.numel() == 1] + [1e-20])
+    for n, g32 in res['fp32'][1].items():
+        gtc = res['tc'][1][n]
+        ref_norm = g32.norm().clamp_min(1e-20) if g32.numel() > 1 else torch.tensor(scal, device=g32.device)
+        l2 = float((gtc - g32).norm() / ref_norm)
+        assert l2 <= 3e-2, f'256px grad {n}: L2 rel {l2:.3e}'
+
+
 def test_random_noise_path_and_dataparallel_keys(mods):
     """randomize_noise=True draws one normal_() per layer (model.py:299-301); module works under DataParallel."""
     model = mods['model']

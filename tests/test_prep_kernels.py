@@ -162,12 +162,12 @@ def test_backward_finalizers(env):
     nout = 3
     tpart = torch.randn(B, chunks, nout, pin, device=dev)
     w2 = torch.randn(nout, I, device=dev)
-    g_w = torch.empty(nout, I, device=dev)
+    g_w = torch.empty(B, nout, I, device=dev)
     g_s2 = torch.empty(B, pin, device=dev)
     check(lib.cagc_torgb_bwd_finalize(None, tpart.data_ptr(), s.data_ptr(), w2.data_ptr(), c, g_w.data_ptr(),
                                       g_s2.data_ptr(), B, chunks, I, pin, nout))
     t = tpart.double().sum(1)[:, :, :I]
-    _close(g_w, c * torch.einsum('boi,bi->oi', t, s.double()[:, :I]), 1e-5)
+    _close(g_w.sum(0), c * torch.einsum('boi,bi->oi', t, s.double()[:, :I]), 1e-5)
     _close(g_s2[:, :I], c * torch.einsum('boi,oi->bi', t, w2.double()), 1e-5)
     assert float(g_s2[:, I:].abs().sum()) == 0.0
 
