@@ -248,37 +248,61 @@ __global__ void __launch_bounds__(256) torgb_fwd_kernel(const float* __restrict_
     const int p_lo = blockIdx.x * chunk;
     const int p_hi = min(HW, p_lo + chunk);
     const int Hs = H >> 1, Ws = W >> 1;
-    for (int pbase = p_lo; pbase < p_hi; pbase += 32) {  // warp-uniform trip count (shuffles below)
-        const int p = pbase + grp;
-        const bool pvalid = p < p_hi;
-        const float* xp = x + ((int64_t)b * HW + (pvalid ? p : p_lo)) * pitch;
-        float acc[kRgbMaxOut] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
-        for (int c4 = lane8; c4 < c4n; c4 += 8) {
-            const float4 xv = ldg4(xp + c4 * 4);
+    // two pixels per 8-lane group and step: 8 independent 128-bit loads in flight per lane before the first FMA
+    // (the kernel is bound by load latency, not by bytes), and each effective-weight read serves both pixels
+    for (int pbase = p_lo; pbase < p_hi; pbase += 64) {  // warp-uniform trip count (shuffles below)
+        const int pa = pbase + grp, pb = pbase + 32 + grp;
+        const bool va = pa < p_hi, vb = pb < p_hi;
+        const float* xa = x + ((int64_t)b * HW + (va ? pa : p_lo)) * pitch;
+        const float* xb = x + ((int64_t)b * HW + (vb ? pb : p_lo)) * pitch;
+        float acc[2][kRgbMaxOut] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+        for (int c4b = lane8; c4b < c4n; c4b += 32) {
+            float4 ra[4], rb[4];
 #pragma unroll
-            for (int o = 0; o < kRgbMaxOut; ++o) {
-                if (o < nout) {
-                    const float4 wv = ld4(&weff[o * pitch + c4 * 4]);
-                    acc[o] = fmaf(xv.x, wv.x, acc[o]);
-                    acc[o] = fmaf(xv.y, wv.y, acc[o]);
-                    acc[o] = fmaf(xv.z, wv.z, acc[o]);
-                    acc[o] = fmaf(xv.w, wv.w, acc[o]);
+            for (int u = 0; u < 4; ++u) {
+                const int c4 = c4b + 8 * u;
+                ra[u] = c4 < c4n ? ldg4(xa + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                rb[u] = c4 < c4n ? ldg4(xb + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int c4 = c4b + 8 * u;
+                if (c4 < c4n) {
+#pragma unroll
+                    for (int o = 0; o < kRgbMaxOut; ++o) {
+                        if (o < nout) {
+                            const float4 wv = ld4(&weff[o * pitch + c4 * 4]);
+                            acc[0][o] = fmaf(ra[u].x, wv.x, acc[0][o]);
+                            acc[0][o] = fmaf(ra[u].y, wv.y, acc[0][o]);
+                            acc[0][o] = fmaf(ra[u].z, wv.z, acc[0][o]);
+                            acc[0][o] = fmaf(ra[u].w, wv.w, acc[0][o]);
+                            acc[1][o] = fmaf(rb[u].x, wv.x, acc[1][o]);
+                            acc[1][o] = fmaf(rb[u].y, wv.y, acc[1][o]);
+                            acc[1][o] = fmaf(rb[u].z, wv.z, acc[1][o]);
+                            acc[1][o] = fmaf(rb[u].w, wv.w, acc[1][o]);
+                        }
+                    }
                 }
             }
         }
 #pragma unroll
-        for (int o = 0; o < kRgbMaxOut; ++o) {
-            acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], 4);
-            acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], 2);
-            acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], 1);
-        }
-        if (pvalid && lane8 < nout) {
-            const int o = lane8;
-            float v = acc[0];
+        for (int h = 0; h < 2; ++h)
 #pragma unroll
-            for (int q = 1; q < kRgbMaxOut; ++q)
-                if (o == q) v = acc[q];
+            for (int o = 0; o < kRgbMaxOut; ++o) {
+                acc[h][o] += __shfl_xor_sync(0xffffffffu, acc[h][o], 4);
+                acc[h][o] += __shfl_xor_sync(0xffffffffu, acc[h][o], 2);
+                acc[h][o] += __shfl_xor_sync(0xffffffffu, acc[h][o], 1);
+            }
+        // lanes 0 .. nout-1 of a group finish pixel a, lanes 4 .. 4+nout-1 pixel b
+        const int half = lane8 >> 2, o = lane8 & 3;
+        const int p = half ? pb : pa;
+        if ((half ? vb : va) && o < nout) {
+            float v = acc[0][0];
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int q = 0; q < kRgbMaxOut; ++q)
+                    if (half == h && o == q) v = acc[h][q];
             if (bias) v += __ldg(bias + o);
             const int y = p / W, xx = p - y * W;
             if (skip) {
