@@ -115,6 +115,26 @@ __global__ void __launch_bounds__(256) style_affine_kernel(const __grid_constant
     const float* a = p.A[l] + (int64_t)i * p.D;
     const float bv = p.bias[l] ? __ldg(p.bias[l] + i) * p.bias_mul[l] : 0.f;
     const float* lat = p.latent + (int64_t)p.lat[l] * p.lat_sl;
+    if (p.D <= 1024) {
+        // the weight row lives in registers (all of its loads in flight at once); per sample the latent row is read
+        // with independent loads as well -- a plain dot-product loop serialises on one load latency per element
+        float ar[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) ar[k] = (lane + 32 * k < p.D) ? __ldg(a + lane + 32 * k) : 0.f;
+        for (int b = 0; b < p.B; ++b) {
+            const float* w = lat + (int64_t)b * p.lat_sb;
+            float wv[32];
+#pragma unroll
+            for (int k = 0; k < 32; ++k) wv[k] = (lane + 32 * k < p.D) ? __ldg(w + lane + 32 * k) : 0.f;
+            float acc = 0.f;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) acc = fmaf(ar[k], wv[k], acc);
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
+            if (lane == 0) out[(int64_t)b * pin + i] = fmaf(acc, p.scale[l], bv);
+        }
+        return;
+    }
     for (int b = 0; b < p.B; ++b) {
         const float* w = lat + (int64_t)b * p.lat_sb;
         float acc = 0.f;
@@ -145,6 +165,7 @@ __global__ void __launch_bounds__(256) style_affine_bwd_kernel(const __grid_cons
         const float* lat = p.latent + (int64_t)p.lat[l] * p.lat_sl;
         for (int j0 = 0; j0 < p.D; j0 += 128) {      // 4 columns per lane per pass
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
             for (int b = 0; b < p.B; ++b) {
                 const float g = __ldg(gs + (int64_t)b * pin + i);
                 const float* w = lat + (int64_t)b * p.lat_sb;
@@ -182,7 +203,8 @@ __global__ void __launch_bounds__(256) style_affine_bwd_kernel(const __grid_cons
             if (j < p.D) {
                 const float* a = p.A[l] + j;
                 float t = 0.f;
-                for (int i = 0; i < I; ++i) t = fmaf(sg[i], __ldg(a + (int64_t)i * p.D), t);
+#pragma unroll 8
+                for (int i = 0; i < I; ++i) t = fmaf(sg[i], __ldg(a + (int64_t)i * p.D), t);   // 8 loads in flight
                 acc += t;
             }
         }
