@@ -86,5 +86,8 @@ if os.path.exists(raw):
         out.append(f"| `{name}` | {r[idx['launch__grid_size']]} | {g(cols[0])} | {g(cols[1])} | {g(cols[2])} | "
                    f"{float(r[idx[cols[3]]]):.1f} | {float(r[idx[cols[4]]]):.1f} | {float(r[idx[cols[5]]]):.1f} | "
                    f"{r[idx[cols[6]]]} |")
+notes = os.path.join(P, f'{tag}_notes.md')     # hand-written sections (other configs, probes) travel with the summary
+if os.path.exists(notes):
+    out.append('\n' + open(notes).read().rstrip())
 open(os.path.join(P, f'{tag}_summary.md'), 'w').write('\n'.join(out) + '\n')
 print('\n'.join(out)[:3000])
