@@ -2,11 +2,15 @@
 
 Fused form of model.py:241-289 / :351-367 / :380-395 (math: SURVEY.md Appendix B):
 
-    s = modulation(style)                      -- EqualLinear, plain library GEMM, autograd by torch
-    d = rsqrt(s^2 @ Wsq^T + eps)               -- tiny, composed from torch ops so autograd supplies
-                                                  the demodulation terms of dW and ds
-    a = lrelu(d * conv(s*x, c*W) + nw*noise + bias) * sqrt2      <- ONE native kernel (same-res)
-    a = lrelu(d * blur(convT2(s*x, c*W)) + nw*noise + bias)*sqrt2 <- two native kernels (up-conv)
+    s_l = modulation_l(latent)   for ALL layers     <- ONE native kernel (style_affine), one more for its backward
+    prep(W)  -> operand slabs (fwd + dgrad), Wsq, padded bias   <- ONE native kernel per layer (cached when frozen)
+    d = rsqrt(s^2 @ Wsq^T + eps)                                <- ONE native kernel (demod)
+    a = lrelu(d * conv(s*x, c*W) + nw*noise + bias) * sqrt2      <- modulate + ONE conv kernel (same-res)
+    a = lrelu(d * blur(convT2(s*x, c*W)) + nw*noise + bias)*sqrt2 <- modulate + conv (all 4 parities) + FIR (up-conv)
+
+The backward of a layer is act_bwd -> finalize (g_bias, gq = dL/d(demod radicand), g_noise_w) -> [FIR] -> dgrad
+conv -> mod_bwd -> style-gradient finalize -> wgrad (split partials) -> wgrad finalize (parameter layout, demod
+term): the demodulation terms of dW and ds are folded into the finalize kernels, nothing is left to ATen autograd.
 
 Activations travel between layers as "NHWC-p" buffers: fp32 [B, H, W, P] with the channel pitch P
 rounded up to a multiple of 8 and the padding channels kept at zero, exposed to Python as ordinary
@@ -337,8 +341,6 @@ class _StyledConvFn(Function):
                           'style_grad_finalize')
                 if need_x:
                     g_x = nhwc_view(gxt, cin)
-            elif need_s and gq is not None:
-                raise RuntimeError('ModulatedConv2d: style gradient without input gradient is not implemented')
             if need_w:
                 # exact-fp32 mode (saliency): SIMT engine; tensor-pipe mode: tcgen05 TF32.  Both leave split-K
                 # partials that cagc_wgrad_finalize reduces in a fixed order (deterministic), folding in the

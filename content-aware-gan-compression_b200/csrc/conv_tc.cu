@@ -775,16 +775,23 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
 }
 
-// elementwise x~ = round_tf32(x * s[b, c])  (s == nullptr: plain rounding); NHWC-p, float4
+// elementwise x~ = round_tf32(x * s[b, c])  (s == nullptr: plain rounding); NHWC-p, float4.  blockIdx.y = sample;
+// the channel-quad index of a thread advances by a fixed amount per grid stride (no division in the loop)
 __global__ void __launch_bounds__(256) modulate_kernel(const float* __restrict__ x, const float* __restrict__ s,
-                                                       float* __restrict__ out, int64_t n4, int64_t per_sample4,
-                                                       int c4n) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-        float4 v = ld4(x + 4 * i);
-        if (s) {
-            const int64_t b = i / per_sample4;
-            const int c4 = (int)(i % c4n);
-            const float4 sv = ldg4(s + (b * c4n + c4) * 4);
+                                                       float* __restrict__ out, int per_sample4, int c4n) {
+    const int b = blockIdx.y;
+    const int stride = gridDim.x * 256;
+    const int step_c = stride % c4n;
+    int i = blockIdx.x * 256 + threadIdx.x;
+    int c4 = i % c4n;
+    const float* xs = x + (int64_t)b * per_sample4 * 4;
+    float* os = out + (int64_t)b * per_sample4 * 4;
+    const float* sb = s ? s + (int64_t)b * c4n * 4 : nullptr;
+#pragma unroll 4
+    for (; i < per_sample4; i += stride) {
+        float4 v = ldg4(xs + 4 * (int64_t)i);
+        if (sb) {
+            const float4 sv = ldg4(sb + c4 * 4);
             v.x *= sv.x; v.y *= sv.y; v.z *= sv.z; v.w *= sv.w;
         }
         uint32_t r0, r1, r2, r3;
@@ -792,7 +799,9 @@ __global__ void __launch_bounds__(256) modulate_kernel(const float* __restrict__
         asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r1) : "f"(v.y));
         asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r2) : "f"(v.z));
         asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r3) : "f"(v.w));
-        st4(out + 4 * i, make_float4(__uint_as_float(r0), __uint_as_float(r1), __uint_as_float(r2), __uint_as_float(r3)));
+        st4(os + 4 * (int64_t)i, make_float4(__uint_as_float(r0), __uint_as_float(r1), __uint_as_float(r2), __uint_as_float(r3)));
+        c4 += step_c;
+        if (c4 >= c4n) c4 -= c4n;
     }
 }
 
@@ -2035,11 +2044,13 @@ int cagc_modulate(cagc_stream_t stream_, const float* x, const float* s, float* 
     cudaStream_t stream = (cudaStream_t)stream_;
     CAGC_REQUIRE(x && out, "modulate: null pointer");
     CAGC_REQUIRE(pitch > 0 && pitch % 4 == 0, "modulate: pitch must be a positive multiple of 4");
-    const int64_t n4 = (int64_t)B * H * W * pitch / 4;
-    if (n4 == 0) return 0;
-    int64_t blocks = ceil_div<int64_t>(n4, 256);
-    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-    cagc::tc::modulate_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, s, out, n4, (int64_t)H * W * pitch / 4, pitch / 4);
+    const int64_t per4 = (int64_t)H * W * pitch / 4;
+    if (per4 == 0 || B == 0) return 0;
+    CAGC_REQUIRE(per4 < (1LL << 30) && B <= 65535, "modulate: tensor too large");
+    int64_t bx = ceil_div<int64_t>(per4, 256);
+    const int64_t cap = std::max<int64_t>(1, (int64_t)kNumSMs * 16 / B);
+    if (bx > cap) bx = cap;
+    cagc::tc::modulate_kernel<<<dim3((unsigned)bx, (unsigned)B), 256, 0, stream>>>(x, s, out, (int)per4, pitch / 4);
     return launched("modulate_kernel");
 }
 

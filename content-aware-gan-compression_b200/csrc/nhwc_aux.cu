@@ -131,13 +131,19 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const float* __restrict__ 
     constexpr float kInvPos = 0.70710678118654752440f;            // 1/sqrt2
     constexpr float kInvNeg = 0.70710678118654752440f / 0.2f;     // 1/(0.2*sqrt2)
 
+    const bool flat = (sh == (int64_t)W * sw);      // rows of ga follow each other: no per-pixel division
 #pragma unroll 2
     for (int p = p_lo + py; p < p_hi; p += PY) {
-        const int y = p / W, x = p - y * W;
         const int64_t off = ((int64_t)b * HW + p) * pitch + c;
         const float4 a4 = ldg4(a + off);
         float gav[4];
-        const float* gp = ga + b * sb + y * sh + x * sw + (int64_t)c * sc;
+        const float* gp;
+        if (flat) {
+            gp = ga + b * sb + (int64_t)p * sw + (int64_t)c * sc;
+        } else {
+            const int y = p / W, x = p - y * W;
+            gp = ga + b * sb + y * sh + x * sw + (int64_t)c * sc;
+        }
         if (ga_vec) {
             const float4 t = ld4(gp);
             gav[0] = t.x; gav[1] = t.y; gav[2] = t.z; gav[3] = t.w;
