@@ -544,7 +544,7 @@ def test_tcgen05_generator_vs_golden(golden_dir, mods):
     close(img, ref, 1e-2, 'tc generator image')
 
 
-@pytest.mark.parametrize('c,h,w,pad', [(8, 19, 23, (2, 2)), (24, 33, 70, (1, 1)), (40, 257, 257, (1, 1)),
+@pytest.mark.parametrize('c,h,w,pad', [(8, 19, 23, (2, 2)), (16, 40, 300, (1, 1)), (24, 33, 70, (1, 1)), (40, 257, 257, (1, 1)),
                                        (80, 129, 129, (1, 1)), (160, 65, 65, (2, 2)), (32, 300, 40, (2, 2)),
                                        (128, 64, 64, (1, 1)), (12, 20, 20, (1, 1)), (72, 5, 3, (2, 2))])
 def test_fir_nhwc_streaming_kernel(mods, c, h, w, pad):
@@ -561,6 +561,32 @@ def test_fir_nhwc_streaming_kernel(mods, c, h, w, pad):
     xc = x.cuda().contiguous(memory_format=torch.channels_last)
     y = op.upfirdn2d(xc, k.float().cuda(), pad=pad)
     close(y, ref, TOL_BW, f'nhwc stream fir c={c}')
+
+
+def test_fir_nhwc_device_taps_entry_point(mods):
+    """cagc_fir_nhwc (taps read from device memory: the path taken for a FIR buffer first seen during CUDA-graph
+    capture) and cagc_fir_nhwc_taps (taps in the parameter block) must give identical results."""
+    L, check = mods['lib'].lib, mods['lib'].check
+    torch.manual_seed(5)
+    b, h, w, p = 2, 37, 45, 40
+    x = torch.randn(b, h, w, p, device='cuda')
+    fir = torch.rand(4, 4, device='cuda')
+    taps = (__import__('ctypes').c_float * 16)(*fir.cpu().reshape(-1).tolist())
+    scale = torch.rand(b, p, device='cuda') + 0.5
+    noise = torch.randn(b, 1, h - 1, w - 1, device='cuda')
+    nw = torch.tensor([0.3], device='cuda')
+    bias = torch.randn(p, device='cuda')
+    outs = []
+    for use_taps in (False, True):
+        y = torch.empty(b, h - 1, w - 1, p, device='cuda')
+        args = (x.data_ptr(), fir.data_ptr()) + ((taps,) if use_taps else ()) + \
+               (scale.data_ptr(), noise.data_ptr(), nw.data_ptr(), bias.data_ptr(), y.data_ptr(), b, h, w, p, 39, 4, 4,
+                1, 1, 1, 1, (h - 1) * (w - 1), 1)
+        check((L.cagc_fir_nhwc_taps if use_taps else L.cagc_fir_nhwc)(None, *args), 'fir')
+        outs.append(y)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1])
+    assert float(outs[0][..., 39:].abs().sum()) == 0.0        # padding channel written as zero
 
 
 def test_upfirdn2d_channels_last_and_discriminator(mods):
