@@ -197,14 +197,21 @@ __global__ void __launch_bounds__(256) style_affine_bwd_kernel(const __grid_cons
         for (int l = 0; l < p.n_layers; ++l) {
             if (p.lat[l] != idx || !p.gs[l]) continue;   // block-uniform
             const int I = p.I[l];
+            const int I8 = (I + 7) & ~7;                 // the staged row is zero padded to a multiple of 8 ...
             __syncthreads();
-            for (int i = threadIdx.x; i < I; i += 256) sg[i] = __ldg(p.gs[l] + (int64_t)b * p.pin[l] + i) * p.scale[l];
+            for (int i = threadIdx.x; i < I8; i += 256)
+                sg[i] = i < I ? __ldg(p.gs[l] + (int64_t)b * p.pin[l] + i) * p.scale[l] : 0.f;
             __syncthreads();
             if (j < p.D) {
                 const float* a = p.A[l] + j;
                 float t = 0.f;
-#pragma unroll 8
-                for (int i = 0; i < I; ++i) t = fmaf(sg[i], __ldg(a + (int64_t)i * p.D), t);   // 8 loads in flight
+                for (int i0 = 0; i0 < I8; i0 += 8) {     // ... so the 8-wide body (8 loads in flight) needs no remainder
+                    float av[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) av[u] = __ldg(a + (int64_t)min(i0 + u, I - 1) * p.D);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) t = fmaf(sg[i0 + u], av[u], t);
+                }
                 acc += t;
             }
         }
@@ -540,7 +547,7 @@ int cagc_style_affine_bwd(cagc_stream_t stream_, int n_layers, const void* const
     p.g_latent = g_latent;
     const int lat_blocks = g_latent ? B * n_latent : 0;
     if (p.param_blocks + lat_blocks == 0) return 0;
-    const size_t smem = sizeof(float) * max_i;
+    const size_t smem = sizeof(float) * (((size_t)max_i + 7) & ~(size_t)7);
     CAGC_REQUIRE(smem <= 48 * 1024, "style_affine_bwd: layer too wide");
     style_affine_bwd_kernel<<<p.param_blocks + lat_blocks, 256, smem, stream>>>(p);
     return launched("style_affine_bwd_kernel");
