@@ -1121,6 +1121,154 @@ wgrad_tc_alltaps_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
 }
 
 // ================================================================================================
+// All-taps weight gradient of the stride-2 TRANSPOSED 3x3 convolution (mode 1):
+//     gw[(ky,kx)][i][o] = sum_{b,y,x} a[b,y,x,i] * g_T[b, 2y+ky, 2x+kx, o]
+// Per 32-pixel stage the input tile a[32 px][M] is loaded once; of the gradient, for every needed row 2y+ky, the
+// even-column samples E[j] = g_T[2(x0+j)] (33 of them) and the odd-column samples O[j] = g_T[2(x0+j)+1] (32) arrive
+// through TMA boxes with element stride 2.  Tap (ky, kx) is then a row-shifted MN-major descriptor view of those
+// rows: kx = 0 -> E, kx = 1 -> O, kx = 2 -> E shifted by one sample.  6 gradient boxes per channel box and stage
+// instead of 9, and the input once instead of 9 times.
+// ================================================================================================
+constexpr int kWgUpKy = 2 * kWgRowPitch;                         // K rows reserved per gradient row: E (33) | O (32)
+
+struct WgUpParams {
+    float* partial;
+    int a_pitch, g_pitch, n_mma, b_boxes;
+    int n_ky, nsplits, tiles_total, tiles_per_split;             // n_ky gradient rows (= 3 taps each) per CTA
+    int tiles_x, tiles_y, stages;
+    uint32_t b_box_bytes, stage_bytes;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_tc_alltaps_up_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_ge,
+                           const __grid_constant__ CUtensorMap map_go, const __grid_constant__ WgUpParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 1];
+    __shared__ uint32_t tmem_base_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int S = p.stages;
+    constexpr uint32_t a_bytes = 4 * kBoxBytes;                   // M = 128 always addresses four channel boxes
+    auto a_addr = [&](int s) { return smem_base + (uint32_t)s * p.stage_bytes; };
+    auto b_addr = [&](int s) { return smem_base + (uint32_t)s * p.stage_bytes + a_bytes; };
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (kMaxStages + s); };
+    const uint32_t acc_bar = bar0 + 8u * (2 * kMaxStages);
+
+    const int i0 = blockIdx.x * kTileM;
+    const int ky0 = blockIdx.y * p.n_ky;
+    const int nky = min(p.n_ky, 3 - ky0);
+    const int split = blockIdx.z;
+    const int t_lo = split * p.tiles_per_split;
+    const int t_hi = min(p.tiles_total, t_lo + p.tiles_per_split);
+    const int total = t_hi - t_lo;            // host guarantees >= 1
+
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < 3 * p.n_ky * p.n_mma) tmem_cols <<= 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        mbar_init(acc_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                     "r"(tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_acc = tmem_base_slot;
+
+    if (warp == 0) {
+        const int a_ld = min(4, (p.a_pitch - i0 + 31) / 32);
+        const uint32_t tx_bytes = (uint32_t)a_ld * kBoxBytes + (uint32_t)(p.b_boxes * nky) * (33u + 32u) * 128u;
+        for (int it = 0; it < total; ++it) {
+            const int s = it % S;
+            const uint32_t ph = (uint32_t)(it / S) & 1u;
+            mbar_wait(empty_bar(s), ph ^ 1u);
+            int t = t_lo + it;
+            const int tx = t % p.tiles_x;
+            t /= p.tiles_x;
+            const int y0 = t % p.tiles_y;
+            const int b0 = t / p.tiles_y;
+            const int x0 = tx * kWgPix;
+            if (elect_one()) {
+                mbar_expect_tx(full_bar(s), tx_bytes);
+                for (int c = 0; c < a_ld; ++c)
+                    tma_load_4d(a_addr(s) + c * kBoxBytes, &map_a, full_bar(s), i0 + 32 * c, x0, y0, b0);
+                for (int c = 0; c < p.b_boxes; ++c)
+                    for (int r = 0; r < nky; ++r) {
+                        const uint32_t dst = b_addr(s) + (uint32_t)c * p.b_box_bytes + (uint32_t)(r * kWgUpKy) * 128u;
+                        tma_load_4d(dst, &map_ge, full_bar(s), 32 * c, 2 * x0, 2 * y0 + ky0 + r, b0);
+                        tma_load_4d(dst + kWgRowPitch * 128, &map_go, full_bar(s), 32 * c, 2 * x0 + 1, 2 * y0 + ky0 + r, b0);
+                    }
+            }
+            __syncwarp();
+        }
+    } else if (warp == 1) {
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                               ((uint32_t)(p.n_mma >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+        constexpr uint32_t kHi = (512u >> 4) | (1u << 14) | (1u << 29);
+        constexpr uint32_t kLoA = (uint32_t)(kBoxBytes >> 4) << 16;
+        const uint32_t lo_b = (p.b_box_bytes >> 4) << 16;
+        for (int it = 0; it < total; ++it) {
+            const int s = it % S;
+            const uint32_t ph = (uint32_t)(it / S) & 1u;
+            mbar_wait(full_bar(s), ph);
+            tc_fence_after();
+            const uint32_t a_lo = ((a_addr(s) >> 4) & 0x3fffu) | kLoA, b_lo = ((b_addr(s) >> 4) & 0x3fffu) | lo_b;
+            if (elect_one()) {
+                for (int r = 0; r < nky; ++r)
+                    for (int kx = 0; kx < 3; ++kx) {
+                        // kx = 0: E rows 0..31, kx = 1: O rows (36 rows further), kx = 2: E rows 1..32
+                        const int row = r * kWgUpKy + (kx == 1 ? kWgRowPitch : (kx == 2 ? 1 : 0));
+                        const uint32_t b_t = b_lo + (uint32_t)(row * 8);
+                        const uint32_t d = tmem_acc + (uint32_t)((r * 3 + kx) * p.n_mma);
+                        tc_mma_tf32_lh(d, a_lo, kHi, b_t, kHi, idesc, it > 0 ? 1u : 0u);
+                        tc_mma_tf32_lh(d, a_lo + 64, kHi, b_t + 64, kHi, idesc, 1u);
+                        tc_mma_tf32_lh(d, a_lo + 128, kHi, b_t + 128, kHi, idesc, 1u);
+                        tc_mma_tf32_lh(d, a_lo + 192, kHi, b_t + 192, kHi, idesc, 1u);
+                    }
+                tc_commit(empty_bar(s));
+                if (it == total - 1) tc_commit(acc_bar);
+            }
+            __syncwarp();
+        }
+    } else {
+        const int q = warp & 3;
+        const int ii = i0 + q * 32 + lane;     // accumulator row = input channel
+        mbar_wait(acc_bar, 0);
+        tc_fence_after();
+        for (int tl = 0; tl < 3 * nky; ++tl) {
+            float* dst = p.partial + (((int64_t)split * 9 + ky0 * 3 + tl) * p.a_pitch + ii) * p.g_pitch;
+            for (int c = 0; c < p.n_mma; c += 16) {
+                float v[16];
+                tc_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(tl * p.n_mma + c), v);
+                if (ii >= p.a_pitch) continue;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const int o = c + g * 4;
+                    if (o < p.g_pitch) st4(dst + o, make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(tmem_cols) : "memory");
+    }
+}
+
+// ================================================================================================
 // Streaming NHWC-p FIR: a CTA owns a (pixel-column strip x channel chunk x row segment) of one sample and
 // marches down the rows.  A producer warp streams ONE input row per stage through a TMA/mbarrier ring
 // (box = chunk channels x (strip + KW - 1) pixels, padding = out-of-bounds zero fill); the 256 consumer
@@ -1799,10 +1947,11 @@ static bool wgrad_alltaps_plan(int B, int H, int W, int a_pitch, int g_pitch, in
                                int* groups, int* nsplits) {
     using namespace cagc::tc;
     static const int env = [] { const char* e = getenv("CAGC_TC_WGRAD_ALL"); return e ? atoi(e) : 1; }();
-    if (!env || mode != 0 || ksize != 3 || W < kWgPix || W % kWgPix != 0) return false;
+    if (!env || ksize != 3 || W < kWgPix || W % kWgPix != 0) return false;
     const int n_mma = (g_pitch + 15) & ~15;
-    const int tp = std::min(9, 512 / n_mma);
+    int tp = std::min(9, 512 / n_mma);
     if (tp < 3) return false;
+    if (mode == 1) tp = tp / 3 * 3;                   // up-conv form: whole gradient rows (3 taps each) per CTA
     const int gr = ceil_div(9, tp);
     const int64_t tiles = (int64_t)(W / kWgPix) * H * B;
     const int64_t fixed = (int64_t)ceil_div(a_pitch, kTileM) * gr;
@@ -1815,8 +1964,9 @@ static bool wgrad_alltaps_plan(int B, int H, int W, int a_pitch, int g_pitch, in
 static int wgrad_onetap_splits(int B, int H, int W, int a_pitch, int g_pitch, int ksize);
 
 int cagc_tc_wgrad_splits(int B, int H, int W, int a_pitch, int g_pitch, int ksize) {
-    int all_sp = 0, tp, gr, sp;   // the caller sizes its partial buffer before it knows the mode: cover both kernels
+    int all_sp = 0, tp, gr, sp;   // the caller sizes its partial buffer before it knows the mode: cover all kernels
     if (wgrad_alltaps_plan(B, H, W, a_pitch, g_pitch, ksize, 0, &tp, &gr, &sp)) all_sp = sp;
+    if (wgrad_alltaps_plan(B, H, W, a_pitch, g_pitch, ksize, 1, &tp, &gr, &sp)) all_sp = std::max(all_sp, sp);
     return std::max(all_sp, wgrad_onetap_splits(B, H, W, a_pitch, g_pitch, ksize));
 }
 
@@ -1844,7 +1994,53 @@ int cagc_tc_wgrad(cudaStream_t stream, const float* a, const float* g, float* pa
     if (!encode) return fail(CAGC_E_UNSUPPORTED, "%s: cuTensorMapEncodeTiled not available from the driver", what);
     {
         int tp, gr, sp;
-        if (wgrad_alltaps_plan(B, H, W, a_pitch, g_pitch, ksize, mode, &tp, &gr, &sp) && sp <= nsplits) {
+        static const int up_env = [] { const char* e = getenv("CAGC_TC_WGRAD_UP"); return e ? atoi(e) : 1; }();
+        if (mode == 1 && up_env && wgrad_alltaps_plan(B, H, W, a_pitch, g_pitch, ksize, mode, &tp, &gr, &sp) &&
+            sp <= nsplits) {
+            WgUpParams q{};
+            q.partial = partial; q.a_pitch = a_pitch; q.g_pitch = g_pitch;
+            q.n_mma = (g_pitch + 15) & ~15;
+            q.b_boxes = ceil_div(q.n_mma, 32);
+            q.n_ky = tp / 3;
+            q.tiles_x = W / kWgPix; q.tiles_y = H;
+            q.tiles_total = q.tiles_x * H * B;
+            q.tiles_per_split = ceil_div(q.tiles_total, sp);
+            sp = ceil_div(q.tiles_total, q.tiles_per_split);
+            q.nsplits = sp;
+            q.b_box_bytes = (uint32_t)(q.n_ky * kWgUpKy) * 128u;
+            q.stage_bytes = 4u * kBoxBytes + (uint32_t)q.b_boxes * q.b_box_bytes;
+            q.stages = std::min(kMaxStages, (int)((kSmemBudget1 - 1024) / q.stage_bytes));
+            if (q.stages >= 2) {
+                const size_t smem_up = (size_t)q.stages * q.stage_bytes + 1024;
+                const int Hg = 2 * H + 1, Wg = 2 * W + 1;
+                CUtensorMap map_a, map_ge, map_go;
+                if (encode_act_map(encode, &map_a, a, B, H, W, a_pitch, kWgPix, 1, 1, 1) != 0)
+                    return fail(CAGC_E_INVALID, "%s: cuTensorMapEncodeTiled(a, up all taps) failed", what);
+                cuuint64_t dims[4] = {(cuuint64_t)g_pitch, (cuuint64_t)Wg, (cuuint64_t)Hg, (cuuint64_t)B};
+                cuuint64_t strides[3] = {(cuuint64_t)g_pitch * 4, (cuuint64_t)Wg * g_pitch * 4, (cuuint64_t)Hg * Wg * g_pitch * 4};
+                cuuint32_t es[4] = {1, 2, 1, 1};
+                cuuint32_t box_e[4] = {32, 66, 1, 1}, box_o[4] = {32, 64, 1, 1};     // element stride 2: 33 / 32 samples
+                if (encode(&map_ge, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(g), dims, strides, box_e, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS ||
+                    encode(&map_go, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(g), dims, strides, box_o, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                    return fail(CAGC_E_INVALID, "%s: cuTensorMapEncodeTiled(g, up all taps) failed", what);
+                static bool attr_up = false;
+                if (!attr_up) {
+                    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_alltaps_up_kernel,
+                                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget1);
+                    if (e != cudaSuccess) return fail((int)e, "%s: cudaFuncSetAttribute failed: %s", what, cudaGetErrorString(e));
+                    attr_up = true;
+                }
+                *nsplits_io = sp;
+                dim3 grid(ceil_div(a_pitch, kTileM), gr, sp);
+                wgrad_tc_alltaps_up_kernel<<<grid, kThreads, smem_up, stream>>>(map_a, map_ge, map_go, q);
+                return launched(what);
+            }
+        }
+        if (mode == 0 && wgrad_alltaps_plan(B, H, W, a_pitch, g_pitch, ksize, mode, &tp, &gr, &sp) && sp <= nsplits) {
             WgAllParams q{};
             q.partial = partial; q.a_pitch = a_pitch; q.g_pitch = g_pitch;
             q.n_mma = (g_pitch + 15) & ~15;

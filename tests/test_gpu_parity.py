@@ -499,7 +499,8 @@ def test_tcgen05_styled_conv_vs_oracle(mods, b, cin, cout, h, up):
 
 
 @pytest.mark.parametrize('b,cin,cout,h,up', [(2, 64, 48, 16, False), (2, 154, 77, 16, False), (1, 128, 256, 32, False),
-                                             (2, 77, 39, 8, True)])
+                                             (2, 77, 39, 8, True), (1, 77, 39, 32, True), (1, 154, 154, 32, True),
+                                             (1, 154, 77, 32, True), (2, 39, 39, 64, False), (1, 154, 154, 32, False)])
 def test_tcgen05_modconv_gradients_strict(mods, b, cin, cout, h, up):
     """ModulatedConv2d alone (no activation): forward, dgrad (tcgen05) and wgrad element-wise vs the oracle."""
     model, O, config = mods['model'], mods['O'], mods['config']
