@@ -719,18 +719,34 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         for (int item = blockIdx.x; item < items; item += gridDim.x) {
             int x0, y0, b, n0, n_mma;
             decode(item, x0, y0, b, n0, n_mma);
+            // this thread's noise values for all sub-tiles are requested BEFORE waiting for the accumulator: their
+            // latency hides behind the MMAs of the tile instead of adding ~1 us per sub-tile to the epilogue
+            float nzs[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                nzs[j] = 0.f;
+                if (p.noise && j < MT) {
+                    const int pos = j * kTileM + m;
+                    const int ry = pos / p.Wt, rx = pos - ry * p.Wt;
+                    const int ox = x0 + rx, oy = y0 + ry;
+                    if ((rx < p.TW) && (ry < p.R) && (ox < p.Wo) && (oy < p.Ho))
+                        nzs[j] = nwv * __ldg(p.noise + (int64_t)b * p.noise_bstride +
+                                             (int64_t)(oy * p.out_stride + p.out_oy) * p.Wout + (ox * p.out_stride + p.out_ox));
+                }
+            }
             mbar_wait(tfull(acc), tph);
             tc_fence_after();
             const uint32_t d0 = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * acc_stride);
             const float* sc = p.out_scale ? p.out_scale + (int64_t)b * p.n_pitch : nullptr;
-            for (int j = 0; j < MT; ++j) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (j >= MT) break;
                 const int pos = j * kTileM + m;              // raster position inside the tile
                 const int ry = pos / p.Wt, rx = pos - ry * p.Wt;
                 const int ox = x0 + rx, oy = y0 + ry;
                 const bool pvalid = (rx < p.TW) && (ry < p.R) && (ox < p.Wo) && (oy < p.Ho);
                 const int yy = oy * p.out_stride + p.out_oy, xx = ox * p.out_stride + p.out_ox;
-                float nz = 0.f;
-                if (p.noise && pvalid) nz = nwv * __ldg(p.noise + (int64_t)b * p.noise_bstride + (int64_t)yy * p.Wout + xx);
+                const float nz = nzs[j];
                 float* dst = p.out + (((int64_t)b * p.Hout + yy) * p.Wout + xx) * p.n_pitch;
                 for (int c = 0; c < n_mma; c += 16) {
                     float v[16];
