@@ -490,15 +490,27 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         for (int item = blockIdx.x; item < items; item += gridDim.x) {
             int x0s[2], y0s[2], b0s[2], n0, n_mma;
             const int f = decode(item, x0s, y0s, b0s, n0, n_mma);
+            // noise values requested before the accumulator wait (latency hidden behind the tile's MMAs)
+            float nzs[2] = {0.f, 0.f};
+            if (p.noise) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int ox = x0s[j] + lx, oy = y0s[j] + ly, b = b0s[j] + lb;
+                    if (j < MT && (ox < p.ph_Wo[f]) && (oy < p.ph_Ho[f]) && (b < p.B))
+                        nzs[j] = nwv * __ldg(p.noise + (int64_t)b * p.noise_bstride +
+                                             (int64_t)(oy * p.out_stride + p.ph_oy[f]) * p.Wout + (ox * p.out_stride + p.ph_ox[f]));
+                }
+            }
             mbar_wait(tfull_bar(acc), aph);
             tc_fence_after();
             const uint32_t d0 = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * acc_stride);
-            for (int j = 0; j < MT; ++j) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                if (j >= MT) break;
                 const int ox = x0s[j] + lx, oy = y0s[j] + ly, b = b0s[j] + lb;
                 const bool pvalid = (ox < p.ph_Wo[f]) && (oy < p.ph_Ho[f]) && (b < p.B);
                 const int yy = oy * p.out_stride + p.ph_oy[f], xx = ox * p.out_stride + p.ph_ox[f];
-                float nz = 0.f;
-                if (p.noise && pvalid) nz = nwv * __ldg(p.noise + (int64_t)b * p.noise_bstride + (int64_t)yy * p.Wout + xx);
+                const float nz = nzs[j];
                 float* dst = p.out + (((int64_t)b * p.Hout + yy) * p.Wout + xx) * p.n_pitch;
                 const float* sc = p.out_scale ? p.out_scale + (int64_t)b * p.n_pitch : nullptr;
                 for (int c = 0; c < n_mma; c += 16) {
