@@ -94,3 +94,31 @@ def test_product_code_never_imports_the_oracle():
             if f.endswith('.py'):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r'^\s*(from|import)\s+oracle', src, flags=re.M), f
+
+
+def test_tensor_cache_is_keyed_by_identity_and_version():
+    """Derived values of long-lived tensors (FIR taps, frozen-weight slabs) are cached per tensor OBJECT and version
+    counter -- a data pointer is not a safe key (the allocator recycles addresses of freed temporaries)."""
+    import gc
+    import torch
+    from b200gan._lib import TensorCache
+    c = TensorCache()
+    calls = []
+
+    def make(tag):
+        calls.append(tag)
+        return len(calls)
+
+    a = torch.zeros(4)
+    assert c.get(a, 'k', lambda: make('a')) == 1
+    assert c.get(a, 'k', lambda: make('a')) == 1 and calls == ['a']            # hit
+    assert c.get(a, 'other', lambda: make('a2')) == 2                          # different tag
+    a.add_(1)                                                                  # in-place update bumps the version
+    assert c.get(a, 'k', lambda: make('a3')) == 3
+    b = a.clone()                                                              # equal values, different object
+    assert c.get(b, 'k', lambda: make('b')) == 4
+    n = len(c._d)
+    del b
+    gc.collect()
+    assert len(c._d) == n - 1                                                  # entries die with their tensor
+    assert c.get(a, 'none', lambda: None) is None and ('id', 'none') not in c._d
