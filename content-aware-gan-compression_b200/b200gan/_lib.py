@@ -130,7 +130,9 @@ class TensorCache:
     def get(self, t: torch.Tensor, tag, make):
         key = (id(t), tag)
         hit = self._d.get(key)
-        if hit is not None and hit[0]() is t and hit[1] == t._version:
+        # identity + version counter + storage address: `module.to(device)` swaps `param.data` without touching
+        # either the object or its version
+        if hit is not None and hit[0]() is t and hit[1] == t._version and hit[3] == t.data_ptr():
             return hit[2]
         val = make()
         if val is None:
@@ -138,7 +140,7 @@ class TensorCache:
         d = self._d
         if len(d) > 8192:
             d.clear()
-        d[key] = (weakref.ref(t, lambda _r, k=key, d=d: d.pop(k, None)), t._version, val)
+        d[key] = (weakref.ref(t, lambda _r, k=key, d=d: d.pop(k, None)), t._version, val, t.data_ptr())
         return val
 
 

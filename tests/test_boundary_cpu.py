@@ -122,3 +122,6 @@ def test_tensor_cache_is_keyed_by_identity_and_version():
     gc.collect()
     assert len(c._d) == n - 1                                                  # entries die with their tensor
     assert c.get(a, 'none', lambda: None) is None and ('id', 'none') not in c._d
+    before = len(calls)
+    a.data = torch.ones(4)                                                     # what module.to(device) does: same object,
+    assert c.get(a, 'k', lambda: make('a4')) == before + 1                     # same version, new storage -> rebuilt
