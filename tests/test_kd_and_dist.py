@@ -96,6 +96,15 @@ def _worker(rank, world, port, q):
         gathered = [torch.zeros_like(local) for _ in range(world)]
         dist.all_gather(gathered, local)
         assert torch.allclose(bucket.flat_grad, sum(gathered))
+        # the KD step's protocol: gradients detached during backward, packed with one batched copy, then reduced
+        bucket.detach_grads()
+        net(x).square().sum().backward()
+        assert all(p.grad is not None and p.grad.data_ptr() != bucket.flat_grad.data_ptr() for p in net.parameters())
+        bucket.pack_grads()
+        assert torch.equal(bucket.flat_grad, local)      # same local gradients as the accumulate-in-place form
+        bucket.allreduce_mean_()
+        assert torch.allclose(bucket.flat_grad, sum(gathered))
+        assert next(net.parameters()).grad.data_ptr() == bucket.flat_grad.data_ptr()
         # gather_grad: average over ranks, one message
         for p in net.parameters():
             p.grad = torch.full_like(p, float(rank + 1))
