@@ -1,15 +1,19 @@
 #!/usr/bin/env python
 """Benchmark of the KD retraining generator step (BASELINE.json metric: images/sec, 256px 70%-pruned
-StyleGAN2 student, full-size teacher, batch 16 per GPU) -- see DESIGN.md "Measurement".
+StyleGAN2 student, full-size teacher, global batch 16) -- see DESIGN.md "Measurement".
 
-    python bench.py --gpus N --steps K --warmup W            # our arm (N>1: launched by torchrun)
-    python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle port on the host cores
+    python bench.py --gpus N --steps K --warmup W                 # product arm (N>1: launched by torchrun)
+    python bench.py --impl reference --gpus N --steps K ...       # the reference's OWN code on the host CPU cores
+    python bench.py --config kd1024|fid256|saliency256 ...        # BASELINE.json configs[3], [4], [2]
 
 One step = train.py:280-308 restricted to the hot path and its direct consumers: student forward
 (RGB list) + discriminator forward + GAN loss, teacher forward, masked L1 KD loss, backward, gradient
 all-reduce over ranks, fused Adam.  LPIPS-VGG / BiSeNet are third-party networks outside the path
 (their weights are not available offline) and are excluded on both arms.
-Prints ONE JSON line on rank 0.
+
+Scaling: the north star shards the minibatch of 16 over the GPUs of one box, so the headline mode is STRONG
+scaling (global batch 16, per-rank 16/N); the weak-scaling figure (16 per GPU) is measured in the same run and
+reported under "weak_scaling".  Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
@@ -22,19 +26,29 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.join(ROOT, 'content-aware-gan-compression_b200')
-for p in (PKG, ROOT):
-    if p not in sys.path:
-        sys.path.insert(0, p)
 
 if os.environ.get('NCCL_DEBUG', '').upper() in ('VERSION', 'WARN'):
     del os.environ['NCCL_DEBUG']           # both print NCCL's version banner on stdout: rank 0 prints ONE JSON line
-
-import torch  # noqa: E402
 
 STUDENT_SHAPES = {256: [154] * 10 + [77, 77, 39, 39],
                   1024: [154] * 10 + [77, 77, 39, 39, 20, 20, 10, 10]}
 # conv FLOPs per image, reference convention (Util/Calculators.py:16-61 x2), SURVEY.md §8d
 GFLOP_PER_IMG = {256: {'student': 8.240, 'teacher': 90.236}, 1024: {'student': 13.973, 'teacher': 148.520}}
+GLOBAL_BATCH = 16
+REF_STEP = os.path.join(ROOT, 'oracle', 'ref_step.py')
+
+
+def kd_workload(size):
+    s = STUDENT_SHAPES[size]
+    return (f'KD-like generator step {size}px: 70%-pruned student {s[0]}/{s[-1]}ch f+b, full teacher f, '
+            f'discriminator f+dgrad, masked L1 KD, grad all-reduce, Adam; global batch {GLOBAL_BATCH}; '
+            f'style mixing inject_index=5')
+
+
+def kd_config(size, world):
+    """`config` of the JSON line -- identical on the product arm and on the reference arm."""
+    return {'workload': kd_workload(size), 'global_batch': GLOBAL_BATCH, 'parallelism': f'dp{world}',
+            'l2': 'per-step working set (>=4 GB of activations) exceeds the 126 MB L2; no explicit flush'}
 
 
 def load_peaks():
@@ -90,169 +104,202 @@ class ClockSampler:
                 'samples': len(sm)}
 
 
-def synthetic_mask(size, device):
-    """Stand-in for the BiSeNet face mask (Util/content_aware_pruning.py:61-117): centred ellipse."""
-    yy, xx = torch.meshgrid(torch.arange(size, device=device), torch.arange(size, device=device), indexing='ij')
-    c = (size - 1) / 2
-    return ((((yy - c) / (0.42 * size)) ** 2 + ((xx - c) / (0.34 * size)) ** 2) <= 1).float().view(1, 1, size, size)
+# ------------------------------------------------------------------------------------------------
+# reference arms: the reference's own code (oracle/_ref, staged by oracle/stage_ref.py) in its own process
+# ------------------------------------------------------------------------------------------------
+def run_ref_step(device, size, batch, steps, warmup, timeout=1500):
+    """oracle/ref_step.py in a subprocess (the reference's `model` / `op` module names collide with the
+    drop-in's).  Returns the parsed JSON or {'unavailable': why}."""
+    cmd = [sys.executable, REF_STEP, '--device', device, '--size', str(size), '--batch', str(batch),
+           '--steps', str(steps), '--warmup', str(warmup)]
+    env = {k: v for k, v in os.environ.items() if k not in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK', 'MASTER_ADDR',
+                                                           'MASTER_PORT', 'CAGC_CONV_ALGO')}
+    try:
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout, env=env)
+    except subprocess.TimeoutExpired:
+        return {'unavailable': f'{" ".join(cmd[1:])} timed out after {timeout} s'}
+    for ln in reversed(r.stdout.strip().splitlines()):
+        if ln.startswith('{'):
+            return json.loads(ln)
+    tail = (r.stderr or r.stdout or '').strip().splitlines()[-1:] or ['no output']
+    return {'unavailable': f'rc {r.returncode}: {tail[0][:300]}'}
 
 
-def cpu_reference_step_time(size, batch, steps, warmup, seed=0):
-    """The reference algorithm's CPU path (oracle port, fp32, all host threads) on a bounded sample of
-    the same workload: `batch` images of the same KD-like step.  Returns (images/s, seconds/step, cores)."""
-    import model  # only to draw identical synthetic weights; no CUDA call is made here
-    from oracle import stylegan2_oracle as O
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    torch.manual_seed(seed)
-    teacher = model.Generator(size, 512, 8)
-    student = model.Generator(size, 512, 8, generator_net_shape=STUDENT_SHAPES[size])
-    disc = model.Discriminator(size)
-    tp = {k: v.detach() for k, v in teacher.state_dict().items()}
-    sp = {k: v.detach() for k, v in student.state_dict().items()}
-    dp = {k: v.detach() for k, v in disc.state_dict().items()}
-    mask = synthetic_mask(size, 'cpu')
-    times = []
-    for it in range(warmup + steps):
-        z = [torch.randn(batch, 512), torch.randn(batch, 512)]
-        s_noise = [torch.randn(batch, 1, n.shape[2], n.shape[3]) for n in student.make_noise()]
-        t_noise = [torch.randn(batch, 1, n.shape[2], n.shape[3]) for n in teacher.make_noise()]
-        t0 = time.perf_counter()
-        O.kd_step(sp, tp, dp, size, z, s_noise, t_noise, 5, mask)
-        dt = time.perf_counter() - t0
-        if it >= warmup:
-            times.append(dt)
-    sec = sum(times) / len(times)
-    return batch / sec, sec, cores
+def cpu_baseline_from(ref, sample_b, steps, warmup):
+    if 'unavailable' in ref:
+        return None
+    return {'value': ref['images_per_s'], 'unit': 'images/s', 'cores': ref['cores'], 'kind': 'reference',
+            'sample': f"the reference's own model.py + op/ CPU fallbacks (oracle/_ref, unmodified; {ref['import']}), "
+                      f"same KD-like step, bounded sample: batch {sample_b} per step, {warmup} warm-up + {steps} "
+                      f"timed steps, torch {ref['torch']} CPU fp32, {ref['cores']} threads, "
+                      f"{ref['sec_per_step']:.2f} s/step"}
 
 
 def run_reference(args):
+    """`--impl reference`: the reference's own CPU implementation of the step, all host threads.  This process
+    imports neither the product package nor the oracle restatement."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    sample_b = 2
-    ips, sec, cores = cpu_reference_step_time(args.size, sample_b, args.steps, max(1, min(args.warmup, 1)))
+    sample_b = 2            # >= 2: Util/content_aware_pruning.py:108 squeezes the batch dim at 1 (SURVEY App. C)
+    warm = max(1, min(args.warmup, 2))
+    ref = run_ref_step('cpu', args.size, sample_b, args.steps, warm)
+    if 'unavailable' in ref:
+        print(json.dumps({'impl': 'reference', 'unavailable': ref['unavailable']}))
+        return
+    ips, sec = ref['images_per_s'], ref['sec_per_step']
     line = {
         'impl': 'reference', 'metric': f'images/sec KD step {args.size}px pruned StyleGAN2', 'value': ips,
         'unit': 'images/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': f'KD-like generator step {args.size}px, 70%-pruned student + full teacher + D, '
-                               f'bounded sample: batch {sample_b} per step (the GPU arm runs batch {args.batch}/GPU)'},
-        'cpu_baseline': {'value': ips, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
-                         'sample': f'oracle.kd_step, batch {sample_b}, {args.steps} timed steps, torch CPU fp32, '
-                                   f'{cores} threads'},
+        'config': kd_config(args.size, args.gpus),
+        'cpu_baseline': cpu_baseline_from(ref, sample_b, args.steps, warm),
         'e2e': {'value': ips, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
     print(json.dumps(line))
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
-    ap.add_argument('--warmup', type=int, default=5)
-    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--size', type=int, default=256, choices=[256, 1024])
-    ap.add_argument('--batch', type=int, default=16, help='images per GPU per step (weak scaling)')
-    ap.add_argument('--algo', default='auto', choices=['auto', 'simt', 'tc'])
-    ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--no-graph', action='store_true', help='launch every kernel from Python instead of one CUDA graph per step')
-    args = ap.parse_args()
-    if args.impl == 'reference':
-        return run_reference(args)
-    args.warmup = max(args.warmup, 3)
+# ------------------------------------------------------------------------------------------------
+def synthetic_mask(size, device):
+    """Stand-in for the BiSeNet face mask (Util/content_aware_pruning.py:61-117): centred ellipse."""
+    import torch
+    yy, xx = torch.meshgrid(torch.arange(size, device=device), torch.arange(size, device=device), indexing='ij')
+    c = (size - 1) / 2
+    return ((((yy - c) / (0.42 * size)) ** 2 + ((xx - c) / (0.34 * size)) ** 2) <= 1).float().view(1, 1, size, size)
 
-    from b200gan import dist as D, config, _lib
+
+class Ctx:
+    """Per-process setup shared by the product-arm configs."""
+
+    def __init__(self, args):
+        for p in (PKG, ROOT):
+            if p not in sys.path:
+                sys.path.insert(0, p)
+        import torch
+        from b200gan import dist as D, config, _lib
+        self.torch, self.D, self.config, self.lib = torch, D, config, _lib
+        self.local = D.init_from_env()
+        self.rank, self.world = D.get_rank(), D.get_world_size()
+        assert torch.cuda.is_available(), 'bench.py (impl b200) needs a CUDA device; there is no CPU fallback'
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device('cuda', self.local)
+        algo = {'simt': config.ALGO_SIMT_FP32, 'tc': config.ALGO_TCGEN05_TF32}.get(args.algo)
+        if algo is None:
+            algo = config.best_available_algo()
+        config.set_default_algo(algo)
+        self.algo = algo
+        self.tf32 = algo == config.ALGO_TCGEN05_TF32
+        torch.manual_seed(1234 + self.rank)
+
+    def barrier_sync(self):
+        self.D.synchronize()
+        self.torch.cuda.synchronize(self.dev)
+
+    def max_over_ranks(self, ms):
+        t = self.torch.tensor([ms], device=self.dev)
+        if self.world > 1:
+            self.torch.distributed.all_reduce(t, op=self.torch.distributed.ReduceOp.MAX)
+        return float(t.item())
+
+    def time_steps(self, fn, n):
+        """EXACTLY n calls of fn(i) between barrier + synchronize on both sides; device time, max over ranks."""
+        torch = self.torch
+        self.barrier_sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            fn(i)
+        e1.record()
+        self.barrier_sync()
+        return self.max_over_ranks(e0.elapsed_time(e1))
+
+    def broadcast_module(self, m):
+        if self.world > 1:
+            for t in list(m.parameters()) + list(m.buffers()):
+                self.torch.distributed.broadcast(t.data, 0)
+
+
+def bench_kd(args, cx):
+    torch, D, config, _lib = cx.torch, cx.D, cx.config, cx.lib
     from b200gan.kd import KDStep
     import model
+    rank, world, dev = cx.rank, cx.world, cx.dev
+    size = args.size
+    strong = args.scaling == 'strong'
+    if strong:
+        assert GLOBAL_BATCH % world == 0, f'global batch {GLOBAL_BATCH} does not shard over {world} ranks'
+        B = GLOBAL_BATCH // world
+    else:
+        B = GLOBAL_BATCH
+    args.warmup = max(args.warmup, 3)
+    inject = 5
 
-    local = D.init_from_env()
-    rank, world = D.get_rank(), D.get_world_size()
-    assert torch.cuda.is_available(), 'bench.py (impl b200) needs a CUDA device; there is no CPU fallback'
-    torch.cuda.set_device(local)
-    dev = torch.device('cuda', local)
-
-    algo = {'simt': config.ALGO_SIMT_FP32, 'tc': config.ALGO_TCGEN05_TF32}.get(args.algo)
-    if algo is None:
-        algo = config.best_available_algo()
-    config.set_default_algo(algo)
-
-    torch.manual_seed(1234 + rank)
-    size, B = args.size, args.batch
     teacher = model.Generator(size, 512, 8).to(dev)
     student = model.Generator(size, 512, 8, generator_net_shape=STUDENT_SHAPES[size]).to(dev)
     disc = model.Discriminator(size).to(dev)
-    if world > 1:   # identical replicas on every rank
-        for m in (teacher, student, disc):
-            for t in list(m.parameters()) + list(m.buffers()):
-                torch.distributed.broadcast(t.data, 0)
+    for m in (teacher, student, disc):
+        cx.broadcast_module(m)                      # identical replicas on every rank
     kd = KDStep(student, teacher, disc, mask=synthetic_mask(size, dev))
-    inject = 5
 
-    def fresh_latents():
-        return [torch.randn(B, 512, device=dev), torch.randn(B, 512, device=dev)]
+    def fresh_latents(b):
+        return [torch.randn(b, 512, device=dev), torch.randn(b, 512, device=dev)]
 
-    def barrier_sync():
-        D.synchronize()
-        torch.cuda.synchronize(dev)
-
-    # ---------------- device-resident timing (value)
     use_graph = not args.no_graph
-    if use_graph:
-        kd.capture(B, inject)            # includes 3 eager warm-up steps on a side stream
-        run_step = lambda z: kd.step_graphed(z)
-    else:
-        run_step = lambda z: kd.step(z, inject)
-    for _ in range(args.warmup):
-        run_step(fresh_latents())
-    lat = [fresh_latents() for _ in range(args.steps)]
-    sampler = ClockSampler(local)
-    barrier_sync()
-    if rank == 0:
-        sampler.start()
-    n0 = _lib.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        run_step(lat[i])
-    e1.record()
-    barrier_sync()
-    launches = (kd.launches_per_replay * args.steps) if use_graph else (_lib.launch_count() - n0)
-    clocks = sampler.stop() if rank == 0 else None
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
-    ms_total = float(ms.item())
+
+    def measure(kd, B, steps, warmup, with_clocks):
+        """value leg: device-resident latents.  Returns (ms_total, launches, clocks)."""
+        if use_graph:
+            kd.capture(B, inject)            # includes 3 eager warm-up steps on a side stream
+            run_step = lambda z: kd.step_graphed(z)
+        else:
+            run_step = lambda z: kd.step(z, inject)
+        for _ in range(warmup):
+            run_step(fresh_latents(B))
+        lat = [fresh_latents(B) for _ in range(min(steps, 64))]
+        sampler = ClockSampler(cx.local) if (with_clocks and rank == 0) else None
+        cx.barrier_sync()
+        if sampler:
+            sampler.start()
+        n0 = _lib.launch_count()
+        ms_total = cx.time_steps(lambda i: run_step(lat[i % len(lat)]), steps)
+        launches = (kd.launches_per_replay * steps) if use_graph else (_lib.launch_count() - n0)
+        return ms_total, launches, (sampler.stop() if sampler else None), run_step, lat
+
+    ms_total, launches, clocks, run_step, lat = measure(kd, B, args.steps, args.warmup, True)
     value = world * B * args.steps / (ms_total / 1e3)
 
     # ---------------- end-to-end through the public API: pinned host latents in, loss out, every step
-    hz = [[torch.randn(B, 512).pin_memory(), torch.randn(B, 512).pin_memory()] for _ in range(args.steps)]
+    hz = [[torch.randn(B, 512).pin_memory(), torch.randn(B, 512).pin_memory()] for _ in range(min(args.steps, 64))]
     for _ in range(2):
         kd.step_from_host(hz[0], inject)
-    barrier_sync()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    for i in range(args.steps):
-        kd.step_from_host(hz[i], inject)
-    f1.record()
-    barrier_sync()
-    ems = torch.tensor([f0.elapsed_time(f1)], device=dev)
-    if world > 1:
-        torch.distributed.all_reduce(ems, op=torch.distributed.ReduceOp.MAX)
-    e2e_value = world * B * args.steps / (float(ems.item()) / 1e3)
+    e2e_ms = cx.time_steps(lambda i: kd.step_from_host(hz[i % len(hz)], inject), args.steps)
+    e2e_value = world * B * args.steps / (e2e_ms / 1e3)
+
+    # ---------------- sustained leg: the same step for >= 200 iterations (clocks settle under the power cap)
+    sustained = None
+    if args.sustained_steps > 0:
+        sampler = ClockSampler(cx.local) if rank == 0 else None
+        cx.barrier_sync()
+        if sampler:
+            sampler.start()
+        sus_ms = cx.time_steps(lambda i: run_step(lat[i % len(lat)]), args.sustained_steps)
+        sc = sampler.stop() if sampler else None
+        sustained = {'steps': args.sustained_steps, 'ms_per_step': sus_ms / args.sustained_steps,
+                     'value': world * B * args.sustained_steps / (sus_ms / 1e3), 'unit': 'images/s',
+                     'timed_region_s': sus_ms / 1e3, 'clocks': sc}
 
     # ---------------- per-kernel CUDA events (roofline): eager steps, events on the launching stream
     prof = config.KernelProfiler()
     overlap_stream, kd.teacher_stream = kd.teacher_stream, None   # one stream: a kernel's events bracket only itself
     kd.step(lat[0], inject)
-    barrier_sync()
+    cx.barrier_sync()
     config.set_profiler(prof)
     prof_steps = min(args.steps, 5)
     for i in range(prof_steps):
-        kd.step(lat[i], inject)
-    barrier_sync()
+        kd.step(lat[i % len(lat)], inject)
+    cx.barrier_sync()
     config.set_profiler(None)
     kd.teacher_stream = overlap_stream
 
@@ -264,14 +311,14 @@ def main():
             real = teacher(z, return_rgb_list=True, inject_index=inject)
         (3.0 * (real[-1] - fake[-1]).abs().mean()).backward()
         kd.bucket.pack_grads()
-    zs = fresh_latents()
+    zs = fresh_latents(B)
     side = torch.cuda.Stream(device=dev)
     side.wait_stream(torch.cuda.current_stream(dev))
     with torch.cuda.stream(side):
         for _ in range(2):
             slice_step(zs)
     torch.cuda.current_stream(dev).wait_stream(side)
-    barrier_sync()
+    cx.barrier_sync()
     if use_graph:
         sg = torch.cuda.CUDAGraph()
         with torch.cuda.graph(sg):
@@ -280,14 +327,24 @@ def main():
     else:
         run_slice = lambda: slice_step(zs)
     run_slice()
-    barrier_sync()
+    cx.barrier_sync()
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s0.record()
     for i in range(args.steps):
         run_slice()
     s1.record()
-    barrier_sync()
+    cx.barrier_sync()
     slice_ms = s0.elapsed_time(s1) / args.steps
+
+    # ---------------- the other scaling mode, same run (N > 1 only: at N = 1 the two coincide)
+    other = None
+    if world > 1 and not args.no_second_mode:
+        B2 = GLOBAL_BATCH if strong else GLOBAL_BATCH // world
+        del kd.graph
+        kd.graph = None
+        ms2, _, _, _, _ = measure(kd, B2, args.steps, args.warmup, False)
+        other = {'scaling': 'weak' if strong else 'strong', 'per_gpu_batch': B2, 'global_batch': B2 * world,
+                 'value': world * B2 * args.steps / (ms2 / 1e3), 'unit': 'images/s', 'ms_per_step': ms2 / args.steps}
 
     if rank != 0:
         return
@@ -314,21 +371,25 @@ def main():
         r = summ[dom]
         ach = r['flops'] / (r['ms'] / 1e3) / 1e12
         tf32 = 'algo1' in dom
-        # TF32 tensor peak = half the measured bf16 peak (same pipe, half the rate); fp32 SIMT kernels are
-        # reported against the same tensor-pipe number so the fraction shows the distance to the target
-        peak = peaks['bf16_tflops_sustained'] / 2
+        # The per-kernel events come from a short eager burst (a few steps, each kernel bracketed alone): the BURST
+        # tensor peak applies.  TF32 peak = half the measured bf16 peak (same pipe, half the rate); fp32 SIMT kernels
+        # are reported against the same number so the fraction shows the distance to the target.
+        peak = peaks['bf16_tflops'] / 2
         traffic, traffic_src = None, None
-        tpath = os.path.join(ROOT, 'profiles', 'r1_traffic.json')
-        if tf32 and os.path.exists(tpath):
-            tj = json.load(open(tpath)).get('conv_tc_family')
-            if tj:
-                traffic, traffic_src = tj['dram_bytes_per_launch'], tj['source']
+        for tname in ('r2_traffic.json', 'r1_traffic.json'):
+            tpath = os.path.join(ROOT, 'profiles', tname)
+            if tf32 and os.path.exists(tpath):
+                tj = json.load(open(tpath)).get('conv_tc_family')
+                if tj:
+                    traffic, traffic_src = tj['dram_bytes_per_launch'], tj['source']
+                    break
         roofline = {'kernel': dom, 'bound': 'tensor', 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s',
                     'frac': ach / peak, 'traffic': traffic, 'traffic_source': traffic_src,
                     'algorithmic_bytes_per_launch': r['bytes'] / max(r['launches'], 1),
                     'algorithmic_flops_per_launch': r['flops'] / max(r['launches'], 1),
                     'avg_launch_us': r['ms'] / max(r['launches'], 1) * 1e3,
-                    'peak_source': f"{peaks['source']} bf16 sustained {peaks['bf16_tflops_sustained']} TF/s / 2 (TF32)",
+                    'peak_source': f"{peaks['source']} bf16 BURST {peaks['bf16_tflops']} TF/s / 2 (TF32); kernels "
+                                   f"timed alone in a {prof_steps}-step eager burst",
                     'precision': 'tf32 tcgen05' if tf32 else 'fp32 SIMT (no tensor pipe)'}
     hbm = {}
     for n in ('fir_nhwc',):
@@ -347,34 +408,44 @@ def main():
     cl = {k: v for k, v in layers.items() if k.startswith('conv_') and v['tflops']}
     top_layers = {k: cl[k] for k in sorted(cl, key=lambda k: -cl[k]['avg_launch_us'] * cl[k]['launches_per_step'])[:6]}
 
-    cpu = None
+    cpu, ref_gpu = None, None
     if world == 1 and not args.no_cpu_baseline:
-        ips, sec, cores = cpu_reference_step_time(size, 2, 2, 1)
-        cpu = {'value': ips, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
-               'sample': f'oracle.kd_step (CPU restatement of the reference path), batch 2, 1 warm-up + 2 timed steps, '
-                         f'torch CPU fp32, {cores} threads, {sec:.2f} s/step'}
+        ref = run_ref_step('cpu', size, 2, 2, 1, timeout=600)
+        cpu = cpu_baseline_from(ref, 2, 2, 1) or {'unavailable': ref.get('unavailable')}
+    if world == 1 and not args.no_ref_gpu:
+        # the real competitor: the reference CUDA path -- its SIMT op/*.cu compiled for sm_100a +
+        # cuDNN grouped convolutions (TF32 allowed, torch's default) -- on this same B200, full batch, CUDA events
+        torch.cuda.empty_cache()
+        rg = run_ref_step('cuda', size, GLOBAL_BATCH, 30 if size == 256 else 6, 8 if size == 256 else 2, timeout=900)
+        if 'unavailable' in rg:
+            ref_gpu = rg
+        else:
+            ref_gpu = {'value': rg['images_per_s'], 'unit': 'images/s', 'ms_per_step': rg['sec_per_step'] * 1e3,
+                       'batch': rg['batch'], 'steps': rg['steps'], 'warmup': rg['warmup'], 'tf32': rg['tf32'],
+                       'speedup_of_this_repo': value / rg['images_per_s'],
+                       'what': "the reference's own model.py + op/*.cu (sm_100a JIT build) + cuDNN on this B200, "
+                               'same KD-like step, eager (no CUDA graph: the reference has none)'}
 
     gf = GFLOP_PER_IMG[size]
     line = {
         'metric': f'images/sec KD step {size}px pruned StyleGAN2', 'value': value, 'unit': 'images/s',
         'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_total / args.steps,
-        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'tf32' if algo == config.ALGO_TCGEN05_TF32 else 'f32', 'data': 'synthetic',
-        'config': {'workload': f'KD-like generator step {size}px: 70%-pruned student {STUDENT_SHAPES[size][0]}/'
-                               f'{STUDENT_SHAPES[size][-1]}ch f+b, full teacher f, discriminator f+dgrad, masked L1 KD, '
-                               f'grad all-reduce, fused Adam; batch {B}/GPU; style mixing inject_index={inject}',
-                   'global_batch': B * world, 'parallelism': f'dp{world}',
-                   'l2': 'per-step working set (>=4 GB of activations) exceeds the 126 MB L2; no explicit flush',
-                   'conv_algo': 'tcgen05-tf32' if algo == config.ALGO_TCGEN05_TF32 else 'simt-fp32',
+        'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None,
+        'dtype': 'tf32' if cx.tf32 else 'f32', 'data': 'synthetic',
+        'config': kd_config(size, world) if strong else dict(kd_config(size, world), global_batch=B * world),
+        'config_detail': {'per_gpu_batch': B, 'conv_algo': 'tcgen05-tf32' if cx.tf32 else 'simt-fp32',
                    'launch': ('one CUDA graph per step' if use_graph else 'eager launches') + (', teacher forward on a parallel graph branch' if kd.teacher_stream is not None else ''),
                    'kernel_timing': f'CUDA events around each native launch over {prof_steps} eager steps in this run'},
-        'e2e': {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': 2 * B * 512 * 4,
-                'd2h_bytes_per_step': 4},
+        'e2e': {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': 2 * B * 512 * 4 * world,
+                'd2h_bytes_per_step': 4 * world},
         'gpu_launches': int(launches),
         'clocks': clocks,
         'roofline': roofline,
         'roofline_hbm': hbm,
         'cpu_baseline': cpu,
+        'reference_gpu': ref_gpu,
+        'sustained': sustained,
+        ('weak_scaling' if strong else 'strong_scaling'): other,
         'generator_slice': {'ms_per_step': slice_ms, 'images_per_s': B / (slice_ms / 1e3),
                             'tflops': B * (3 * gf['student'] + gf['teacher']) / slice_ms,
                             'note': 'student f+b + teacher f only, rank 0'},
@@ -384,7 +455,148 @@ def main():
     print(json.dumps(line))
 
 
-if __name__ == '__main__':
-    main()
+def bench_fid(args, cx):
+    """BASELINE configs[4]: get_fid.py's sampling loop (Evaluation/fid.py:19-38) -- 256px pruned generator, batch 64
+    per step sharded over the ranks, truncation 1, fresh latents and noise every batch, under no_grad.  Generator
+    only (Inception and the FID arithmetic are outside the path).  One CUDA graph per batch; e2e = pinned-host
+    latents in, images back to pinned host memory."""
+    torch = cx.torch
+    import model
+    dev, world, rank = cx.dev, cx.world, cx.rank
+    size, gb = 256, 64
+    assert gb % world == 0
+    B = gb // world
+    args.warmup = max(args.warmup, 3)
+    gen = model.Generator(size, 512, 8, generator_net_shape=STUDENT_SHAPES[size]).to(dev).eval()
+    cx.broadcast_module(gen)
+    for p in gen.parameters():
+        p.requires_grad_(False)
+    z_static = torch.zeros(B, 512, device=dev)
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side), torch.no_grad():
+        for _ in range(3):
+            gen([z_static], truncation=1)
+    torch.cuda.current_stream(dev).wait_stream(side)
+    torch.cuda.synchronize(dev)
+    graph = torch.cuda.CUDAGraph()
+    n0 = cx.lib.launch_count()
+    with torch.cuda.graph(graph), torch.no_grad():
+        img_static = gen([z_static], truncation=1)
+    per_replay = cx.lib.launch_count() - n0
+
+    def step(i):
+        z_static.normal_()
+        graph.replay()
+    for _ in range(args.warmup):
+        step(0)
+    sampler = ClockSampler(cx.local) if rank == 0 else None
+    cx.barrier_sync()
+    if sampler:
+        sampler.start()
+    ms = cx.time_steps(step, args.steps)
+    clocks = sampler.stop() if sampler else None
+    value = gb * args.steps / (ms / 1e3)
+    hz = [torch.randn(B, 512).pin_memory() for _ in range(8)]
+    himg = torch.empty(B, 3, size, size).pin_memory()
+
+    def e2e_step(i):
+        z_static.copy_(hz[i % 8], non_blocking=True)
+        graph.replay()
+        himg.copy_(img_static, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+    e2e_step(0)
+    e2e_ms = cx.time_steps(e2e_step, args.steps)
+    if rank != 0:
+        return
+    gf = GFLOP_PER_IMG[size]['student']
+    print(json.dumps({
+        'metric': 'images/sec get_fid.py sampling 256px pruned StyleGAN2', 'value': value, 'unit': 'images/s',
+        'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps,
+        'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'tf32' if cx.tf32 else 'f32',
+        'data': 'synthetic',
+        'config': {'workload': 'get_fid.py sampling loop: 256px 70%-pruned generator forward, batch 64 per step '
+                               '(sharded over ranks), truncation 1, fresh latents + noise per batch',
+                   'global_batch': gb, 'per_gpu_batch': B, 'parallelism': f'dp{world}', 'launch': 'one CUDA graph per batch',
+                   'l2': 'activations of a batch (>1 GB) exceed the 126 MB L2'},
+        'e2e': {'value': gb * args.steps / (e2e_ms / 1e3), 'unit': 'images/s', 'h2d_bytes_per_step': gb * 512 * 4,
+                'd2h_bytes_per_step': gb * 3 * size * size * 4},
+        'gpu_launches': int(per_replay * args.steps), 'clocks': clocks,
+        'generator_tflops': gb * gf / (ms / args.steps), 'roofline': None, 'cpu_baseline': None}))
+
+
+def bench_saliency(args, cx):
+    """BASELINE configs[2]: content-aware saliency, full 256px generator, batches of 8 latents (forward with the
+    autograd graph, sparse +-1 cotangent, backward, per-channel scores).  One step = one batch of 8.  Reports both
+    engines: exact-fp32 SIMT and the fp32-accurate tensor-pipe split (3xTF32) when available."""
+    torch, config = cx.torch, cx.config
+    import numpy as np
+    import model
+    from b200gan import saliency as S
+    dev, rank, world = cx.dev, cx.rank, cx.world
+    gen = model.Generator(256, 512, 8).to(dev)
+    cx.broadcast_module(gen)
+    bs = 8
+    res = {}
+    modes = [('simt_fp32', config.ALGO_SIMT_FP32)]
+    if hasattr(config, 'ALGO_TCGEN05_3XTF32'):
+        modes.append(('tcgen05_3xtf32', config.ALGO_TCGEN05_3XTF32))
+    for name, algo in modes:
+        def one(i):
+            S.content_aware_scores(gen, bs, bs, 0.05, dev, seed=100 + i + 1000 * rank, algo=algo) \
+                if 'algo' in S.content_aware_scores.__code__.co_varnames else \
+                S.content_aware_scores(gen, bs, bs, 0.05, dev, seed=100 + i + 1000 * rank)
+        for i in range(max(1, min(args.warmup, 2))):
+            one(i)
+        ms = cx.time_steps(one, args.steps)
+        res[name] = {'ms_per_batch_of_8': ms / args.steps, 'latents_per_s': world * bs * args.steps / (ms / 1e3),
+                     'tflops': world * bs * 3 * GFLOP_PER_IMG[256]['teacher'] / (ms / args.steps)}
+    if rank != 0:
+        return
+    best = max(res, key=lambda k: res[k]['latents_per_s'])
+    print(json.dumps({
+        'metric': 'latents/sec content-aware saliency 256px full StyleGAN2', 'value': res[best]['latents_per_s'],
+        'unit': 'latents/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': res[best]['ms_per_batch_of_8'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'saliency pass (Util/content_aware_pruning.py:200-249): full 256px generator fwd+bwd '
+                               'per batch of 8 latents, whole batches per rank, host-side mask/noise included',
+                   'engine': best, 'parallelism': f'dp{world}'},
+        'engines': res, 'roofline': None, 'cpu_baseline': None, 'gpu_launches': None, 'e2e': None}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--config', default='kd256', choices=['kd256', 'kd1024', 'fid256', 'saliency256'])
+    ap.add_argument('--size', type=int, default=None, choices=[256, 1024])
+    ap.add_argument('--scaling', default='strong', choices=['strong', 'weak'],
+                    help='strong: global batch 16 sharded over the ranks (north star); weak: 16 per GPU')
+    ap.add_argument('--algo', default='auto', choices=['auto', 'simt', 'tc'])
+    ap.add_argument('--sustained-steps', type=int, default=200)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-ref-gpu', action='store_true')
+    ap.add_argument('--no-second-mode', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='launch every kernel from Python instead of one CUDA graph per step')
+    args = ap.parse_args()
+    if args.size is None:
+        args.size = 1024 if args.config == 'kd1024' else 256
+    if args.impl == 'reference':
+        return run_reference(args)
+    cx = Ctx(args)
+    if args.config in ('kd256', 'kd1024'):
+        bench_kd(args, cx)
+    elif args.config == 'fid256':
+        bench_fid(args, cx)
+    else:
+        bench_saliency(args, cx)
+    import torch
     if torch.distributed.is_available() and torch.distributed.is_initialized():
         torch.distributed.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -1,5 +1,15 @@
-"""Process-wide switches of the hot path (thread-local so DataParallel replicas do not race)."""
+"""Process-wide switches of the hot path.
+
+Convolution engine selection, in order of precedence:
+  1. the calling thread's `use_algo(...)` / `exact_fp32()` context,
+  2. a context entered by ANOTHER thread (nn.DataParallel runs the replicas in worker threads while the caller
+     sits inside its `with` block -- train.py:522-525, get_fid.py:27),
+  3. the process default: `CAGC_CONV_ALGO` = `tc` | `simt` | `auto` (default `auto`: the tcgen05 TF32 path when
+     the current device is sm_100, which is what an unmodified train.py / get_fid.py therefore runs on).
+The autograd backward of a layer uses the engine its forward captured (it runs on an autograd thread).
+"""
 import contextlib
+import os
 import threading
 
 _state = threading.local()
@@ -7,7 +17,9 @@ _state = threading.local()
 ALGO_SIMT_FP32 = 0   # exact fp32 SIMT engine (saliency pass, validation)
 ALGO_TCGEN05_TF32 = 1  # sm_100a tensor pipe, TF32 operands / fp32 accumulate (reference cuDNN convs also run TF32)
 
-_default_algo = ALGO_SIMT_FP32
+_default_algo = {'simt': ALGO_SIMT_FP32, 'tc': ALGO_TCGEN05_TF32}.get(os.environ.get('CAGC_CONV_ALGO', 'auto').lower())
+_shared_lock = threading.Lock()
+_shared_stack = []      # contexts currently open in any thread (innermost last)
 
 
 def set_default_algo(algo: int):
@@ -21,16 +33,34 @@ def best_available_algo() -> int:
 
 
 def conv_algo() -> int:
-    return getattr(_state, 'algo', _default_algo)
+    global _default_algo
+    a = getattr(_state, 'algo', None)
+    if a is not None:
+        return a
+    if _shared_stack:
+        try:
+            return _shared_stack[-1]
+        except IndexError:
+            pass
+    if _default_algo is None:
+        _default_algo = best_available_algo()      # resolved on first use: needs the CUDA context
+    return _default_algo
 
 
 @contextlib.contextmanager
 def use_algo(algo: int):
     prev = getattr(_state, 'algo', None)
     _state.algo = int(algo)
+    with _shared_lock:
+        _shared_stack.append(int(algo))
     try:
         yield
     finally:
+        with _shared_lock:
+            for i in range(len(_shared_stack) - 1, -1, -1):
+                if _shared_stack[i] == int(algo):
+                    del _shared_stack[i]
+                    break
         if prev is None:
             del _state.algo
         else:

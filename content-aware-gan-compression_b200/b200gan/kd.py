@@ -20,7 +20,8 @@ from ._lib import lib, check
 
 class KDStep:
     def __init__(self, student, teacher, discriminator, lr: float = 0.002 * 0.8, betas=(0.0, 0.99 ** 0.8),
-                 eps: float = 1e-8, kd_l1_lambda: float = 3.0, mask: Optional[torch.Tensor] = None):
+                 eps: float = 1e-8, kd_l1_lambda: float = 3.0, mask: Optional[torch.Tensor] = None,
+                 kd_mode: str = 'Output_Only'):
         self.student, self.teacher, self.disc = student, teacher, discriminator
         for p in teacher.parameters():
             p.requires_grad_(False)
@@ -35,6 +36,9 @@ class KDStep:
         self.lr, self.betas, self.eps = lr, betas, eps
         self.kd_l1_lambda = kd_l1_lambda
         self.mask = mask
+        if kd_mode not in ('Output_Only', 'Intermediate'):
+            raise ValueError(f'kd_mode {kd_mode!r}: expected Output_Only or Intermediate (train.py:163-169)')
+        self.kd_mode = kd_mode
         self.device = self.bucket.flat_param.device
         self.t_dev = torch.zeros(1, device=self.device)      # Adam step count, device-resident (graph-safe)
         self.graph = None
@@ -54,17 +58,23 @@ class KDStep:
             self.teacher_stream.wait_event(ready)
             with torch.cuda.stream(self.teacher_stream), torch.no_grad():
                 real = self.teacher(z, return_rgb_list=True, inject_index=inject_index, noise=t_noise)
-                real[-1].record_stream(main)
+                for r in real:
+                    r.record_stream(main)
         else:
             with torch.no_grad():
                 real = self.teacher(z, return_rgb_list=True, inject_index=inject_index, noise=t_noise)
         g_loss = F.softplus(-self.disc(fake[-1].contiguous(memory_format=torch.channels_last))).mean()
         if self.teacher_stream is not None:
             main.wait_stream(self.teacher_stream)
-        s_img, t_img = fake[-1], real[-1]
-        if self.mask is not None:
-            s_img, t_img = s_img * self.mask, t_img * self.mask
-        kd = self.kd_l1_lambda * torch.mean(torch.abs(t_img - s_img))
+        if self.kd_mode == 'Output_Only':                      # train.py:163-164
+            s_img, t_img = fake[-1], real[-1]
+            if self.mask is not None:
+                s_img, t_img = s_img * self.mask, t_img * self.mask
+            kd = self.kd_l1_lambda * torch.mean(torch.abs(t_img - s_img))
+        else:
+            # train.py:165-169: every resolution of the two rgb lists; the comprehension re-binds both names to the
+            # list entries, so the content mask (applied to the last pair only, :157-158) does not enter this mode
+            kd = self.kd_l1_lambda * sum(torch.mean(torch.abs(t - f)) for t, f in zip(real, fake))
         return g_loss, kd
 
     def step(self, z: List[torch.Tensor], inject_index: int, s_noise=None, t_noise=None) -> torch.Tensor:
@@ -83,7 +93,15 @@ class KDStep:
                                      self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.bucket.numel,
                                      self.lr, b1, b2, self.eps, 1.0 / D.get_world_size(), 1.0, 1.0,
                                      self.t_dev.data_ptr()), 'adam_step')
+        self._bump_versions()
         return total.detach()
+
+    def _bump_versions(self):
+        """The fused Adam kernel writes the parameters behind autograd's back (raw pointer into the flat bucket):
+        bump every parameter's version counter so that anything keyed on it -- the frozen-weight operand cache of
+        b200gan.modconv when the student is frozen for a discriminator step (train.py:247), autograd's saved-tensor
+        checks -- sees the update."""
+        torch._C._increment_version(self.bucket.params)
 
     # ------------------------------------------------------------------ CUDA-graph form
     def capture(self, batch: int, inject_index: int, style_dim: int = 512):
@@ -115,6 +133,7 @@ class KDStep:
         for dst, src in zip(self.z_static, z):
             dst.copy_(src, non_blocking=True)
         self.graph.replay()
+        self._bump_versions()          # a replay runs the Adam kernel too; the capture-time bump is not replayed
         return self.loss_static
 
     def step_from_host(self, z_host: List[torch.Tensor], inject_index: int) -> float:

@@ -226,6 +226,9 @@ class _StyledConvFn(Function):
                 x_in, s_arg, falgo = xb, s_p.data_ptr(), config.ALGO_SIMT_FP32
             w_fwd = prep.w_fwd
             if noise is not None:
+                require_cuda(noise, 'ModulatedConv2d(noise)')
+                if noise.device != dev:
+                    raise RuntimeError(f'noise lives on {noise.device}, the activation on {dev}')
                 noise = noise.detach().contiguous()
                 nb = noise.shape[0]
                 ho, wo = (2 * h, 2 * w) if upsample else (h, w)

@@ -77,8 +77,9 @@ def content_aware_scores(generator, n_sample: int, batch_size: int, noise_prob: 
     batches (in batch order) of per-layer score vectors.
 
     seed=None: consume the global torch / numpy RNG streams exactly like the reference (single process).
-    seed=int : every batch owns its RNG streams (torch.Generator / RandomState seeded with seed+batch),
-               which makes the result independent of how batches are sharded over ranks.
+    seed=int : every batch owns its RNG stream (numpy RandomState seeded with seed+batch: latents, per-layer
+               noise, salt & pepper, in that order), which makes the result independent of how batches are
+               sharded over ranks and reproducible on any host (tests/golden/config3_saliency.npz).
     """
     mask_fn = mask_fn or default_mask
     sizes = batch_sizes(n_sample, batch_size)
@@ -95,10 +96,12 @@ def content_aware_scores(generator, n_sample: int, batch_size: int, noise_prob: 
                 z = torch.randn(b, latent_dim).to(device)
                 noise, rng = None, np.random
             else:
-                gen = torch.Generator(device='cpu').manual_seed(seed + idx)
-                z = torch.randn(b, latent_dim, generator=gen).to(device)
-                noise = [torch.randn(b, 1, n.shape[2], n.shape[3], generator=gen).to(device) for n in g.make_noise()]
+                # one numpy RandomState per batch (frozen, platform-independent stream): latents, then the per-layer
+                # noise maps in execution order, then the salt & pepper draws continue the same stream
                 rng = np.random.RandomState(seed + idx)
+                z = torch.from_numpy(rng.standard_normal((b, latent_dim)).astype(np.float32)).to(device)
+                noise = [torch.from_numpy(rng.standard_normal((b, 1, n.shape[2], n.shape[3])).astype(np.float32)).to(device)
+                         for n in g.make_noise()]
             generator.zero_grad()
             img = generator([z], noise=noise) if noise is not None else generator([z])
             noisy = noisy_images(img, mask_fn, noise_prob, rng)

@@ -44,6 +44,22 @@ inline int launched(const char* what) {
         if (_rc != 0) return _rc; \
     } while (0)
 
+// One-time-per-DEVICE flags.  cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device (per-context)
+// property: a single process that drives several GPUs (nn.DataParallel, the reference's only live multi-GPU
+// path: train.py:522-525, get_fid.py:27) must opt in on each of them.  One bit per device ordinal; threads racing on the
+// same device both set the (idempotent) attribute.
+using DeviceOnce = std::atomic<unsigned long long>;
+inline bool device_once_needed(const DeviceOnce& m) {
+    int d = 0;
+    cudaGetDevice(&d);
+    return !((m.load(std::memory_order_acquire) >> (d & 63)) & 1ull);
+}
+inline void device_once_done(DeviceOnce& m) {
+    int d = 0;
+    cudaGetDevice(&d);
+    m.fetch_or(1ull << (d & 63), std::memory_order_release);
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 template <typename T>

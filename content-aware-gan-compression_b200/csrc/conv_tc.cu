@@ -837,17 +837,17 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+static EncodeTiledFn lookup_encode() {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+        return (EncodeTiledFn)sym;
+    return nullptr;
+}
+
 static EncodeTiledFn get_encode() {
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void* sym = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = (EncodeTiledFn)sym;
-    }
+    static EncodeTiledFn fn = lookup_encode();      // thread-safe one-time initialisation (C++11 magic static)
     return fn;
 }
 
@@ -1735,11 +1735,11 @@ static int try_halo_conv(cudaStream_t stream, const ConvP& c, const char* what, 
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { *rc = fail(CAGC_E_INVALID, "%s: cuTensorMapEncodeTiled(B, halo) failed with %d", what, (int)r); return 1; }
     }
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_set{0};
+    if (device_once_needed(attr_set)) {
         cudaError_t e = cudaFuncSetAttribute(conv_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_budget);
         if (e != cudaSuccess) { *rc = fail((int)e, "%s: cudaFuncSetAttribute failed: %s", what, cudaGetErrorString(e)); return 1; }
-        attr_set = true;
+        device_once_done(attr_set);
     }
     const size_t smem = 2 * (size_t)p.a_stride + (size_t)p.b_stages * p.b_bytes + 1024;
     const int64_t items = (int64_t)p.strips * p.ytiles * c.B * n_tiles;
@@ -1840,13 +1840,13 @@ int cagc_tc_conv(cudaStream_t stream, const ConvP& c, const char* what) {
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(CAGC_E_INVALID, "%s: cuTensorMapEncodeTiled(B) failed with %d", what, (int)r);
     }
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_set{0};
+    if (device_once_needed(attr_set)) {
         cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget1);
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(conv_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget1);
         if (e != cudaSuccess) return fail((int)e, "%s: cudaFuncSetAttribute failed: %s", what, cudaGetErrorString(e));
-        attr_set = true;
+        device_once_done(attr_set);
     }
     // persistent form: whenever a double-buffered accumulator fits in TMEM (MT * n_tile <= 256 columns)
     static const int persist_env = [] { const char* e = getenv("CAGC_TC_PERSIST"); return e ? atoi(e) : 1; }();
@@ -1959,11 +1959,11 @@ int cagc_tc_conv_multi(cudaStream_t stream, const ConvP* ph, int nphase, const c
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { *rc = fail(CAGC_E_INVALID, "%s: cuTensorMapEncodeTiled(B) failed with %d", what, (int)r); return 1; }
     }
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_set{0};
+    if (device_once_needed(attr_set)) {
         cudaError_t e = cudaFuncSetAttribute(conv_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget1);
         if (e != cudaSuccess) { *rc = fail((int)e, "%s: cudaFuncSetAttribute failed: %s", what, cudaGetErrorString(e)); return 1; }
-        attr_set = true;
+        device_once_done(attr_set);
     }
     conv_tc_persist_kernel<<<kNumSMs, kThreads, smem, stream>>>(map_a, map_b, p);
     *rc = launched(what);
@@ -2055,12 +2055,12 @@ int cagc_tc_wgrad(cudaStream_t stream, const float* a, const float* g, float* pa
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
                     return fail(CAGC_E_INVALID, "%s: cuTensorMapEncodeTiled(g, up all taps) failed", what);
-                static bool attr_up = false;
-                if (!attr_up) {
+                static DeviceOnce attr_up{0};
+                if (device_once_needed(attr_up)) {
                     cudaError_t e = cudaFuncSetAttribute(wgrad_tc_alltaps_up_kernel,
                                                          cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget1);
                     if (e != cudaSuccess) return fail((int)e, "%s: cudaFuncSetAttribute failed: %s", what, cudaGetErrorString(e));
-                    attr_up = true;
+                    device_once_done(attr_up);
                 }
                 *nsplits_io = sp;
                 dim3 grid(ceil_div(a_pitch, kTileM), gr, sp);
@@ -2098,12 +2098,12 @@ int cagc_tc_wgrad(cudaStream_t stream, const float* a, const float* g, float* pa
             }
             if (encode_act_map(encode, &map_g, g, B, H, W, g_pitch, kWgPix, 1, 1, 1) != 0)
                 return fail(CAGC_E_INVALID, "%s: cuTensorMapEncodeTiled(g, all taps) failed", what);
-            static bool attr_all = false;
-            if (!attr_all) {
+            static DeviceOnce attr_all{0};
+            if (device_once_needed(attr_all)) {
                 cudaError_t e = cudaFuncSetAttribute(wgrad_tc_alltaps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                      kSmemBudget1);
                 if (e != cudaSuccess) return fail((int)e, "%s: cudaFuncSetAttribute failed: %s", what, cudaGetErrorString(e));
-                attr_all = true;
+                device_once_done(attr_all);
             }
             *nsplits_io = sp;
             dim3 grid(ceil_div(a_pitch, kTileM), gr, sp);
@@ -2144,11 +2144,11 @@ int cagc_tc_wgrad(cudaStream_t stream, const float* a, const float* g, float* pa
     const int Hg = mode == 1 ? 2 * H + ksize - 2 : H, Wg = mode == 1 ? 2 * W + ksize - 2 : W;
     r = encode_act_map(encode, &map_g, g, B, Hg, Wg, g_pitch, p.bw, p.bh, p.bb, p.g_stride);
     if (r != 0) return fail(CAGC_E_INVALID, "%s: cuTensorMapEncodeTiled(g) failed with %d", what, r);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_set{0};
+    if (device_once_needed(attr_set)) {
         cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
         if (e != cudaSuccess) return fail((int)e, "%s: cudaFuncSetAttribute failed: %s", what, cudaGetErrorString(e));
-        attr_set = true;
+        device_once_done(attr_set);
     }
     dim3 grid(ceil_div(a_pitch, kTileM), p.ntaps, nsplits);
     wgrad_tc_kernel<<<grid, kThreads, smem, stream>>>(map_a, map_g, p);
@@ -2233,8 +2233,8 @@ int cagc_tc_fir_nhwc(cudaStream_t stream, const float* in, const float* fir, con
     if (!p.n_main_chunks) map_main = map_tail;
     if (!p.tail_w) map_tail = map_main;
     const size_t smem = (size_t)p.stages * p.stage_stride + 128;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_set{0};
+    if (device_once_needed(attr_set)) {
         cudaError_t e = cudaFuncSetAttribute(fir_nhwc_stream_kernel<4, 4, PXT, true>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
         if (e == cudaSuccess)
@@ -2248,7 +2248,7 @@ int cagc_tc_fir_nhwc(cudaStream_t stream, const float* in, const float* fir, con
             e = cudaFuncSetAttribute(fir_nhwc_stream_kernel<4, 4, PXT, false>,
                                      cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) { *rc = fail((int)e, "fir_nhwc[stream]: cudaFuncSetAttribute failed"); return 1; }
-        attr_set = true;
+        device_once_done(attr_set);
     }
     if (smem > 100 * 1024) return 0;
     dim3 grid(p.n_main + n_tail, segs, B);
@@ -2262,7 +2262,13 @@ int cagc_tc_fir_nhwc(cudaStream_t stream, const float* in, const float* fir, con
 
 extern "C" {
 
-int cagc_tc_available(void) { return 1; }
+int cagc_tc_available(void) {
+    // the tcgen05 / TMA kernels exist only for sm_100: answer for the CURRENT device
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return (major == 10 && tc::get_encode() != nullptr) ? 1 : 0;
+}
 
 int cagc_modulate(cagc_stream_t stream_, const float* x, const float* s, float* out, int B, int H, int W, int pitch) {
     cudaStream_t stream = (cudaStream_t)stream_;

@@ -272,8 +272,10 @@ class StyledConv(nn.Module):
             f = 2 if self.conv.upsample else 1
             noise = input.new_empty(b, 1, h * f, w * f).normal_()
         act = self.activate
-        if act.negative_slope != 0.2 or abs(act.scale - math.sqrt(2)) > 1e-12:
-            # non-default activation constants: unfused tail
+        if act.negative_slope != 0.2 or abs(act.scale - math.sqrt(2)) > 1e-12 or \
+                (noise.requires_grad and torch.is_grad_enabled()):
+            # non-default activation constants, or a caller that optimises the noise maps themselves (the projector,
+            # Miscellaneous/Image2StyleGAN_util.py:54, sets noise.requires_grad): unfused, differentiable tail
             out, s = self.conv._run(input, style, s_p=_s)
             out = act(self.noise(out, noise=noise))
         else:

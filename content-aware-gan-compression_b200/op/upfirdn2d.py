@@ -84,7 +84,10 @@ class _UpFirDn2d(Function):
         out_h, out_w = out.shape[2:]
         g_pad = (kw - pad_x0 - 1, in_w * up_x - out_w * down_x + pad_x0 - up_x + 1,
                  kh - pad_y0 - 1, in_h * up_y - out_h * down_y + pad_y0 - up_y + 1)
-        ctx.save_for_backward(kernel, torch.flip(kernel, [0, 1]))
+        # flip(kernel) is cached per (long-lived) FIR buffer: a fresh tensor per call would miss the identity-keyed
+        # host-tap cache in the backward and cost one blocking device->host copy per Blur backward
+        from b200gan.modconv import _flipped
+        ctx.save_for_backward(kernel, _flipped(kernel))
         ctx.cfg = (up, down, pad, g_pad)
         return out
 

@@ -1,6 +1,10 @@
 import os
 import sys
 
+# tests state their engine explicitly (use_algo / exact_fp32); everything else is checked on the exact-fp32 engine.
+# The product default is `auto` = tcgen05 TF32 on sm_100 (b200gan/config.py).
+os.environ.setdefault('CAGC_CONV_ALGO', 'simt')
+
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -10,7 +14,7 @@ GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 # The drop-in boundary is the pair of top-level modules `model` and `op`
 # (SURVEY.md §8b): put the package dir first on sys.path so `import model`
 # binds to ours exactly as the reference scripts would see it.
-for p in (PKG, ROOT):
+for p in (PKG, ROOT, GOLDEN):
     if p not in sys.path:
         sys.path.insert(0, p)
 

@@ -166,7 +166,8 @@ def gen_layers():
 
 
 # ------------------------------------------------------------------ tiny generator
-TINY = dict(size=32, style_dim=32, n_mlp=2, net_shape=[12, 12, 12, 12, 8, 8, 6, 6])
+sys.path.insert(0, HERE)
+from synth import TINY, KD_TINY, CONFIG3  # noqa: E402  (shared with the tests)
 
 
 def salt_pepper_fn(mask, noise_pm1, hit):
@@ -262,11 +263,138 @@ def gen_generator():
     np.savez_compressed(os.path.join(HERE, 'generator_tiny.npz'), **out)
 
 
+# ------------------------------------------------------------------ discriminator + KD-like step
+def gen_kd_tiny():
+    """Reference `Discriminator` (model.py:740-798) forward + input gradient, and the KD-like generator step
+    composed from the reference's own modules the way train.py:280-308 / :145-169 composes them (student
+    forward with rgb list -> D -> g_nonsaturating_loss :215-218; teacher forward; content mask multiply
+    (Get_Masked_Tensor's effect on a constant mask); L1 KD in both kd_modes).  Weights / inputs are re-drawn
+    from seeds (tests/golden/synth.py): only the reference's OUTPUTS are stored."""
+    import synth
+    c = KD_TINY
+    out = {}
+    disc = synth.load_synth(ref_model.Discriminator(c['size']).double(), c['seed_disc'])
+    student = synth.load_synth(ref_model.Generator(c['size'], c['style_dim'], c['n_mlp'],
+                                                   generator_net_shape=c['student']).double(), c['seed_student'])
+    teacher = synth.load_synth(ref_model.Generator(c['size'], c['style_dim'], c['n_mlp'],
+                                                   generator_net_shape=c['teacher']).double(), c['seed_teacher'])
+    shapes = [(n.shape[2], n.shape[3]) for n in student.make_noise()]
+    z, noise2, rs = synth.latents_and_noise(c['seed_inputs'], c['batch'], c['style_dim'], shapes + shapes, n_latents=2)
+    z = [torch.from_numpy(a) for a in z]
+    s_noise = [torch.from_numpy(a) for a in noise2[:len(shapes)]]
+    t_noise = [torch.from_numpy(a) for a in noise2[len(shapes):]]
+    # (a) discriminator alone: logits and the gradient w.r.t. its input image
+    x = torch.from_numpy(rs.standard_normal((c['batch'], 3, c['size'], c['size']))).requires_grad_(True)
+    cot = torch.from_numpy(rs.standard_normal((c['batch'], 1)))
+    pred = disc(x)
+    gx, = torch.autograd.grad(pred, x, cot)
+    out['d_x'], out['d_cot'], out['d_pred'], out['d_gx'] = npy(x), npy(cot), npy(pred), npy(gx)
+    pred2 = disc(x[:2])                      # batch smaller than stddev_group (model.py:785)
+    out['d_pred_b2'] = npy(pred2)
+    # (b) KD-like step, both kd_modes (train.py:163-169)
+    mask = torch.from_numpy(synth.ellipse_mask(c['size']).astype(np.float64)).view(1, 1, c['size'], c['size'])
+    for p in disc.parameters():
+        p.requires_grad_(False)              # train.py:287
+    names = [n for n, _ in student.named_parameters()]
+    for mode in ('Output_Only', 'Intermediate'):
+        student.zero_grad()
+        fake_list = student(z, return_rgb_list=True, inject_index=c['inject'], noise=s_noise)   # train.py:291
+        g_loss = F.softplus(-disc(fake_list[-1])).mean()                                       # train.py:293-294, 215-218
+        real_list = teacher(z, return_rgb_list=True, inject_index=c['inject'], noise=t_noise)   # train.py:151
+        real_list = [r.detach() for r in real_list]
+        if mode == 'Output_Only':
+            kd = 3.0 * torch.mean(torch.abs(real_list[-1] * mask - fake_list[-1] * mask))       # train.py:157-164
+        else:
+            # train.py:165-169: the masked pair for the last image, the plain pairs are the loop's other items.  The
+            # reference loop re-binds fake_img to the list entries, i.e. it uses the UNMASKED student images and the
+            # unmasked teacher images for every resolution (fake_img_teacher_list is not masked): restated as such.
+            kd = 3.0 * sum(torch.mean(torch.abs(r - f)) for r, f in zip(real_list, fake_list))
+        total = g_loss + kd
+        total.backward()
+        out[f'{mode}.g_loss'], out[f'{mode}.kd'] = npy(g_loss), npy(kd)
+        for n, p in student.named_parameters():
+            out[f'{mode}.grad.{n}'] = npy(p.grad) if p.grad is not None else np.zeros(tuple(p.shape))
+        if mode == 'Output_Only':
+            out['fake_last'], out['real_last'] = npy(fake_list[-1]), npy(real_list[-1])
+    out['param_names'] = np.array(names)
+    out['d_keys'] = np.array(list(disc.state_dict().keys()))
+    out['student_keys'] = np.array(list(student.state_dict().keys()))
+    np.savez_compressed(os.path.join(HERE, 'kd_tiny.npz'), **out)
+
+
+# ------------------------------------------------------------------ RNG consumption order
+def gen_rng_order():
+    """`randomize_noise=True`: NoiseInjection draws `image.new_empty(B,1,H,W).normal_()` per layer in call order
+    (model.py:299-301).  Store the reference image produced by its INTERNAL draws under a fixed seed together
+    with the noise list obtained by replaying the recipe (one normal_() per layer, execution order, output
+    resolution) under the same seed -- and assert here that feeding that list explicitly reproduces the image."""
+    import synth
+    out = {}
+    g = synth.load_synth(ref_model.Generator(TINY['size'], TINY['style_dim'], TINY['n_mlp'],
+                                             generator_net_shape=TINY['net_shape']).double(), 41)
+    b = 3
+    z = torch.from_numpy(np.random.RandomState(42).standard_normal((b, TINY['style_dim'])))
+    torch.manual_seed(99)
+    img_internal = g([z])                                   # fresh noise drawn inside NoiseInjection
+    torch.manual_seed(99)
+    replay = [torch.empty(b, 1, n.shape[2], n.shape[3]).normal_() for n in g.make_noise()]
+    # make_noise() itself consumed the stream; redo the replay with shapes only
+    shapes = [(n.shape[2], n.shape[3]) for n in replay]
+    torch.manual_seed(99)
+    replay = [torch.empty(b, 1, h, w).normal_() for (h, w) in shapes]
+    img_replay = g([z], noise=replay)
+    assert torch.equal(img_internal, img_replay), 'replayed draw order differs from the reference internal order'
+    out['z'], out['img'] = npy(z), npy(img_internal)
+    for i, n in enumerate(replay):
+        out[f'noise{i}'] = npy(n)
+    out['seed_weights'] = np.array(41)
+    np.savez_compressed(os.path.join(HERE, 'rng_order.npz'), **out)
+
+
+# ------------------------------------------------------------------ BASELINE config 3: saliency at full size
+def gen_config3(max_batches=None):
+    """BASELINE.json configs[2]: content-aware saliency of the FULL 256px generator over 64 latents (8 batches of
+    8).  The loop is Get_Content_Aware_Pruning_Score (Util/content_aware_pruning.py:217-247) with
+    the reference's own Get_Salt_Pepper_Noisy_Image (:152-171) and Get_Weight_Gradient (:174-196), unmodified;
+    the BiSeNet mask is replaced by the synthetic ellipse (no face in a random-init generator's output) and the
+    per-layer noise is passed explicitly so that both sides see the same numbers.  fp64 on CPU: ~15 min here."""
+    import time
+    import synth
+    from Util.content_aware_pruning import Get_Salt_Pepper_Noisy_Image, Get_Weight_Gradient
+    c = CONFIG3
+    g = synth.load_synth(ref_model.Generator(c['size'], 512, 8).double(), c['seed_weights'])
+    shapes = [(n.shape[2], n.shape[3]) for n in g.make_noise()]
+    mask = synth.ellipse_mask(c['size'])
+    n_batch = c['n_sample'] // c['batch_size']
+    sizes = [c['batch_size']] * (n_batch - 1) + [c['batch_size'] + c['n_sample'] % c['batch_size']]
+    out = {'n_batches': np.array(len(sizes)), 'batch_sizes': np.array(sizes)}
+    csum = 0.0
+    for k, v in g.state_dict().items():
+        csum += float(v.abs().sum())
+    out['weights_abs_sum'] = np.array(csum)
+    for idx, b in enumerate(sizes[:max_batches]):
+        t0 = time.time()
+        z, noise, rs = synth.latents_and_noise(c['seed_batches'] + idx, b, 512, shapes)
+        np.random.set_state(rs.get_state())          # the salt & pepper draws continue the batch's stream
+        img = g(noise_z=[torch.from_numpy(z[0])], noise=[torch.from_numpy(n) for n in noise])
+        noisy = torch.cat([Get_Salt_Pepper_Noisy_Image(img[i:i + 1], mask, c['noise_prob']) for i in range(b)])
+        scores = Get_Weight_Gradient(noisy, img, g)
+        g.zero_grad()
+        for li, s in enumerate(scores):
+            out[f'b{idx}.score{li}'] = s
+        out[f'b{idx}.img_abs_sum'] = np.array(float(img.detach().abs().sum()))
+        print(f'config3 batch {idx}: {time.time() - t0:.1f} s', flush=True)
+        np.savez_compressed(os.path.join(HERE, 'config3_saliency.npz'), **out)
+
+
 if __name__ == '__main__':
-    gen_upfirdn2d()
-    gen_fused_act()
-    gen_layers()
-    gen_generator()
+    which = sys.argv[1:] or ['upfirdn2d', 'fused_act', 'layers', 'generator']
+    sys.path.insert(0, HERE)
+    from torch.nn import functional as F  # noqa: E402
+    table = {'upfirdn2d': gen_upfirdn2d, 'fused_act': gen_fused_act, 'layers': gen_layers, 'generator': gen_generator,
+             'kd_tiny': gen_kd_tiny, 'rng_order': gen_rng_order, 'config3': gen_config3}
+    for w in which:
+        table[w]()
     for f in sorted(os.listdir(HERE)):
         if f.endswith('.npz'):
             print(f, os.path.getsize(os.path.join(HERE, f)))

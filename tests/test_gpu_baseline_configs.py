@@ -1,0 +1,289 @@
+"""GPU parity at BASELINE.json's OWN configurations, against the fp64 CPU oracle and against fixtures generated
+from the unmodified reference (tests/golden/make_golden.py), not against another engine of this library:
+
+  * configs[1] 256px KD step: the 70%-pruned student (154/77/39, B=2) and the full teacher (512/256/128, B=1),
+    forward + KD-slice gradients, on BOTH convolution engines (exact-fp32 SIMT <= 1e-4, tcgen05 TF32 <= 1e-2);
+  * configs[2] saliency of the full 256px generator over 64 latents (8 x 8): per-batch scores and the 70% prune
+    mask against scores the reference itself produced in fp64 (tests/golden/config3_saliency.npz) -- bit-exact mask;
+  * the discriminator and the KD-like step (both kd_modes) against reference-generated fixtures (kd_tiny.npz);
+  * RNG consumption order of randomize_noise=True (rng_order.npz).
+
+Weights and inputs are re-drawn from seeds (tests/golden/synth.py); the oracle runs live on the host CPU (seconds).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import synth
+
+pytestmark = pytest.mark.gpu
+
+STUDENT_256 = [154] * 10 + [77, 77, 39, 39]
+
+
+def relmax(a, b):
+    a = a.detach().double().cpu() if torch.is_tensor(a) else torch.as_tensor(np.asarray(a)).double()
+    b = b.detach().double().cpu() if torch.is_tensor(b) else torch.as_tensor(np.asarray(b)).double()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def rel_l2(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def _synth_generator(model, size, style_dim, n_mlp, shape, seed):
+    gen = model.Generator(size, style_dim, n_mlp, generator_net_shape=shape)
+    synth.load_synth(gen, seed)
+    sd64 = {k: v.double() for k, v in gen.state_dict().items()}
+    return gen.cuda(), sd64
+
+
+def _inputs(seed, b, gen, n_latents=2):
+    shapes = [(n.shape[2], n.shape[3]) for n in gen.make_noise()]
+    z, noise, _ = synth.latents_and_noise(seed, b, 512, shapes, n_latents=n_latents)
+    return [torch.from_numpy(a) for a in z], [torch.from_numpy(a) for a in noise]
+
+
+@pytest.mark.parametrize('who', ['student', 'teacher'])
+def test_256px_generators_vs_fp64_oracle(who):
+    """configs[1]'s two generators at full size against oracle.generator_forward (fp64): every image of the rgb
+    list on both engines; for the student also the KD-slice gradient of EVERY parameter (the quantity the KD step
+    all-reduces), exact-fp32 engine in max-norm, TF32 engine in L2 (13 leaky-ReLU layers: a sign flip of a
+    near-zero pre-activation moves single elements by O(1) while the tensor stays close)."""
+    import model
+    from b200gan import config
+    from oracle import stylegan2_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    student = who == 'student'
+    gen, sd64 = _synth_generator(model, 256, 512, 8, STUDENT_256 if student else None, 51 if student else 52)
+    b = 2 if student else 1
+    z, noise = _inputs(53, b, gen)
+    q = {k: (v.clone().requires_grad_(True) if (student and v.dtype.is_floating_point and 'kernel' not in k
+                                                 and 'noises' not in k) else v) for k, v in sd64.items()}
+    with torch.set_grad_enabled(student):
+        ref = O.generator_forward(q, 256, z, noise, inject_index=5, return_rgb_list=True)
+    cot = torch.from_numpy(np.random.RandomState(54).standard_normal(tuple(ref[-1].shape)))
+    if student:
+        # KD-slice loss: masked L1 against a fixed "teacher image" (the cotangent pattern of train.py:163-164)
+        target = cot
+        names = [k for k, v in q.items() if v.requires_grad]
+        gref = dict(zip(names, torch.autograd.grad(3.0 * (target - ref[-1]).abs().mean(), [q[k] for k in names])))
+    zc, nc = [t.float().cuda() for t in z], [t.float().cuda() for t in noise]
+    for algo, tol_img, tol_grad, norm in ((config.ALGO_SIMT_FP32, 1e-4, 1e-3, 'max'),
+                                          (config.ALGO_TCGEN05_TF32, 1e-2, 3e-2, 'l2')):
+        gen.zero_grad()
+        with config.use_algo(algo), torch.set_grad_enabled(student):
+            out = gen(zc, inject_index=5, noise=nc, return_rgb_list=True)
+            if student:
+                (3.0 * (target.float().cuda() - out[-1]).abs().mean()).backward()
+        assert len(out) == len(ref) == 7
+        for i, (o, r) in enumerate(zip(out, ref)):
+            e = relmax(o, r)
+            assert e <= tol_img, f'{who} algo {algo} rgb {i}: {e:.3e} > {tol_img:.0e}'
+        if student:
+            scal = max(float(g.abs().max()) for g in gref.values() if g.numel() == 1)
+            worst = 0.0
+            for n, p in gen.named_parameters():
+                r = gref[n]
+                if r.numel() == 1:           # scalar gradients (noise weights): heavy cancellation, measured against their kind
+                    e = abs(float(p.grad) - float(r)) / scal
+                else:
+                    e = relmax(p.grad, r) if norm == 'max' else rel_l2(p.grad, r)
+                worst = max(worst, e)
+                assert e <= tol_grad, f'student algo {algo} grad {n}: {e:.3e} > {tol_grad:.0e} ({norm})'
+            print(f'student 256px algo {algo}: worst gradient error {worst:.2e} ({norm})')
+
+
+def test_config3_saliency_prune_mask_vs_reference_golden(golden_dir):
+    """BASELINE configs[2]: full 256px generator, 64 latents in 8 batches of 8, 5 % salt & pepper inside the
+    content mask.  The golden per-batch scores come from the unmodified reference run in fp64
+    (make_golden.gen_config3).  Gate: the 70 % prune mask (the integer product of the pass) is bit-exact in every
+    layer; per-batch scores agree to fp32 accuracy; full-argsort agreement is reported as a statistic
+    (SURVEY.md finding 7)."""
+    import model
+    from b200gan import saliency as S
+    from oracle import stylegan2_oracle as O
+    c = synth.CONFIG3
+    g = np.load(os.path.join(golden_dir, 'config3_saliency.npz'))
+    gen = model.Generator(c['size'], 512, 8)
+    synth.load_synth(gen, c['seed_weights'])
+    csum = sum(float(v.double().abs().sum()) for v in gen.state_dict().values())
+    assert abs(csum - float(g['weights_abs_sum'])) <= 1e-9 * csum, 'synthetic weights differ from the golden run'
+    gen = gen.cuda()
+    n_b = int(g['n_batches'])
+    assert S.batch_sizes(c['n_sample'], c['batch_size']) == [int(v) for v in g['batch_sizes']]
+    per_batch = S.content_aware_scores(gen, c['n_sample'], c['batch_size'], c['noise_prob'], 'cuda',
+                                       mask_fn=lambda img: synth.ellipse_mask(img.shape[-1]), seed=c['seed_batches'])
+    assert len(per_batch) == n_b
+    n_layers = len(per_batch[0])
+    assert n_layers == 14
+    worst = 0.0
+    for bi in range(n_b):
+        for li in range(n_layers):
+            ref = g[f'b{bi}.score{li}']
+            e = float(np.abs(per_batch[bi][li] - ref).max() / np.abs(ref).max())
+            worst = max(worst, e)
+            assert e <= 2e-4, f'batch {bi} layer {li}: score error {e:.2e}'
+    tot = S.total_scores(per_batch)
+    ref_tot = S.total_scores([[g[f'b{bi}.score{li}'] for li in range(n_layers)] for bi in range(n_b)])
+    ours, refm = S.prune_masks(tot, 0.7), O.prune_mask_from_scores(ref_tot, 0.7)
+    agree = []
+    for li, (a, r) in enumerate(zip(ours, refm)):
+        assert np.array_equal(a, r), f'layer {li}: prune mask differs in {int((a != r).sum())} channels'
+        agree.append(float((np.argsort(tot[li]) == np.argsort(ref_tot[li])).mean()))
+    print(f'config 3: worst per-batch score error {worst:.2e}; full-argsort agreement per layer '
+          f'{[round(a, 3) for a in agree]}')
+
+
+def _kd_tiny(golden_dir):
+    import model
+    c = synth.KD_TINY
+    g = np.load(os.path.join(golden_dir, 'kd_tiny.npz'))
+    disc = synth.load_synth(model.Discriminator(c['size']), c['seed_disc'])
+    student = synth.load_synth(model.Generator(c['size'], c['style_dim'], c['n_mlp'], generator_net_shape=c['student']),
+                               c['seed_student'])
+    teacher = synth.load_synth(model.Generator(c['size'], c['style_dim'], c['n_mlp'], generator_net_shape=c['teacher']),
+                               c['seed_teacher'])
+    shapes = [(n.shape[2], n.shape[3]) for n in student.make_noise()]
+    z, noise2, _ = synth.latents_and_noise(c['seed_inputs'], c['batch'], c['style_dim'], shapes + shapes, n_latents=2)
+    f = lambda arrs: [torch.from_numpy(a).float().cuda() for a in arrs]
+    return c, g, disc.cuda(), student.cuda(), teacher.cuda(), f(z), f(noise2[:len(shapes)]), f(noise2[len(shapes):])
+
+
+def test_discriminator_vs_reference_golden(golden_dir):
+    """model.Discriminator (reference model.py:740-798) forward and input gradient against the reference's own
+    fp64 output; full-fp32 library math for this check."""
+    c, g, disc, *_ = _kd_tiny(golden_dir)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    from b200gan import config
+    with config.exact_fp32():
+        x = torch.from_numpy(g['d_x']).float().cuda().requires_grad_(True)
+        pred = disc(x)
+        gx, = torch.autograd.grad(pred, x, torch.from_numpy(g['d_cot']).float().cuda())
+        assert relmax(pred, g['d_pred']) <= 1e-4
+        assert relmax(gx, g['d_gx']) <= 1e-4
+        with torch.no_grad():
+            assert relmax(disc(x[:2].detach()), g['d_pred_b2']) <= 1e-4
+        # channels-last input (the layout the KD step feeds) gives the same numbers
+        xl = x.detach().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+        pl = disc(xl)
+        gl, = torch.autograd.grad(pl, xl, torch.from_numpy(g['d_cot']).float().cuda())
+        assert relmax(pl, g['d_pred']) <= 1e-4 and relmax(gl, g['d_gx']) <= 1e-4
+
+
+@pytest.mark.parametrize('mode', ['Output_Only', 'Intermediate'])
+def test_kd_step_vs_reference_golden(golden_dir, mode):
+    """KDStep (train.py:280-308 / :145-169) loss and every student gradient against the fixture composed from
+    the reference's own modules."""
+    from b200gan import config
+    from b200gan.kd import KDStep
+    c, g, disc, student, teacher, z, s_noise, t_noise = _kd_tiny(golden_dir)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    mask = torch.from_numpy(synth.ellipse_mask(c['size']).astype(np.float32)).view(1, 1, c['size'], c['size']).cuda()
+    kd = KDStep(student, teacher, disc, mask=mask, kd_mode=mode)
+    with config.exact_fp32():
+        loss = kd.step(z, c['inject'], s_noise, t_noise)
+    ref_loss = float(g[f'{mode}.g_loss']) + float(g[f'{mode}.kd'])
+    assert abs(float(loss) - ref_loss) <= 1e-4 * abs(ref_loss), (float(loss), ref_loss)
+    for n, p in student.named_parameters():
+        ref = g[f'{mode}.grad.{n}']
+        if np.abs(ref).max() == 0:
+            assert float(p.grad.abs().max()) == 0.0, n
+            continue
+        e = relmax(p.grad, ref)
+        assert e <= 1e-3, f'{mode} grad {n}: {e:.3e}'
+
+
+def test_rng_consumption_order(golden_dir):
+    """randomize_noise=True (model.py:299-301): (1) the golden image, produced by the REFERENCE's internal draws,
+    is reproduced when the replayed draw list (one normal_() per layer, execution order, output resolution) is fed
+    explicitly; (2) on the GPU, our internal draws are bit-identical to the same replay under the same seed --
+    so a checkpoint + seed yields the same noise maps as the reference module would draw on this device."""
+    import model
+    from b200gan import config
+    t = synth.TINY
+    g = np.load(os.path.join(golden_dir, 'rng_order.npz'))
+    gen = synth.load_synth(model.Generator(t['size'], t['style_dim'], t['n_mlp'], generator_net_shape=t['net_shape']),
+                           int(g['seed_weights'])).cuda()
+    z = torch.from_numpy(g['z']).float().cuda()
+    with config.exact_fp32(), torch.no_grad():
+        img = gen([z], noise=[torch.from_numpy(g[f'noise{i}']).float().cuda() for i in range(7)])
+        assert relmax(img, g['img']) <= 1e-4
+        b = z.shape[0]
+        shapes = [(n.shape[2], n.shape[3]) for n in gen.make_noise()]
+        torch.manual_seed(1234)
+        internal = gen([z])                                  # fresh noise drawn inside the fused StyledConv
+        torch.manual_seed(1234)
+        replay = [torch.empty(b, 1, h, w, device='cuda').normal_() for (h, w) in shapes]
+        explicit = gen([z], noise=replay)
+        assert torch.equal(internal, explicit), 'internal noise draws are not one normal_() per layer in call order'
+        # and the rgb-list / style-mixing entry point consumes the stream identically
+        torch.manual_seed(1234)
+        z2 = torch.randn_like(z)
+        torch.manual_seed(77)
+        a = gen([z, z2], inject_index=3, return_rgb_list=True)[-1]
+        torch.manual_seed(77)
+        replay = [torch.empty(b, 1, h, w, device='cuda').normal_() for (h, w) in shapes]
+        assert torch.equal(a, gen([z, z2], inject_index=3, noise=replay))
+
+
+def test_frozen_student_sees_adam_updates():
+    """the fused Adam kernel updates parameters through raw pointers; a student that is then frozen
+    (train.py:247, requires_grad(generator, False)) must not be served stale cached operands."""
+    import model
+    from b200gan import config
+    from b200gan.kd import KDStep
+    c = synth.KD_TINY
+    disc = synth.load_synth(model.Discriminator(c['size']), 1).cuda()
+    student = synth.load_synth(model.Generator(c['size'], c['style_dim'], c['n_mlp'], generator_net_shape=c['student']), 2).cuda()
+    teacher = synth.load_synth(model.Generator(c['size'], c['style_dim'], c['n_mlp'], generator_net_shape=c['teacher']), 3).cuda()
+    kd = KDStep(student, teacher, disc, lr=0.05)
+    z = [torch.randn(2, c['style_dim'], device='cuda'), torch.randn(2, c['style_dim'], device='cuda')]
+    noise = [torch.randn(2, 1, n.shape[2], n.shape[3], device='cuda') for n in student.make_noise()]
+    with config.exact_fp32():
+        for p in student.parameters():
+            p.requires_grad_(False)
+        with torch.no_grad():
+            before = student(z, inject_index=2, noise=noise).clone()      # fills the frozen-operand cache
+        for p in student.parameters():
+            p.requires_grad_(True)
+        kd.step(z, 2)
+        for p in student.parameters():
+            p.requires_grad_(False)
+        with torch.no_grad():
+            after = student(z, inject_index=2, noise=noise)
+            for p in student.parameters():
+                p.requires_grad_(True)
+            fresh = student(z, inject_index=2, noise=noise)               # trainable parameters are never cached
+    assert not torch.equal(before, after), 'frozen student still served the pre-update operands'
+    assert torch.equal(after, fresh)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
+def test_dataparallel_two_devices():
+    """nn.DataParallel over two devices (train.py:522-525, get_fid.py:27): per-device shared-memory opt-in,
+    engine selection visible to the replica threads; forward + backward equal the single-device result."""
+    import model
+    from b200gan import config
+    gen = synth.load_synth(model.Generator(64, 64, 2, generator_net_shape=[64, 64, 64, 64, 48, 48, 40, 40, 39, 39]), 5).cuda()
+    z = torch.randn(4, 64, device='cuda')
+    noise = [torch.randn(4, 1, n.shape[2], n.shape[3], device='cuda') for n in gen.make_noise()]
+    for algo in (config.ALGO_SIMT_FP32, config.ALGO_TCGEN05_TF32):
+        with config.use_algo(algo):
+            gen.zero_grad()
+            ref = gen([z], noise=noise)
+            ref.square().mean().backward()
+            gref = {n: p.grad.clone() for n, p in gen.named_parameters()}
+            gen.zero_grad()
+            dp = torch.nn.DataParallel(gen, device_ids=[0, 1])
+            out = dp([z], noise=noise)
+            out.square().mean().backward()
+        assert relmax(out, ref) <= 1e-5
+        for n, p in gen.named_parameters():
+            assert relmax(p.grad, gref[n]) <= 2e-3, n

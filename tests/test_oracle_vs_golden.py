@@ -176,3 +176,73 @@ def test_path_length_golden(golden_dir):
     img = O.generator_forward(sd, 32, [latent], noise, input_is_latent=True)
     pl = O.path_lengths(img, latent, T(g['pl_noise']))
     close(pl.detach(), g['path_lengths'], 1e-9)
+
+
+# ------------------------------------------------------------------ discriminator, KD-like step, RNG order
+# (weights / inputs are re-drawn from seeds by tests/golden/synth.py, exactly as make_golden.py drew them for
+#  the reference; only the reference's outputs live in the fixtures)
+def _kd_tiny_inputs(g):
+    import model          # the drop-in module tree supplies key order and shapes (no compute: CPU construction only)
+    import synth
+    from synth import KD_TINY as c
+    disc_t = model.Discriminator(c['size']).state_dict()
+    stu_t = model.Generator(c['size'], c['style_dim'], c['n_mlp'], generator_net_shape=c['student']).state_dict()
+    tea_t = model.Generator(c['size'], c['style_dim'], c['n_mlp'], generator_net_shape=c['teacher']).state_dict()
+    assert list(disc_t.keys()) == list(g['d_keys'])
+    assert list(stu_t.keys()) == list(g['student_keys'])
+
+    def sd(template, seed):
+        out = {k: v.double() for k, v in template.items()}
+        out.update({k: T(v) for k, v in synth.synth_state(template, seed).items()})
+        return out
+    dp, sp, tp = sd(disc_t, c['seed_disc']), sd(stu_t, c['seed_student']), sd(tea_t, c['seed_teacher'])
+    n_layers = sum(1 for k in stu_t if k.startswith('noises.'))
+    res = [stu_t[f'noises.noise_{i}'].shape[2:] for i in range(n_layers)]
+    z, noise2, rs = synth.latents_and_noise(c['seed_inputs'], c['batch'], c['style_dim'],
+                                            [tuple(r) for r in res] * 2, n_latents=2)
+    z = [T(a) for a in z]
+    s_noise, t_noise = [T(a) for a in noise2[:n_layers]], [T(a) for a in noise2[n_layers:]]
+    return c, dp, sp, tp, z, s_noise, t_noise, rs
+
+
+def test_discriminator_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'kd_tiny.npz'))
+    c, dp, *_ = _kd_tiny_inputs(g)
+    close(T(g['d_x']).numpy(), g['d_x'])
+    x = T(g['d_x']).requires_grad_(True)
+    pred = O.discriminator_forward(dp, x, c['size'])
+    close(pred.detach(), g['d_pred'])
+    gx, = torch.autograd.grad(pred, x, T(g['d_cot']))
+    close(gx, g['d_gx'], 1e-9)
+    close(O.discriminator_forward(dp, x[:2].detach(), c['size']), g['d_pred_b2'])
+
+
+@pytest.mark.parametrize('mode', ['Output_Only', 'Intermediate'])
+def test_kd_step_golden(golden_dir, mode):
+    import synth
+    g = np.load(os.path.join(golden_dir, 'kd_tiny.npz'))
+    c, dp, sp, tp, z, s_noise, t_noise, _ = _kd_tiny_inputs(g)
+    mask = T(synth.ellipse_mask(c['size']).astype(np.float64)).view(1, 1, c['size'], c['size'])
+    loss, grads = O.kd_step(sp, tp, dp, c['size'], z, s_noise, t_noise, c['inject'], mask, kd_mode=mode)
+    close(loss, g[f'{mode}.g_loss'] + g[f'{mode}.kd'])
+    for n in g['param_names']:
+        ref = g[f'{mode}.grad.{n}']
+        got = grads[n].numpy() if n in grads else np.zeros_like(ref)
+        if np.abs(ref).max() == 0:
+            assert np.abs(got).max() == 0, n
+        else:
+            close(got, ref, 1e-9)
+
+
+def test_rng_order_golden(golden_dir):
+    """The noise list stored next to the image is the replay of one normal_() per layer in execution order
+    (make_golden.gen_rng_order asserts the replay is bit-identical to the reference's internal draws)."""
+    import model
+    import synth
+    from synth import TINY
+    g = np.load(os.path.join(golden_dir, 'rng_order.npz'))
+    tmpl = model.Generator(TINY['size'], TINY['style_dim'], TINY['n_mlp'], generator_net_shape=TINY['net_shape']).state_dict()
+    sd = {k: v.double() for k, v in tmpl.items()}
+    sd.update({k: T(v) for k, v in synth.synth_state(tmpl, int(g['seed_weights'])).items()})
+    noise = [T(g[f'noise{i}']) for i in range(7)]
+    close(O.generator_forward(sd, TINY['size'], [T(g['z'])], noise), g['img'])
