@@ -37,6 +37,8 @@ INCLUDE = ['model.py', 'train.py', 'train_hyperparams.py', 'prune.py', 'get_fid.
            'Evaluation/calc_inception.py', 'Miscellaneous/distributed.py', 'LICENSE', 'LICENSE-NVIDIA', 'LICENSE-LPIPS',
            'LICENSE-FID']
 SKIP_DIRS = {'__pycache__', 'modules'}          # Util/face_parsing/modules = unused in-place ABN
+# 53 MB of parser weights: only needed to run prune.py / train.py with the real face parser (the tests use the
+# synthetic mask); left out by default because every gpurun call pushes the tree (--with-bisenet-weights adds them)
 BISENET = 'Util/face_parsing/pretrained_model/79999_iter.pth'
 
 
@@ -56,7 +58,7 @@ def env_for_ref():
     return env
 
 
-def stage(with_bisenet_weights=True, prebuild=True, verbose=True):
+def stage(with_bisenet_weights=False, prebuild=True, verbose=True):
     if not os.path.isdir(REF_SRC):
         if os.path.isdir(DST):
             return DST                     # GPU box: use what travelled with the tree
@@ -100,4 +102,4 @@ def stage(with_bisenet_weights=True, prebuild=True, verbose=True):
 
 
 if __name__ == '__main__':
-    stage(with_bisenet_weights='--no-bisenet-weights' not in sys.argv, prebuild='--no-build' not in sys.argv)
+    stage(with_bisenet_weights='--with-bisenet-weights' in sys.argv, prebuild='--no-build' not in sys.argv)

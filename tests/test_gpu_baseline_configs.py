@@ -21,6 +21,8 @@ import synth
 pytestmark = pytest.mark.gpu
 
 STUDENT_256 = [154] * 10 + [77, 77, 39, 39]
+# input gradient of the discriminator on the exact-fp32 engine (the fp32 CPU oracle reaches 7e-7 on this fixture)
+D_GRAD_TOL = 1e-4
 
 
 def relmax(a, b):
@@ -166,14 +168,14 @@ def test_discriminator_vs_reference_golden(golden_dir):
         pred = disc(x)
         gx, = torch.autograd.grad(pred, x, torch.from_numpy(g['d_cot']).float().cuda())
         assert relmax(pred, g['d_pred']) <= 1e-4
-        assert relmax(gx, g['d_gx']) <= 1e-4
+        assert relmax(gx, g['d_gx']) <= D_GRAD_TOL, relmax(gx, g['d_gx'])
         with torch.no_grad():
             assert relmax(disc(x[:2].detach()), g['d_pred_b2']) <= 1e-4
         # channels-last input (the layout the KD step feeds) gives the same numbers
         xl = x.detach().contiguous(memory_format=torch.channels_last).requires_grad_(True)
         pl = disc(xl)
         gl, = torch.autograd.grad(pl, xl, torch.from_numpy(g['d_cot']).float().cuda())
-        assert relmax(pl, g['d_pred']) <= 1e-4 and relmax(gl, g['d_gx']) <= 1e-4
+        assert relmax(pl, g['d_pred']) <= 1e-4 and relmax(gl, g['d_gx']) <= D_GRAD_TOL, relmax(gl, g['d_gx'])
 
 
 @pytest.mark.parametrize('mode', ['Output_Only', 'Intermediate'])
