@@ -27,9 +27,8 @@ class KDStep:
             p.requires_grad_(False)
         for p in discriminator.parameters():
             p.requires_grad_(False)          # train.py:286-287 (requires_grad(D, False))
-        # the discriminator's library convolutions run NHWC kernels: keep its tensors channels-last so that
-        # no NCHW<->NHWC conversion surrounds them; our upfirdn2d / fused_leaky_relu work on that storage
-        discriminator.to(memory_format=torch.channels_last)
+        # the frozen discriminator runs on the package's own engines (b200gan/dconv.py): NHWC-p activations, weights
+        # re-laid out once into operand slabs (cached: the parameters are frozen), the image read through its strides
         self.bucket = D.FlatBucket(student.parameters())
         self.exp_avg = torch.zeros_like(self.bucket.flat_param)
         self.exp_avg_sq = torch.zeros_like(self.bucket.flat_param)
@@ -63,7 +62,7 @@ class KDStep:
         else:
             with torch.no_grad():
                 real = self.teacher(z, return_rgb_list=True, inject_index=inject_index, noise=t_noise)
-        g_loss = F.softplus(-self.disc(fake[-1].contiguous(memory_format=torch.channels_last))).mean()
+        g_loss = F.softplus(-self.disc(fake[-1])).mean()
         if self.teacher_stream is not None:
             main.wait_stream(self.teacher_stream)
         if self.kd_mode == 'Output_Only':                      # train.py:163-164

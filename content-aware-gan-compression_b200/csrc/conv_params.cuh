@@ -18,6 +18,7 @@ struct ConvP {
     const float* noise;
     const float* noise_w;
     const float* bias;
+    const float* residual;   // optional tensor of the output's layout, added AFTER the activation (ResBlock skip)
     float* out;
     int B, Hin, Win, in_pitch;
     int Ho, Wo, in_stride;
@@ -25,7 +26,8 @@ struct ConvP {
     int out_valid;
     int Hout, Wout, out_stride, out_oy, out_ox;
     int64_t noise_bstride;
-    int act;
+    int act;                 // 0: none, 1: leaky ReLU (slope 0.2) * act_gain
+    float act_gain;          // sqrt2 unless stated (0 is read as sqrt2)
     int ntaps;
     Tap taps[kMaxTaps];
 };

@@ -131,14 +131,20 @@ __global__ void __launch_bounds__(256, 2) conv_simt_kernel(const ConvP p) {
             v[0] += nz; v[1] += nz; v[2] += nz; v[3] += nz;
         }
         v[0] += bias4.x; v[1] += bias4.y; v[2] += bias4.z; v[3] += bias4.w;
+        const int64_t off = (((int64_t)b * p.Hout + yy) * p.Wout + xx) * p.n_cols + n;
         if (p.act) {
+            const float gain = (p.act_gain != 0.f) ? p.act_gain : kSqrt2;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) v[j] = lrelu_sqrt2(v[j]);
+            for (int j = 0; j < 4; ++j) v[j] = lrelu_gain(v[j], gain);
+        }
+        if (p.residual) {
+            const float4 r4 = ldg4(p.residual + off);
+            v[0] += r4.x; v[1] += r4.y; v[2] += r4.z; v[3] += r4.w;
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j)
             if (n + j >= p.out_valid) v[j] = 0.f;
-        st4(p.out + (((int64_t)b * p.Hout + yy) * p.Wout + xx) * p.n_cols + n, make_float4(v[0], v[1], v[2], v[3]));
+        st4(p.out + off, make_float4(v[0], v[1], v[2], v[3]));
     }
 }
 
@@ -269,6 +275,9 @@ __global__ void __launch_bounds__(256) split_reduce_kernel(const float* __restri
 }  // namespace cagc
 
 using namespace cagc;
+
+// the SIMT engine for callers in other translation units (disc.cu)
+int cagc_simt_conv(cudaStream_t stream, const cagc::ConvP& p, const char* what) { return launch_conv(stream, p, what); }
 
 static int check_nhwc(const char* what, int B, int H, int W, int in_pitch, int out_pitch, int ksize) {
     CAGC_REQUIRE(B >= 0 && H >= 0 && W >= 0, "%s: negative size", what);

@@ -38,6 +38,8 @@ struct TcParams {
     const float* noise;
     const float* noise_w;
     const float* bias;
+    const float* residual;
+    float act_gain;
     float* out;
     int B, Ho, Wo;              // iteration domain
     int bw, bh, bb;             // box: bw*bh*bb == 128
@@ -322,7 +324,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 }
                 if (p.act) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) o[j] = lrelu_sqrt2(o[j]);
+                    for (int j = 0; j < 4; ++j) o[j] = lrelu_gain(o[j], p.act_gain);
+                }
+                if (p.residual) {
+                    const float4 r4 = ldg4(p.residual + (dst - p.out) + n);
+                    o[0] += r4.x; o[1] += r4.y; o[2] += r4.z; o[3] += r4.w;
                 }
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
@@ -533,7 +539,11 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                         }
                         if (p.act) {
 #pragma unroll
-                            for (int jj = 0; jj < 4; ++jj) o[jj] = lrelu_sqrt2(o[jj]);
+                            for (int jj = 0; jj < 4; ++jj) o[jj] = lrelu_gain(o[jj], p.act_gain);
+                        }
+                        if (p.residual) {
+                            const float4 r4 = ldg4(p.residual + (dst - p.out) + n);
+                            o[0] += r4.x; o[1] += r4.y; o[2] += r4.z; o[3] += r4.w;
                         }
 #pragma unroll
                         for (int jj = 0; jj < 4; ++jj)
@@ -576,6 +586,8 @@ struct HaloParams {
     const float* noise;
     const float* noise_w;
     const float* bias;
+    const float* residual;
+    float act_gain;
     float* out;
     int B, Ho, Wo;                  // iteration domain (output pixels of this launch)
     int TW, R, Wt, rows_box;        // tile width / rows, raster pitch, box rows (R + dyspan)
@@ -780,7 +792,11 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         }
                         if (p.act) {
 #pragma unroll
-                            for (int jj = 0; jj < 4; ++jj) o[jj] = lrelu_sqrt2(o[jj]);
+                            for (int jj = 0; jj < 4; ++jj) o[jj] = lrelu_gain(o[jj], p.act_gain);
+                        }
+                        if (p.residual) {
+                            const float4 r4 = ldg4(p.residual + (dst - p.out) + n);
+                            o[0] += r4.x; o[1] += r4.y; o[2] += r4.z; o[3] += r4.w;
                         }
 #pragma unroll
                         for (int jj = 0; jj < 4; ++jj)
@@ -1701,6 +1717,7 @@ static int try_halo_conv(cudaStream_t stream, const ConvP& c, const char* what, 
     p.b_stages = (int)std::min<int64_t>(kHaloMaxB, left / p.b_bytes);
     if (p.b_stages < 2) return 0;
     p.out_scale = c.out_scale; p.noise = c.noise; p.noise_w = c.noise_w; p.bias = c.bias; p.out = c.out;
+    p.residual = c.residual; p.act_gain = (c.act_gain != 0.f) ? c.act_gain : kSqrt2;
     p.B = c.B; p.Ho = c.Ho; p.Wo = c.Wo;
     p.dx_min = dxmin; p.dy_min = dymin;
     p.k_valid = c.in_pitch; p.n_pitch = c.n_cols; p.out_valid = c.out_valid;
@@ -1765,6 +1782,7 @@ int cagc_tc_conv(cudaStream_t stream, const ConvP& c, const char* what) {
     }
     TcParams p{};
     p.out_scale = c.out_scale; p.noise = c.noise; p.noise_w = c.noise_w; p.bias = c.bias; p.out = c.out;
+    p.residual = c.residual; p.act_gain = (c.act_gain != 0.f) ? c.act_gain : kSqrt2;
     p.B = c.B; p.Ho = c.Ho; p.Wo = c.Wo;
     p.bw = std::min(16, next_pow2(c.Wo));
     p.bh = std::min(kTileM / p.bw, next_pow2(c.Ho));
@@ -1895,6 +1913,7 @@ int cagc_tc_conv_multi(cudaStream_t stream, const ConvP* ph, int nphase, const c
     if ((int64_t)c.B * Hmax * Wmax == 0 || taps_total > kMaxTaps) return 0;
     TcParams p{};
     p.out_scale = c.out_scale; p.noise = c.noise; p.noise_w = c.noise_w; p.bias = c.bias; p.out = c.out;
+    p.residual = c.residual; p.act_gain = (c.act_gain != 0.f) ? c.act_gain : kSqrt2;
     p.B = c.B; p.Ho = Hmax; p.Wo = Wmax;
     p.bw = std::min(16, next_pow2(Wmax));
     p.bh = std::min(kTileM / p.bw, next_pow2(Hmax));

@@ -20,6 +20,7 @@ from torch.nn import functional as F
 from op import FusedLeakyReLU, fused_leaky_relu, upfirdn2d
 from b200gan import config as _cfg
 from b200gan import modconv as _mc
+from b200gan import dconv as _dc
 
 
 import os as _os
@@ -489,8 +490,10 @@ class Generator(nn.Module):
 
 
 # --------------------------------------------------------------------------------------------
-# Discriminator (reference model.py:670-798).  Its convolutions are ordinary library convs; it
-# sits on the KD step through our upfirdn2d (Blur) and fused bias+leaky-ReLU kernels.
+# Discriminator (reference model.py:670-798).  Frozen (the KD generator step): every block runs on the
+# package's own convolution engines with fused epilogues (b200gan/dconv.py).  Trainable (D steps, R1
+# double backward -- outside the benchmarked path): differentiable composition of library convolutions
+# with our upfirdn2d (Blur) and fused bias+leaky-ReLU kernels.
 # --------------------------------------------------------------------------------------------
 class ConvLayer(nn.Sequential):
     def __init__(self, in_channel, out_channel, kernel_size, downsample=False, blur_kernel=[1, 3, 3, 1], bias=True,
@@ -516,6 +519,10 @@ class ResBlock(nn.Module):
         self.skip = ConvLayer(in_channel, out_channel, 1, downsample=True, activate=False, bias=False)
 
     def forward(self, input):
+        if input.is_cuda and not _cfg.is_second_order() and _dc.res_block_eligible(self):
+            # frozen discriminator (the generator step, train.py:286-287): the whole block is one autograd node on the
+            # package's convolution engines, bias / activation / residual merge in the epilogues (b200gan/dconv.py)
+            return _dc.res_block(input, self)
         out = self.conv1(input)
         c2, sk = self.conv2, self.skip
         if isinstance(c2[-1], FusedLeakyReLU) and len(c2) == 3 and len(sk) == 2 and sk[1].bias is None:
@@ -553,8 +560,25 @@ class Discriminator(nn.Module):
             EqualLinear(channels[4], 1),
         )
 
+    def _own_engines(self, input):
+        """True when this forward can run on the package's convolution engines: CUDA input, first-order autograd,
+        every parameter frozen (train.py:286-287) and the standard layer layout."""
+        if not input.is_cuda or _cfg.is_second_order() or input.shape[1] > 4:
+            return False
+        first, last = self.convs[0], self.final_conv
+        if not (len(first) == 2 and isinstance(first[0], EqualConv2d) and isinstance(first[1], FusedLeakyReLU)
+                and first[0].weight.shape[-1] == 1 and len(last) == 2 and isinstance(last[1], FusedLeakyReLU)):
+            return False
+        return all(not p.requires_grad for p in self.parameters())
+
     def forward(self, input):
-        out = self.convs(input)
+        own = self._own_engines(input)
+        if own:
+            out = _dc.from_rgb(input, self.convs[0][0], self.convs[0][1])
+            for blk in list(self.convs)[1:]:
+                out = blk(out)
+        else:
+            out = self.convs(input)
         batch, channel, height, width = out.shape
         group = min(batch, self.stddev_group)
         # minibatch standard deviation feature (reference model.py:783-791)
@@ -563,6 +587,12 @@ class Discriminator(nn.Module):
         sd = sd.mean([2, 3, 4], keepdim=True).squeeze(2)
         sd = sd.repeat(group, 1, height, width)
         out = torch.cat([out, sd], 1)
+        if own:
+            out = _dc.conv_act(out, self.final_conv[0], self.final_conv[1])
+            out = out.reshape(batch, -1)
+            for lin in self.final_linear:
+                out = _mc.equal_linear(out, lin.weight, lin.bias, lin.scale, lin.lr_mul, bool(lin.activation))
+            return out
         out = self.final_conv(out)
         out = out.reshape(batch, -1)
         return self.final_linear(out)

@@ -37,7 +37,7 @@ typedef void* cagc_stream_t; /* cudaStream_t */
 #define CAGC_E_UNSUPPORTED (-2) /* shape outside what the kernels implement */
 
 /* bump when a signature changes; the Python loader checks it */
-#define CAGC_ABI_VERSION 14
+#define CAGC_ABI_VERSION 15
 
 int cagc_abi_version(void);
 const char* cagc_last_error(void);
@@ -275,6 +275,38 @@ int cagc_to_nhwc(cagc_stream_t stream, const float* src, int64_t sb, int64_t sc,
 int cagc_adam_step(cagc_stream_t stream, float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
                    int64_t n, float lr, float beta1, float beta2, float eps, float grad_scale,
                    float bias_corr1, float bias_corr2, const float* step_dev);
+
+/* ----------------------------------------------------------------------
+ * Discriminator path (reference model.py:670-798: ConvLayer / ResBlock / EqualConv2d).  The reference runs
+ * F.conv2d (cuDNN) + upfirdn2d + fused_bias_act launches; here the convolutions run on the same engines as the
+ * generator (shared weights, no modulation) with bias / leaky ReLU / residual add in the epilogue.
+ *
+ * cagc_conv2d: out = act(conv(in, W) + bias) [+ residual] on NHWC-p.
+ *   mode 0: stride 1, zero padding ksize/2 (replaces F.conv2d at model.py:117-124 for ConvLayer without
+ *           downsample; with flipped / transposed slabs it is also its data gradient)
+ *   mode 1: stride 2, no padding, H = 2*Ho + ksize - 2 (the EqualConv2d after Blur, model.py:683-700); its data
+ *           gradient is cagc_conv_up (transposed convolution)
+ *   act != 0: leaky ReLU(0.2) * act_gain (FusedLeakyReLU, op/fused_act.py:104-119; act_gain 0 means sqrt2)
+ *   residual (optional, layout of out, must not alias it) is added after the activation (ResBlock, model.py:731-737)
+ *   w_slabs: as written by cagc_weight_prep for the engine `algo` (0 SIMT fp32, 1 tcgen05 TF32)
+ * cagc_fir_resample_nhwc: upfirdn2d (op/upfirdn2d.py:145-156) with a 4x4 kernel and (up, down) = (1, 2) or (2, 1) on
+ *   NHWC-p: Blur evaluated only where the following stride-2 1x1 convolution reads it (ResBlock skip branch,
+ *   model.py:723-728) and its adjoint.  taps_host: the 16 kernel taps (host memory, row major, unflipped).
+ * cagc_from_rgb_fwd / _bwd: ConvLayer(3, C, 1) (model.py:756): y = lrelu(W*scale*img + b) * gain straight to NHWC-p
+ *   (img through element strides sb, sc, sh, sw); backward: NCHW-contiguous image gradient from (g, y).
+ * cagc_act_mask_nhwc: out = g * gain * (y > 0 ? 1 : 0.2)  (fused_bias_act_kernel.cu:43, act=3 grad=1, no bias)
+ * ---------------------------------------------------------------------- */
+int cagc_conv2d(cagc_stream_t stream, const float* in, const float* w_slabs, const float* bias, const float* residual,
+                float* out, int B, int Hin, int Win, int in_pitch, int out_pitch, int out_valid, int ksize, int mode,
+                int act, float act_gain, int algo);
+int cagc_fir_resample_nhwc(cagc_stream_t stream, const float* in, const float* taps_host, float* out, int B, int in_h,
+                           int in_w, int pitch, int up, int down, int pad0, int pad1);
+int cagc_from_rgb_fwd(cagc_stream_t stream, const float* img, int64_t sb, int64_t sc, int64_t sh, int64_t sw,
+                      const float* w, const float* bias, float* out, int B, int H, int W, int cin, int cout, int pitch,
+                      float wscale, int act, float gain);
+int cagc_from_rgb_bwd(cagc_stream_t stream, const float* g, const float* yact, const float* w, float* gimg, int B,
+                      int H, int W, int cin, int cout, int pitch, float wscale, int act, float gain);
+int cagc_act_mask_nhwc(cagc_stream_t stream, const float* g, const float* y, float* out, int64_t n, float gain);
 
 #ifdef __cplusplus
 }
