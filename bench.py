@@ -364,7 +364,7 @@ def bench_kd(args, cx):
                          'avg_launch_us': per * 1e3,
                          'tflops': (r['flops'] / (r['ms'] / 1e3) / 1e12) if r['flops'] and r['ms'] else None,
                          'gbs': (r['bytes'] / (r['ms'] / 1e3) / 1e9) if r['bytes'] and r['ms'] else None}
-    conv_names = [n for n in summ if n.startswith('conv_')]
+    conv_names = [n for n in summ if n.startswith('conv_') or n.startswith('dconv')]
     dom = max(conv_names, key=lambda n: summ[n]['ms']) if conv_names else None
     roofline = None
     if dom:
@@ -405,7 +405,7 @@ def bench_kd(args, cx):
         hbm['fir_nhwc[largest]'] = {'bound': 'hbm', 'layer': k.split('@')[1], 'achieved': fl[k]['gbs'],
                                     'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': fl[k]['gbs'] / peaks['hbm_gbs'],
                                     'avg_launch_us': fl[k]['avg_launch_us']}
-    cl = {k: v for k, v in layers.items() if k.startswith('conv_') and v['tflops']}
+    cl = {k: v for k, v in layers.items() if (k.startswith('conv_') or k.startswith('dconv')) and v['tflops']}
     top_layers = {k: cl[k] for k in sorted(cl, key=lambda k: -cl[k]['avg_launch_us'] * cl[k]['launches_per_step'])[:6]}
 
     cpu, ref_gpu = None, None
@@ -452,6 +452,8 @@ def bench_kd(args, cx):
         'kernels': kernels,
         'top_conv_layers': top_layers,
     }
+    if args.all_layers:
+        line['all_layers'] = layers
     print(json.dumps(line))
 
 
@@ -580,6 +582,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-ref-gpu', action='store_true')
     ap.add_argument('--no-second-mode', action='store_true')
+    ap.add_argument('--all-layers', action='store_true', help='add every per-layer kernel record to the JSON line')
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel from Python instead of one CUDA graph per step')
     args = ap.parse_args()
     if args.size is None:

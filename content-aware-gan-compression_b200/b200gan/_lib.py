@@ -62,6 +62,7 @@ SIGNATURES = {
     'cagc_torgb_bwd': (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f]),
     'cagc_to_nhwc': (_i, [_p, _p, _l, _l, _l, _l, _p, _i, _i, _i, _i, _i]),
     'cagc_adam_step': (_i, [_p, _p, _p, _p, _p, _l, _f, _f, _f, _f, _f, _f, _f, _p]),
+    'cagc_adam_ema_step': (_i, [_p, _p, _p, _p, _p, _l, _f, _f, _f, _f, _f, _f, _f, _p, _p, _f]),
     'cagc_conv2d': (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i]),
     'cagc_fir_resample_nhwc': (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i]),
     'cagc_from_rgb_fwd': (_i, [_p, _p, _l, _l, _l, _l, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _i, _f]),

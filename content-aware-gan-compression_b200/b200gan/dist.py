@@ -84,8 +84,10 @@ class FlatBucket:
     parameters = 22.3 MB: a single NVLink all-reduce instead of ~90 small ones.
     """
 
-    def __init__(self, params: Iterable[torch.nn.Parameter]):
-        self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
+    def __init__(self, params: Iterable[torch.nn.Parameter], with_grads: bool = True, all_params: bool = False):
+        """with_grads=False: parameter bucket only (the EMA copy of the generator, train.py:124-129).
+        all_params=True: take every parameter, trainable or not (an EMA model is usually frozen)."""
+        self.params: List[torch.nn.Parameter] = [p for p in params if (all_params or p.requires_grad)]
         assert self.params, 'no trainable parameters'
         dev, dt = self.params[0].device, self.params[0].dtype
         # 4-float alignment of every segment keeps 128-bit accesses legal for any consumer of a view
@@ -96,12 +98,13 @@ class FlatBucket:
             n += (p.numel() + 3) // 4 * 4
         self.numel = n
         self.flat_param = torch.zeros(n, device=dev, dtype=dt)
-        self.flat_grad = torch.zeros(n, device=dev, dtype=dt)
+        self.flat_grad = torch.zeros(n, device=dev, dtype=dt) if with_grads else None
         for p, off in zip(self.params, self.offsets):
             seg = self.flat_param[off:off + p.numel()].view_as(p)
             seg.copy_(p.data)
             p.data = seg
-            p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
+            if with_grads:
+                p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
 
     def zero_grad(self):
         self.flat_grad.zero_()

@@ -21,7 +21,7 @@ from ._lib import lib, check
 class KDStep:
     def __init__(self, student, teacher, discriminator, lr: float = 0.002 * 0.8, betas=(0.0, 0.99 ** 0.8),
                  eps: float = 1e-8, kd_l1_lambda: float = 3.0, mask: Optional[torch.Tensor] = None,
-                 kd_mode: str = 'Output_Only'):
+                 kd_mode: str = 'Output_Only', g_ema=None, ema_decay: float = 0.5 ** (32 / (10 * 1000))):
         self.student, self.teacher, self.disc = student, teacher, discriminator
         for p in teacher.parameters():
             p.requires_grad_(False)
@@ -30,6 +30,15 @@ class KDStep:
         # the frozen discriminator runs on the package's own engines (b200gan/dconv.py): NHWC-p activations, weights
         # re-laid out once into operand slabs (cached: the parameters are frozen), the image read through its strides
         self.bucket = D.FlatBucket(student.parameters())
+        # exponential moving average of the student (train.py:124-129 / :398; default decay train.py:352): kept in a
+        # bucket with the student's layout and updated by the same kernel pass as Adam
+        self.ema_bucket = None
+        if g_ema is not None:
+            names = [n for n, p in student.named_parameters() if p.requires_grad]
+            ema_params = dict(g_ema.named_parameters())
+            self.ema_bucket = D.FlatBucket([ema_params[n] for n in names], with_grads=False, all_params=True)
+            assert self.ema_bucket.offsets == self.bucket.offsets, 'g_ema must mirror the student parameter by parameter'
+        self.g_ema, self.ema_decay = g_ema, float(ema_decay)
         self.exp_avg = torch.zeros_like(self.bucket.flat_param)
         self.exp_avg_sq = torch.zeros_like(self.bucket.flat_param)
         self.lr, self.betas, self.eps = lr, betas, eps
@@ -87,11 +96,13 @@ class KDStep:
         self.t_dev += 1
         b1, b2 = self.betas
         with torch.cuda.device(self.device):
-            check(lib.cagc_adam_step(torch.cuda.current_stream(self.device).cuda_stream,
-                                     self.bucket.flat_param.data_ptr(), self.bucket.flat_grad.data_ptr(),
-                                     self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.bucket.numel,
-                                     self.lr, b1, b2, self.eps, 1.0 / D.get_world_size(), 1.0, 1.0,
-                                     self.t_dev.data_ptr()), 'adam_step')
+            check(lib.cagc_adam_ema_step(torch.cuda.current_stream(self.device).cuda_stream,
+                                         self.bucket.flat_param.data_ptr(), self.bucket.flat_grad.data_ptr(),
+                                         self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.bucket.numel,
+                                         self.lr, b1, b2, self.eps, 1.0 / D.get_world_size(), 1.0, 1.0,
+                                         self.t_dev.data_ptr(),
+                                         None if self.ema_bucket is None else self.ema_bucket.flat_param.data_ptr(),
+                                         self.ema_decay), 'adam_step')
         self._bump_versions()
         return total.detach()
 
@@ -101,6 +112,8 @@ class KDStep:
         b200gan.modconv when the student is frozen for a discriminator step (train.py:247), autograd's saved-tensor
         checks -- sees the update."""
         torch._C._increment_version(self.bucket.params)
+        if self.ema_bucket is not None:
+            torch._C._increment_version(self.ema_bucket.params)
 
     # ------------------------------------------------------------------ CUDA-graph form
     def capture(self, batch: int, inject_index: int, style_dim: int = 512):

@@ -10,7 +10,8 @@ only prepares the process around it:
      (train.py:15, Util/network_util.py:8, Evaluation/ppl.py:10);
   2. environment drift of this image is shimmed -- none of it concerns our kernels:
        * torchvision.utils.make_grid / save_image lost the `range=` keyword (Util/network_util.py:46-47, train.py:428-434);
-       * numpy >= 1.24 refuses ragged `np.array([...])` (prune.py:45);
+       * numpy >= 1.24 refuses ragged `np.array([...])` (prune.py:45); scipy >= 1.16 dropped `sqrtm(disp=)`
+         (Evaluation/fid.py:42);
        * `import lpips` needs `skimage` / `IPython` (lpips/__init__.py:7, lpips/networks_basic.py:11-12);
        * pretrained weights are downloaded (Util/face_parsing/resnet.py:83, lpips/pretrained_networks.py:100,
          Evaluation/inception.py:188) and there is no network: downloads return an empty marker and the module keeps its
@@ -49,12 +50,35 @@ def _shim_torchvision_range():
             if 'range' in k:
                 k['value_range'] = k.pop('range')
             return fn(*a, **k)
-        inner.__wrapped__ = fn
+        inner._cagc_range_shim = True
         return inner
     for name in ('make_grid', 'save_image'):
         fn = getattr(vu, name)
-        if not hasattr(fn, '__wrapped__'):
+        if not getattr(fn, '_cagc_range_shim', False):
             setattr(vu, name, wrap(fn))
+
+
+def _shim_scipy_sqrtm():
+    """scipy >= 1.16 dropped sqrtm(disp=...) (Evaluation/fid.py:42 passes disp=False and unpacks (sqrt, errest))."""
+    try:
+        from scipy import linalg
+    except Exception:
+        return
+    real = linalg.sqrtm
+    if getattr(real, '_cagc_disp_shim', False):
+        return
+    import inspect
+    try:
+        if 'disp' in inspect.signature(real).parameters:
+            return
+    except (TypeError, ValueError):
+        pass
+
+    def sqrtm(A, disp=True, **k):
+        out = real(A, **k)
+        return out if disp else (out, 0.0)
+    sqrtm._cagc_disp_shim = True
+    linalg.sqrtm = sqrtm
 
 
 def _shim_ragged_numpy():
@@ -75,20 +99,33 @@ def _shim_ragged_numpy():
 
 
 def _shim_missing_modules():
-    def stub(name, **attrs):
+    """`import lpips` pulls in skimage (measure.compare_ssim, color, transform) and IPython.embed at import time
+    (lpips/__init__.py:7, lpips/dist_model.py:16, lpips/networks_basic.py:11-12); none of them is used by the
+    'net-lin' VGG distance that train.py / Evaluation/ppl.py call.  Missing ones become empty stub modules."""
+    def stub(name, is_pkg=False, **attrs):
         if name in sys.modules:
             return
         try:
             __import__(name)
         except Exception:
             m = types.ModuleType(name)
+            if is_pkg:
+                m.__path__ = []
             m.__dict__.update(attrs)
             sys.modules[name] = m
-    stub('skimage')
-    stub('skimage.measure', compare_ssim=lambda *a, **k: (_ for _ in ()).throw(RuntimeError('skimage is not installed')))
+            if '.' in name:
+                parent, child = name.rsplit('.', 1)
+                setattr(sys.modules[parent], child, m)
+
+    def unavailable(*a, **k):
+        raise RuntimeError('scikit-image is not installed in this image')
+    stub('skimage', is_pkg=True)
+    stub('skimage.measure', compare_ssim=unavailable)
     stub('skimage.color')
-    if 'skimage.measure' in sys.modules and not hasattr(sys.modules['skimage.measure'], 'compare_ssim'):
-        sys.modules['skimage.measure'].compare_ssim = getattr(sys.modules['skimage.measure'], 'structural_similarity', None)
+    stub('skimage.transform')
+    if not hasattr(sys.modules['skimage.measure'], 'compare_ssim'):      # real, newer scikit-image renamed it
+        sys.modules['skimage.measure'].compare_ssim = getattr(sys.modules['skimage.measure'], 'structural_similarity',
+                                                              unavailable)
     stub('IPython', embed=lambda *a, **k: None)
 
 
@@ -200,6 +237,7 @@ def main(argv=None):
         'the drop-in model/op must be the ones bound by name'
     _shim_torchvision_range()
     _shim_ragged_numpy()
+    _shim_scipy_sqrtm()
     _shim_missing_modules()
     _shim_downloads()
     _shim_dataparallel_devices()

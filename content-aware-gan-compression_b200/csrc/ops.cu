@@ -300,7 +300,8 @@ __global__ void __launch_bounds__(256) to_nhwc_direct_kernel(const float* __rest
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                    float* __restrict__ m, float* __restrict__ v, int64_t n, float lr,
                                                    float b1, float b2, float eps, float gscale, float bc1, float bc2,
-                                                   const float* __restrict__ step_dev, int vec) {
+                                                   const float* __restrict__ step_dev, int vec,
+                                                   float* __restrict__ ema, float ema_decay) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     if (step_dev) {  // step count lives on the device so that a captured CUDA graph stays valid across replays
         const float t = __ldg(step_dev);
@@ -316,6 +317,9 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
         float denom = sqrtf(vv) * inv_sqrt_bc2 + eps;
         pp -= step * (mm / denom);
     };
+    // exponential moving average of the updated parameters (train.py:124-129 `accumulate`, called right after
+    // g_optim.step() at :398): ema = ema * decay + (1 - decay) * p, in the same pass over the bucket
+    auto avg = [&](float& ee, float pp) { ee = ee * ema_decay + (1.f - ema_decay) * pp; };
     if (vec) {
         const int64_t n4 = n >> 2;
         for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -327,11 +331,21 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
             st4(p + 4 * i, pv);
             st4(m + 4 * i, mv);
             st4(v + 4 * i, vv);
+            if (ema) {
+                float4 ev = ld4(ema + 4 * i);
+                avg(ev.x, pv.x); avg(ev.y, pv.y); avg(ev.z, pv.z); avg(ev.w, pv.w);
+                st4(ema + 4 * i, ev);
+            }
         }
-        for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
             upd(p[i], g[i], m[i], v[i]);
+            if (ema) avg(ema[i], p[i]);
+        }
     } else {
-        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) upd(p[i], g[i], m[i], v[i]);
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+            upd(p[i], g[i], m[i], v[i]);
+            if (ema) avg(ema[i], p[i]);
+        }
     }
 }
 
@@ -447,16 +461,26 @@ int cagc_to_nhwc(cagc_stream_t stream_, const float* src, int64_t sb, int64_t sc
     return launched("to_nhwc_transpose_kernel");
 }
 
-int cagc_adam_step(cagc_stream_t stream_, float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
-                   int64_t n, float lr, float beta1, float beta2, float eps, float grad_scale, float bias_corr1,
-                   float bias_corr2, const float* step_dev) {
+int cagc_adam_ema_step(cagc_stream_t stream_, float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                       int64_t n, float lr, float beta1, float beta2, float eps, float grad_scale, float bias_corr1,
+                       float bias_corr2, const float* step_dev, float* ema, float ema_decay) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (n == 0) return 0;
     CAGC_REQUIRE(param && grad && exp_avg && exp_avg_sq, "adam_step: null pointer");
-    const int vec = aligned16(param) && aligned16(grad) && aligned16(exp_avg) && aligned16(exp_avg_sq);
+    CAGC_REQUIRE(!ema || (ema_decay >= 0.f && ema_decay <= 1.f), "adam_step: ema decay must lie in [0, 1]");
+    const int vec = aligned16(param) && aligned16(grad) && aligned16(exp_avg) && aligned16(exp_avg_sq) &&
+                    (!ema || aligned16(ema));
     adam_kernel<<<grid_for(vec ? n / 4 + 1 : n), 256, 0, stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1,
-                                                                    beta2, eps, grad_scale, bias_corr1, bias_corr2, step_dev, vec);
+                                                                    beta2, eps, grad_scale, bias_corr1, bias_corr2, step_dev,
+                                                                    vec, ema, ema_decay);
     return launched("adam_kernel");
+}
+
+int cagc_adam_step(cagc_stream_t stream, float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                   int64_t n, float lr, float beta1, float beta2, float eps, float grad_scale, float bias_corr1,
+                   float bias_corr2, const float* step_dev) {
+    return cagc_adam_ema_step(stream, param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, grad_scale, bias_corr1,
+                              bias_corr2, step_dev, nullptr, 0.f);
 }
 
 }  // extern "C"

@@ -275,6 +275,12 @@ int cagc_to_nhwc(cagc_stream_t stream, const float* src, int64_t sb, int64_t sc,
 int cagc_adam_step(cagc_stream_t stream, float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
                    int64_t n, float lr, float beta1, float beta2, float eps, float grad_scale,
                    float bias_corr1, float bias_corr2, const float* step_dev);
+/* Same, with the generator's exponential moving average folded into the pass (reference train.py:124-129
+ * `accumulate(g_ema, g, decay)`, called after every optimizer step at :398): ema (nullable, bucket of the same
+ * layout) <- ema * ema_decay + (1 - ema_decay) * updated param. */
+int cagc_adam_ema_step(cagc_stream_t stream, float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                       int64_t n, float lr, float beta1, float beta2, float eps, float grad_scale,
+                       float bias_corr1, float bias_corr2, const float* step_dev, float* ema, float ema_decay);
 
 /* ----------------------------------------------------------------------
  * Discriminator path (reference model.py:670-798: ConvLayer / ResBlock / EqualConv2d).  The reference runs
