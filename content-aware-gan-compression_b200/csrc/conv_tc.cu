@@ -30,8 +30,12 @@ constexpr int kChunkK = 32;                      // fp32 elements per 128-byte s
 constexpr int kABytes = kTileM * kChunkK * 4;    // 16 KB
 constexpr int kMaxStages = 12;
 constexpr int kMaxPhases = 4;
-constexpr int kSmemBudget = 110 * 1024;          // two CTAs per SM
-constexpr int kSmemBudget1 = 220 * 1024;         // one CTA per SM (two M sub-tiles, > 256 TMEM columns)
+constexpr int kSmemBudget = 110 * 1024;          // two CTAs per SM (weight-gradient kernels)
+constexpr int kSmemBudget1 = 220 * 1024;         // one CTA per SM
+// convolution kernels: 16 KB of static shared memory per CTA belong to the epilogue's transpose staging
+constexpr int kEpiStageBytes = 4 * 32 * 32 * 4;
+constexpr int kConvBudget = kSmemBudget - kEpiStageBytes;     // two CTAs per SM
+constexpr int kConvBudget1 = kSmemBudget1 - kEpiStageBytes;   // one CTA per SM (two M sub-tiles, > 256 TMEM columns)
 
 struct TcParams {
     const float* out_scale;
@@ -134,6 +138,102 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, float* v) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float* v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Epilogue.  tcgen05.ld hands every lane one accumulator ROW (= one output pixel): storing from that layout makes
+// each 16-byte store of a warp touch 32 different cache lines -- measured, that request rate (not the tensor pipe,
+// not L2->SMEM operand traffic) is what held every HBM-heavy layer at ~0.8 TB/s of output.  So each warp transposes
+// its 32 rows x CW columns through a swizzled shared-memory tile: afterwards 8 (CW = 32) or 4 (CW = 16) consecutive
+// lanes own the 16-byte segments of ONE pixel, a warp store covers 4 / 8 pixels x 128 / 64 contiguous bytes (whole
+// sectors), the residual is read with the same pattern, and a lane's four channels -- hence its bias -- are fixed.
+// ------------------------------------------------------------------------------------------------
+struct EpiArgs {
+    const float* out_scale;   // [B][n_pitch] or null
+    const float* bias;        // [n_pitch] or null
+    const float* residual;    // layout of out, or null
+    float* out;
+    int n_pitch, out_valid, act, has_noise;
+    float act_gain;
+};
+
+template <int CW>
+__device__ __forceinline__ void epi_chunk(const EpiArgs& e, float* st, uint32_t taddr, int lane, int n, bool rvalid,
+                                          int64_t roff, float rnz, int rb) {
+    constexpr int NSEG = CW / 4;          // 16-byte segments per row
+    constexpr int RI = 32 / NSEG;         // rows covered by one warp-wide store
+    float v[CW];
+    if (CW == 32) tc_ld32(taddr, v); else tc_ld16(taddr, v);
+    // row `lane`, segment k -> physical segment k ^ (lane % NSEG): conflict-free 128-bit shared stores and loads
+#pragma unroll
+    for (int k = 0; k < NSEG; ++k)
+        st4(st + (lane * NSEG + (k ^ (lane & (NSEG - 1)))) * 4, make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]));
+    __syncwarp();
+    const int seg = lane & (NSEG - 1), rsub = lane / NSEG;
+    const int cn = n + seg * 4;
+    const bool cvalid = cn < e.n_pitch;
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (e.bias && cvalid) b4 = ldg4(e.bias + cn);
+    // rows of one warp almost always belong to one sample: then the demodulation scale is per lane, loaded once
+    const int b0 = __shfl_sync(0xffffffffu, rb, 0);
+    const bool uniform_b = __all_sync(0xffffffffu, rb == b0 || !rvalid);
+    float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (e.out_scale && uniform_b && cvalid) s4 = ldg4(e.out_scale + (int64_t)b0 * e.n_pitch + cn);
+#pragma unroll
+    for (int i = 0; i < NSEG; ++i) {
+        const int row = i * RI + rsub;
+        const bool valid = __shfl_sync(0xffffffffu, (int)rvalid, row) != 0;
+        const int off_lo = __shfl_sync(0xffffffffu, (int)(uint32_t)(roff & 0xffffffffll), row);
+        const int off_hi = __shfl_sync(0xffffffffu, (int)(roff >> 32), row);
+        const float nz = e.has_noise ? __shfl_sync(0xffffffffu, rnz, row) : 0.f;
+        const int b = uniform_b ? b0 : __shfl_sync(0xffffffffu, rb, row);
+        if (!valid || !cvalid) continue;
+        const int64_t off = ((int64_t)off_hi << 32) | (uint32_t)off_lo;
+        const float4 x = ld4(st + (row * NSEG + (seg ^ (row & (NSEG - 1)))) * 4);
+        float o[4] = {x.x, x.y, x.z, x.w};
+        if (e.out_scale) {
+            const float4 sc = uniform_b ? s4 : ldg4(e.out_scale + (int64_t)b * e.n_pitch + cn);
+            o[0] *= sc.x; o[1] *= sc.y; o[2] *= sc.z; o[3] *= sc.w;
+        }
+        if (e.has_noise) { o[0] += nz; o[1] += nz; o[2] += nz; o[3] += nz; }
+        if (e.bias) { o[0] += b4.x; o[1] += b4.y; o[2] += b4.z; o[3] += b4.w; }
+        if (e.act) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = lrelu_gain(o[j], e.act_gain);
+        }
+        if (e.residual) {
+            const float4 r4 = ldg4(e.residual + off + cn);
+            o[0] += r4.x; o[1] += r4.y; o[2] += r4.z; o[3] += r4.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (cn + j >= e.out_valid) o[j] = 0.f;
+        st4(e.out + off + cn, make_float4(o[0], o[1], o[2], o[3]));
+    }
+    __syncwarp();          // the staging tile is rewritten by the next chunk
+}
+
+// all column chunks of one 128-row sub-tile for this warp's 32 rows
+__device__ __forceinline__ void epi_rows(const EpiArgs& e, float* st, uint32_t taddr, int lane, int n0, int n_mma, bool rvalid,
+                                         int64_t roff, float rnz, int rb) {
+    int c = 0;
+    for (; c + 32 <= n_mma; c += 32) epi_chunk<32>(e, st, taddr + (uint32_t)c, lane, n0 + c, rvalid, roff, rnz, rb);
+    if (c < n_mma) epi_chunk<16>(e, st, taddr + (uint32_t)c, lane, n0 + c, rvalid, roff, rnz, rb);
+}
+
 // One elected lane of a converged warp.  The TMA / MMA warps keep their control flow warp-uniform and put only
 // the asynchronous instruction itself under the election: every address / descriptor computation then stays on
 // the uniform datapath, and the single-thread issue loop (the real bound of narrow-N tcgen05 tiles: ~150 cycles
@@ -171,6 +271,59 @@ __device__ __forceinline__ void mma_stage_k(uint32_t d, uint32_t a_lo, uint32_t 
     }
 }
 
+// Warp-uniform issue: all 32 lanes execute the (uniform) descriptor arithmetic, the lane election happens INSIDE the
+// asm block and only predicates the asynchronous instruction.  The C++ around it has no divergent region, so the
+// compiler keeps descriptors / barrier addresses on the uniform datapath (no R2UR round trips, no BSSY/BSYNC):
+// ncu showed ~200 issue-warp instructions per stage with the `if (elect_one())` form, i.e. the issuing warp -- not
+// the tensor pipe -- bounded every layer whose MMAs are short (N <= 128).
+__device__ __forceinline__ void mma_k4_elect(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred pe, pa, pt;\n\t.reg .b64 da, db;\n\t.reg .b32 ta, tb;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "setp.ne.b32 pa, %5, 0;\n\t"
+        "setp.eq.b32 pt, 0, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, pa;\n\t"
+        "add.u32 ta, %1, 2;\n\tadd.u32 tb, %2, 2;\n\t"
+        "mov.b64 da, {ta, %3};\n\tmov.b64 db, {tb, %3};\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, pt;\n\t"
+        "add.u32 ta, %1, 4;\n\tadd.u32 tb, %2, 4;\n\t"
+        "mov.b64 da, {ta, %3};\n\tmov.b64 db, {tb, %3};\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, pt;\n\t"
+        "add.u32 ta, %1, 6;\n\tadd.u32 tb, %2, 6;\n\t"
+        "mov.b64 da, {ta, %3};\n\tmov.b64 db, {tb, %3};\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, pt;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(kDescHiSw128), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mma_k1_elect(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred pe, pa;\n\t.reg .b64 da, db;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "setp.ne.b32 pa, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, pa;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(kDescHiSw128), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// the (up to) four K = 8 steps of one 32-channel stage for one (A tile, B tile) pair; call with the warp converged
+__device__ __forceinline__ void mma_stage_k_uniform(uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, int kk, bool fresh) {
+    if (kk == 4) {
+        mma_k4_elect(d, a_lo, b_lo, idesc, fresh ? 0u : 1u);
+    } else {
+        for (int k = 0; k < kk; ++k) mma_k1_elect(d, a_lo + 2 * k, b_lo + 2 * k, idesc, (fresh && k == 0) ? 0u : 1u);
+    }
+}
+__device__ __forceinline__ void tc_commit_elect(uint32_t bar) {
+    asm volatile(
+        "{\n\t.reg .pred pe;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+        ::"r"(bar) : "memory");
+}
+
 // K-major, 128-byte swizzle shared-memory matrix descriptor: 8-row groups of 1024 bytes
 // (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout [61,64))
 __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
@@ -186,6 +339,7 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
 __global__ void __launch_bounds__(kThreads, 2)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(16) float epi_stage[4][32 * 32];
     __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 1];
     __shared__ uint32_t tmem_base_slot;
 
@@ -295,6 +449,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int lb = m / (p.bw * p.bh);
         mbar_wait(acc_bar, 0);
         tc_fence_after();
+        const EpiArgs ea{p.out_scale, p.bias, p.residual, p.out, p.n_pitch, p.out_valid, p.act, p.noise != nullptr, p.act_gain};
       for (int j = 0; j < MT; ++j) {
         const int ox = x0s[j] + lx, oy = y0s[j] + ly, b = b0s[j] + lb;
         const bool pvalid = (ox < p.Wo) && (oy < p.Ho) && (b < p.B);
@@ -302,40 +457,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         float nz = 0.f;
         if (p.noise && pvalid)
             nz = __ldg(p.noise_w) * __ldg(p.noise + (int64_t)b * p.noise_bstride + (int64_t)yy * p.Wout + xx);
-        float* dst = p.out + (((int64_t)b * p.Hout + yy) * p.Wout + xx) * p.n_pitch;
-        const float* sc = p.out_scale ? p.out_scale + (int64_t)b * p.n_pitch : nullptr;
-        for (int c = 0; c < n_mma; c += 16) {
-            float v[16];
-            tc_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * n_mma + c), v);   // warp-collective
-            if (!pvalid) continue;
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                const int n = n0 + c + g * 4;
-                if (n >= p.n_pitch) break;
-                float o[4] = {v[g * 4 + 0], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]};
-                if (sc) {
-                    const float4 s4 = ldg4(sc + n);
-                    o[0] *= s4.x; o[1] *= s4.y; o[2] *= s4.z; o[3] *= s4.w;
-                }
-                if (p.noise) { o[0] += nz; o[1] += nz; o[2] += nz; o[3] += nz; }
-                if (p.bias) {
-                    const float4 b4 = ldg4(p.bias + n);
-                    o[0] += b4.x; o[1] += b4.y; o[2] += b4.z; o[3] += b4.w;
-                }
-                if (p.act) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) o[j] = lrelu_gain(o[j], p.act_gain);
-                }
-                if (p.residual) {
-                    const float4 r4 = ldg4(p.residual + (dst - p.out) + n);
-                    o[0] += r4.x; o[1] += r4.y; o[2] += r4.z; o[3] += r4.w;
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (n + j >= p.out_valid) o[j] = 0.f;
-                st4(dst + n, make_float4(o[0], o[1], o[2], o[3]));
-            }
-        }
+        const int64_t roff = (((int64_t)b * p.Hout + yy) * p.Wout + xx) * p.n_pitch;
+        epi_rows(ea, epi_stage[q], tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * n_mma), lane, n0, n_mma, pvalid,
+                 roff, nz, b);
       }
     }
 
@@ -362,6 +486,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                        const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(16) float epi_stage[4][32 * 32];
     __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 4];
     __shared__ uint32_t tmem_base_slot;
 
@@ -369,8 +494,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int S = p.stages, MT = p.mt;
     const uint32_t stage_bytes = (uint32_t)MT * kABytes + p.b_bytes;
-    auto a_addr = [&](int s, int j) { return smem_base + (uint32_t)s * stage_bytes + (uint32_t)j * kABytes; };
-    auto b_addr = [&](int s) { return smem_base + (uint32_t)s * stage_bytes + (uint32_t)MT * kABytes; };
+    // stage s: [MT A tiles of 16 KB][B tile] at smem_base + s * stage_bytes
     const uint32_t bar0 = smem_u32(bars);
     auto full_bar = [&](int s) { return bar0 + 8u * s; };
     auto empty_bar = [&](int s) { return bar0 + 8u * (kMaxStages + s); };
@@ -432,31 +556,43 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         return f;
     };
 
+    // Both issue loops keep RUNNING state (stage address / barrier address / chunk and tap counters advanced by adds
+    // with a wrap) instead of re-deriving it from the iteration index: with 64-cycle N = 128 MMAs the single issuing
+    // thread is the bound of the kernel (ncu: ~200 instructions, among them two integer divisions, per 8-MMA stage).
     if (warp == 0) {
         int s = 0;
         uint32_t ph = 0;
+        uint32_t st_addr = smem_base, fb = full_bar(0);
         for (int item = blockIdx.x; item < items; item += gridDim.x) {
             int x0s[2], y0s[2], b0s[2], n0, n_mma;
             const int f = decode(item, x0s, y0s, b0s, n0, n_mma);
-            const int per_item = p.ph_ntaps[f] * nk;
-            for (int it = 0; it < per_item; ++it) {
-                mbar_wait(empty_bar(s), ph ^ 1u);
-                const int tap = it / nk, kc = it - tap * nk;
-                const Tap tp = p.taps[p.ph_tap0[f] + tap];
-                if (elect_one()) {
-                    mbar_expect_tx(full_bar(s), stage_bytes);
-                    for (int j = 0; j < MT; ++j)
-                        tma_load_4d(a_addr(s, j), &map_a, full_bar(s), kc * kChunkK, x0s[j] * p.in_stride + tp.dx,
-                                    y0s[j] * p.in_stride + tp.dy, b0s[j]);
-                    tma_load_3d(b_addr(s), &map_b, full_bar(s), kc * kChunkK, n0, tp.slab);
+            const int ntap = p.ph_ntaps[f], tap0 = p.ph_tap0[f];
+            const int ax0 = x0s[0] * p.in_stride, ay0 = y0s[0] * p.in_stride;
+            const int ax1 = x0s[1] * p.in_stride, ay1 = y0s[1] * p.in_stride;
+            for (int tap = 0; tap < ntap; ++tap) {
+                const Tap tp = p.taps[tap0 + tap];
+                for (int kc = 0; kc < nk; ++kc) {
+                    mbar_wait(fb + 8u * kMaxStages, ph ^ 1u);
+                    if (elect_one()) {
+                        mbar_expect_tx(fb, stage_bytes);
+                        tma_load_4d(st_addr, &map_a, fb, kc * kChunkK, ax0 + tp.dx, ay0 + tp.dy, b0s[0]);
+                        if (MT == 2) tma_load_4d(st_addr + kABytes, &map_a, fb, kc * kChunkK, ax1 + tp.dx, ay1 + tp.dy, b0s[1]);
+                        tma_load_3d(st_addr + (uint32_t)MT * kABytes, &map_b, fb, kc * kChunkK, n0, tp.slab);
+                    }
+                    __syncwarp();
+                    if (++s == S) { s = 0; ph ^= 1u; st_addr = smem_base; fb = bar0; }
+                    else { st_addr += stage_bytes; fb += 8u; }
                 }
-                __syncwarp();
-                if (++s == S) { s = 0; ph ^= 1u; }
             }
         }
     } else if (warp == 1) {
         int s = 0, acc = 0;
         uint32_t ph = 0, aph = 0;
+        const uint32_t lo_base = desc_lo_sw128(smem_base);
+        const uint32_t st_step = stage_bytes >> 4, a_step = (uint32_t)kABytes >> 4, b_off = (uint32_t)MT * a_step;
+        uint32_t lo_s = lo_base, fb = full_bar(0);
+        int kk_last = (p.k_valid - (nk - 1) * kChunkK + 7) >> 3;
+        if (kk_last > 4) kk_last = 4;
         for (int item = blockIdx.x; item < items; item += gridDim.x) {
             int x0s[2], y0s[2], b0s[2], n0, n_mma;
             const int f = decode(item, x0s, y0s, b0s, n0, n_mma);
@@ -466,21 +602,18 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
             mbar_wait(tempty_bar(acc), aph ^ 1u);        // epilogue has drained this accumulator buffer
             tc_fence_after();
             const uint32_t d0 = tmem_acc + (uint32_t)(acc * acc_stride);
+            int kc = 0;
             for (int it = 0; it < per_item; ++it) {
-                mbar_wait(full_bar(s), ph);
+                mbar_wait(fb, ph);
                 tc_fence_after();
-                const int kc = it % nk;
-                int kk = (p.k_valid - kc * kChunkK + 7) >> 3;
-                if (kk > 4) kk = 4;
-                const uint32_t b_lo = desc_lo_sw128(b_addr(s));
-                if (elect_one()) {
-                    for (int j = 0; j < MT; ++j)
-                        mma_stage_k(d0 + (uint32_t)(j * p.n_tile), desc_lo_sw128(a_addr(s, j)), b_lo, idesc, kk, it == 0);
-                    tc_commit(empty_bar(s));
-                    if (it == per_item - 1) tc_commit(tfull_bar(acc));
-                }
-                __syncwarp();
-                if (++s == S) { s = 0; ph ^= 1u; }
+                const int kk = (kc == nk - 1) ? kk_last : 4;
+                mma_stage_k_uniform(d0, lo_s, lo_s + b_off, idesc, kk, it == 0);
+                if (MT == 2) mma_stage_k_uniform(d0 + (uint32_t)p.n_tile, lo_s + a_step, lo_s + b_off, idesc, kk, it == 0);
+                tc_commit_elect(fb + 8u * kMaxStages);
+                if (it == per_item - 1) tc_commit_elect(tfull_bar(acc));
+                if (++kc == nk) kc = 0;
+                if (++s == S) { s = 0; ph ^= 1u; lo_s = lo_base; fb = bar0; }
+                else { lo_s += st_step; fb += 8u; }
             }
             if (++acc == 2) { acc = 0; aph ^= 1u; }
         }
@@ -491,6 +624,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         const int ly = (m / p.bw) % p.bh;
         const int lb = m / (p.bw * p.bh);
         const float nwv = p.noise ? __ldg(p.noise_w) : 0.f;
+        const EpiArgs ea{p.out_scale, p.bias, p.residual, p.out, p.n_pitch, p.out_valid, p.act, p.noise != nullptr, p.act_gain};
         int acc = 0;
         uint32_t aph = 0;
         for (int item = blockIdx.x; item < items; item += gridDim.x) {
@@ -517,40 +651,8 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                 const bool pvalid = (ox < p.ph_Wo[f]) && (oy < p.ph_Ho[f]) && (b < p.B);
                 const int yy = oy * p.out_stride + p.ph_oy[f], xx = ox * p.out_stride + p.ph_ox[f];
                 const float nz = nzs[j];
-                float* dst = p.out + (((int64_t)b * p.Hout + yy) * p.Wout + xx) * p.n_pitch;
-                const float* sc = p.out_scale ? p.out_scale + (int64_t)b * p.n_pitch : nullptr;
-                for (int c = 0; c < n_mma; c += 16) {
-                    float v[16];
-                    tc_ld16(d0 + (uint32_t)(j * p.n_tile + c), v);
-                    if (!pvalid) continue;
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        const int n = n0 + c + g * 4;
-                        if (n >= p.n_pitch) break;
-                        float o[4] = {v[g * 4 + 0], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]};
-                        if (sc) {
-                            const float4 s4 = ldg4(sc + n);
-                            o[0] *= s4.x; o[1] *= s4.y; o[2] *= s4.z; o[3] *= s4.w;
-                        }
-                        if (p.noise) { o[0] += nz; o[1] += nz; o[2] += nz; o[3] += nz; }
-                        if (p.bias) {
-                            const float4 b4 = ldg4(p.bias + n);
-                            o[0] += b4.x; o[1] += b4.y; o[2] += b4.z; o[3] += b4.w;
-                        }
-                        if (p.act) {
-#pragma unroll
-                            for (int jj = 0; jj < 4; ++jj) o[jj] = lrelu_gain(o[jj], p.act_gain);
-                        }
-                        if (p.residual) {
-                            const float4 r4 = ldg4(p.residual + (dst - p.out) + n);
-                            o[0] += r4.x; o[1] += r4.y; o[2] += r4.z; o[3] += r4.w;
-                        }
-#pragma unroll
-                        for (int jj = 0; jj < 4; ++jj)
-                            if (n + jj >= p.out_valid) o[jj] = 0.f;
-                        st4(dst + n, make_float4(o[0], o[1], o[2], o[3]));
-                    }
-                }
+                const int64_t roff = (((int64_t)b * p.Hout + yy) * p.Wout + xx) * p.n_pitch;
+                epi_rows(ea, epi_stage[q], d0 + (uint32_t)(j * p.n_tile), lane, n0, n_mma, pvalid, roff, nz, b);
             }
             // this warp has finished reading the accumulator buffer: hand it back to the MMA warp
             tc_fence_before();
@@ -593,7 +695,10 @@ struct HaloParams {
     int TW, R, Wt, rows_box;        // tile width / rows, raster pitch, box rows (R + dyspan)
     int dx_min, dy_min;
     int strips, ytiles;             // tiles per sample
-    int mt;                         // 128-row M sub-tiles per tile: ceil(R*Wt / 128)
+    int mt;                         // 128-row M sub-tiles per tile: ceil(R*Wt / 128) (raster mode) or R (row mode)
+    int debug;                      // timing experiments only: bit0 skip epilogue work, bit1 skip MMA issue
+    int row_mode;                   // 1: sub-tile j = output row j of the tile (TW <= 128 pixels, no halo columns in M)
+    int sub_rows;                   // raster rows between consecutive sub-tiles: 128 (raster mode) or Wt (row mode)
     int k_valid, n_pitch, out_valid, n_tile, n_rows;
     int Hout, Wout, out_stride, out_oy, out_ox;
     int64_t noise_bstride;
@@ -609,6 +714,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const __grid_constant__ HaloParams p) {
     extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(16) float epi_stage[4][32 * 32];
     __shared__ __align__(8) uint64_t bars[2 * kHaloMaxB + 8];
     __shared__ uint32_t tmem_base_slot;
 
@@ -696,8 +802,17 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             }
         }
     } else if (warp == 1) {
+        // Issue loop with running state: the single issuing thread is the bound of the narrow layers (a 128 x 48 x 8
+        // MMA occupies the tensor pipe for 24 cycles), so nothing is re-derived per stage that an add can carry along.
         int s = 0, ab = 0, acc = 0;
         uint32_t ph = 0, aph = 0, tph = 0;
+        const uint32_t sub_step = ((uint32_t)p.sub_rows * 128u) >> 4;      // descriptor address units (16 bytes)
+        const uint32_t n_tile = (uint32_t)p.n_tile, b_step = p.b_bytes >> 4;
+        const uint32_t b_lo0 = desc_lo_sw128(b_base), a_lo0 = desc_lo_sw128(smem_base), a_step = p.a_stride >> 4;
+        uint32_t b_lo = b_lo0, bf = bfull(0);
+        const int ntaps = p.ntaps;
+        int kk_last = (p.k_valid - (nk - 1) * kChunkK + 7) >> 3;
+        if (kk_last > 4) kk_last = 4;
         for (int item = blockIdx.x; item < items; item += gridDim.x) {
             int x0, y0, b, n0, n_mma;
             decode(item, x0, y0, b, n0, n_mma);
@@ -709,26 +824,28 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             for (int kc = 0; kc < nk; ++kc) {
                 mbar_wait(afull(ab), aph);
                 tc_fence_after();
-                int kk = (p.k_valid - kc * kChunkK + 7) >> 3;
-                if (kk > 4) kk = 4;
-                const uint32_t a_buf = smem_base + (uint32_t)ab * p.a_stride;
-                for (int tap = 0; tap < p.ntaps; ++tap) {
-                    mbar_wait(bfull(s), ph);
+                const int kk = (kc == nk - 1) ? kk_last : 4;
+                const uint32_t a_buf_lo = a_lo0 + (uint32_t)ab * a_step;
+                for (int tap = 0; tap < ntaps; ++tap) {
+                    mbar_wait(bf, ph);
                     tc_fence_after();
-                    const uint32_t b_lo = desc_lo_sw128(b_base + (uint32_t)s * p.b_bytes);
-                    const uint32_t a_lo = desc_lo_sw128(a_buf + (uint32_t)p.tap_row[tap] * 128u);
-                    if (elect_one()) {
-                        for (int j = 0; j < MT; ++j)     // next 128 raster rows: +128*128 bytes = +1024 in the address field
-                            mma_stage_k(d0 + (uint32_t)(j * p.n_tile), a_lo + (uint32_t)j * (kTileM * 128u >> 4), b_lo, idesc,
-                                        kk, kc == 0 && tap == 0);
-                        tc_commit(bempty(s));
-                        if (tap == p.ntaps - 1) {
-                            tc_commit(aempty(ab));
-                            if (kc == nk - 1) tc_commit(tfull(acc));
+                    const uint32_t a_lo = a_buf_lo + (uint32_t)p.tap_row[tap] * 8u;      // 128-byte rows, >> 4
+                    {
+                        uint32_t d = d0, a = a_lo;
+                        const bool fresh = (kc == 0) && (tap == 0);
+                        for (int j = 0; j < MT; ++j) {          // next sub-tile: +sub_rows raster rows
+                            if (!(p.debug & 2)) mma_stage_k_uniform(d, a, b_lo, idesc, kk, fresh);
+                            d += n_tile;
+                            a += sub_step;
+                        }
+                        tc_commit_elect(bf + 8u * kHaloMaxB);
+                        if (tap == ntaps - 1) {
+                            tc_commit_elect(aempty(ab));
+                            if (kc == nk - 1) tc_commit_elect(tfull(acc));
                         }
                     }
-                    __syncwarp();
-                    if (++s == SB) { s = 0; ph ^= 1u; }
+                    if (++s == SB) { s = 0; ph ^= 1u; b_lo = b_lo0; bf = bar0; }
+                    else { b_lo += b_step; bf += 8u; }
                 }
                 if (++ab == 2) { ab = 0; aph ^= 1u; }
             }
@@ -738,6 +855,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const int q = warp & 3;
         const int m = q * 32 + lane;
         const float nwv = p.noise ? __ldg(p.noise_w) : 0.f;
+        const EpiArgs ea{p.out_scale, p.bias, p.residual, p.out, p.n_pitch, p.out_valid, p.act, p.noise != nullptr, p.act_gain};
         int acc = 0;
         uint32_t tph = 0;
         for (int item = blockIdx.x; item < items; item += gridDim.x) {
@@ -751,7 +869,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 nzs[j] = 0.f;
                 if (p.noise && j < MT) {
                     const int pos = j * kTileM + m;
-                    const int ry = pos / p.Wt, rx = pos - ry * p.Wt;
+                    const int ry = p.row_mode ? j : pos / p.Wt, rx = p.row_mode ? m : pos - ry * p.Wt;
                     const int ox = x0 + rx, oy = y0 + ry;
                     if ((rx < p.TW) && (ry < p.R) && (ox < p.Wo) && (oy < p.Ho))
                         nzs[j] = nwv * __ldg(p.noise + (int64_t)b * p.noise_bstride +
@@ -761,49 +879,17 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             mbar_wait(tfull(acc), tph);
             tc_fence_after();
             const uint32_t d0 = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * acc_stride);
-            const float* sc = p.out_scale ? p.out_scale + (int64_t)b * p.n_pitch : nullptr;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 if (j >= MT) break;
                 const int pos = j * kTileM + m;              // raster position inside the tile
-                const int ry = pos / p.Wt, rx = pos - ry * p.Wt;
+                const int ry = p.row_mode ? j : pos / p.Wt, rx = p.row_mode ? m : pos - ry * p.Wt;
                 const int ox = x0 + rx, oy = y0 + ry;
                 const bool pvalid = (rx < p.TW) && (ry < p.R) && (ox < p.Wo) && (oy < p.Ho);
                 const int yy = oy * p.out_stride + p.out_oy, xx = ox * p.out_stride + p.out_ox;
                 const float nz = nzs[j];
-                float* dst = p.out + (((int64_t)b * p.Hout + yy) * p.Wout + xx) * p.n_pitch;
-                for (int c = 0; c < n_mma; c += 16) {
-                    float v[16];
-                    tc_ld16(d0 + (uint32_t)(j * p.n_tile + c), v);
-                    if (!pvalid) continue;
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        const int n = n0 + c + g * 4;
-                        if (n >= p.n_pitch) break;
-                        float o[4] = {v[g * 4 + 0], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]};
-                        if (sc) {
-                            const float4 s4 = ldg4(sc + n);
-                            o[0] *= s4.x; o[1] *= s4.y; o[2] *= s4.z; o[3] *= s4.w;
-                        }
-                        if (p.noise) { o[0] += nz; o[1] += nz; o[2] += nz; o[3] += nz; }
-                        if (p.bias) {
-                            const float4 b4 = ldg4(p.bias + n);
-                            o[0] += b4.x; o[1] += b4.y; o[2] += b4.z; o[3] += b4.w;
-                        }
-                        if (p.act) {
-#pragma unroll
-                            for (int jj = 0; jj < 4; ++jj) o[jj] = lrelu_gain(o[jj], p.act_gain);
-                        }
-                        if (p.residual) {
-                            const float4 r4 = ldg4(p.residual + (dst - p.out) + n);
-                            o[0] += r4.x; o[1] += r4.y; o[2] += r4.z; o[3] += r4.w;
-                        }
-#pragma unroll
-                        for (int jj = 0; jj < 4; ++jj)
-                            if (n + jj >= p.out_valid) o[jj] = 0.f;
-                        st4(dst + n, make_float4(o[0], o[1], o[2], o[3]));
-                    }
-                }
+                const int64_t roff = (((int64_t)b * p.Hout + yy) * p.Wout + xx) * p.n_pitch;
+                if (!(p.debug & 1)) epi_rows(ea, epi_stage[q], d0 + (uint32_t)(j * p.n_tile), lane, n0, n_mma, pvalid, roff, nz, b);
             }
             tc_fence_before();
             __syncwarp();
@@ -1663,7 +1749,7 @@ static int try_halo_conv(cudaStream_t stream, const ConvP& c, const char* what, 
     // default: the narrow (operand-traffic-bound) layers; CAGC_TC_HALO=2 forces every eligible shape
     // (measured per layer, scripts/layer_times.py: wins for N <= 80 -- 39/77-channel layers and their up-conv phases;
     //  at N >= 128 the plain kernels' larger MMAs and two-CTA overlap are faster)
-    if (halo_env == 1 && c.n_cols > 80) return 0;
+    if (halo_env == 1 && c.n_cols > 80 && !(c.n_cols <= 256 && c.Wo >= 128 && c.Wo % 128 == 0)) return 0;
     const int min_w = [] { const char* e = getenv("CAGC_TC_HALO_MINW"); return e ? atoi(e) : 32; }();
     if (c.Wo < min_w) return 0;
     int dxmin = 0, dxmax = 0, dymin = 0, dymax = 0;
@@ -1676,42 +1762,73 @@ static int try_halo_conv(cudaStream_t stream, const ConvP& c, const char* what, 
     p.n_rows = (c.n_cols + 15) & ~15;
     p.n_tile = std::min(256, p.n_rows);
     const int n_tiles = ceil_div(p.n_rows, p.n_tile);
-    p.TW = std::min(c.Wo, 64);
-    if (const char* e = getenv("CAGC_TC_HALO_TW")) p.TW = std::min(c.Wo, std::max(8, atoi(e)));
-    p.Wt = p.TW + dxs;
-    p.strips = ceil_div(c.Wo, p.TW);
     const int mt_max = std::min(8, 512 / p.n_tile);
     p.b_bytes = (uint32_t)p.n_tile * kChunkK * 4;
-    // choose the tile height: best MMA-row / operand-byte efficiency that fits shared memory and TMEM
-    const int smem_budget = 222 * 1024;
+    const int smem_budget = 222 * 1024 - kEpiStageBytes;
+    // the weight ring must cover the TMA round trip of its per-tap stages: 8 small stages for narrow N, at least 4
+    // of the large (>= 16 KB) stages of wide N
+    const int b_min = (p.b_bytes >= 32768) ? 3 : (p.b_bytes >= 16384) ? 4 : std::min(kHaloMaxB, c.ntaps);
+    // Row mode (wide layers, W >= 128): a tile is R full 128-pixel output rows; sub-tile j is output row j, its taps
+    // are the R+dys input rows of the window shifted by dx -- no halo column ever enters the M dimension, weights are
+    // shared by the R rows, every input row is loaded once per 32-channel chunk instead of once per tap.
+    if (const char* e = getenv("CAGC_HALO_DEBUG")) p.debug = atoi(e);
+    p.row_mode = (c.n_cols > 80 && c.Wo >= 128 && c.Wo % 128 == 0) ? 1 : 0;
+    if (const char* e = getenv("CAGC_TC_HALO_ROWMODE")) p.row_mode = atoi(e) && c.Wo >= 128;
     double best = 0;
     int bestR = 0;
-    for (int R = 1; R <= std::min(c.Ho, 32); ++R) {
-        const int mt = ceil_div(R * p.Wt, kTileM);
-        if (mt > mt_max) break;
-        const int rows = std::max((R + dys) * p.Wt, mt * kTileM + dys * p.Wt + dxs);
-        const uint32_t a_stride = ((uint32_t)rows * 128u + 1023u) & ~1023u;
-        // the weight ring must be deep enough to cover the TMA round trip of its small per-tap stages
-        if (2 * (int64_t)a_stride + (int64_t)std::min(kHaloMaxB, c.ntaps) * p.b_bytes + 1024 > smem_budget) break;
-        const int ytiles = ceil_div(c.Ho, R);
-        // cost per useful output pixel: MMA rows + (weighted) operand rows, including the ragged last row tile
-        const double useful = (double)c.Ho * c.Wo;
-        const double mma = (double)ytiles * p.strips * mt * kTileM;
-        const double load = (double)ytiles * p.strips * (R + dys) * p.Wt;
-        const bool dbl = 2 * mt * p.n_tile <= 512;
-        const double score = useful / (mma * (dbl ? 1.0 : 1.15) + 0.5 * load);
-        if (score > best) { best = score; bestR = R; }
+    if (p.row_mode) {
+        p.TW = 128;
+        p.Wt = p.TW + dxs;
+        p.strips = ceil_div(c.Wo, p.TW);
+        for (int R = 1; R <= std::min(c.Ho, mt_max); ++R) {
+            const int rows = (R + dys) * p.Wt;
+            const uint32_t a_stride = ((uint32_t)rows * 128u + 1023u) & ~1023u;
+            if (2 * (int64_t)a_stride + (int64_t)b_min * p.b_bytes + 1024 > smem_budget) break;
+            const bool dbl = 2 * R * p.n_tile <= 512;
+            // operand bytes per output row (A rows + the weights of 9 taps shared by R rows), single-buffered
+            // accumulators pay an un-overlapped epilogue
+            const double bytes = ((double)(R + dys) * p.Wt * 128.0 + (double)c.ntaps * p.b_bytes) / R;
+            const double score = 1.0 / (bytes * (dbl ? 1.0 : 1.12));
+            if (score > best) { best = score; bestR = R; }
+        }
+        if (const char* e = getenv("CAGC_TC_HALO_R")) bestR = std::min(bestR ? mt_max : 0, atoi(e));
+        if (bestR <= 0) return 0;
+        p.R = bestR;
+        p.mt = p.R;
+        p.sub_rows = p.Wt;
+    } else {
+        p.TW = std::min(c.Wo, 64);
+        if (const char* e = getenv("CAGC_TC_HALO_TW")) p.TW = std::min(c.Wo, std::max(8, atoi(e)));
+        p.Wt = p.TW + dxs;
+        p.strips = ceil_div(c.Wo, p.TW);
+        // choose the tile height: best MMA-row / operand-byte efficiency that fits shared memory and TMEM
+        for (int R = 1; R <= std::min(c.Ho, 32); ++R) {
+            const int mt = ceil_div(R * p.Wt, kTileM);
+            if (mt > mt_max) break;
+            const int rows = std::max((R + dys) * p.Wt, mt * kTileM + dys * p.Wt + dxs);
+            const uint32_t a_stride = ((uint32_t)rows * 128u + 1023u) & ~1023u;
+            if (2 * (int64_t)a_stride + (int64_t)b_min * p.b_bytes + 1024 > smem_budget) break;
+            const int ytiles = ceil_div(c.Ho, R);
+            // cost per useful output pixel: MMA rows + (weighted) operand rows, including the ragged last row tile
+            const double useful = (double)c.Ho * c.Wo;
+            const double mma = (double)ytiles * p.strips * mt * kTileM;
+            const double load = (double)ytiles * p.strips * (R + dys) * p.Wt;
+            const bool dbl = 2 * mt * p.n_tile <= 512;
+            const double score = useful / (mma * (dbl ? 1.0 : 1.15) + 0.5 * load);
+            if (score > best) { best = score; bestR = R; }
+        }
+        if (const char* e = getenv("CAGC_TC_HALO_R")) bestR = std::min(bestR ? 32 : 0, atoi(e));
+        if (bestR <= 0) return 0;
+        p.R = bestR;
+        p.mt = ceil_div(p.R * p.Wt, kTileM);
+        p.sub_rows = kTileM;
     }
-    if (const char* e = getenv("CAGC_TC_HALO_R")) bestR = std::min(bestR ? 32 : 0, atoi(e));
-    if (bestR <= 0) return 0;
-    p.R = bestR;
-    p.mt = ceil_div(p.R * p.Wt, kTileM);
     if (p.mt > mt_max) return 0;
     p.rows_box = p.R + dys;
     p.ytiles = ceil_div(c.Ho, p.R);
     p.acc_bufs = (2 * p.mt * p.n_tile <= 512) ? 2 : 1;
     p.a_bytes = (uint32_t)p.rows_box * p.Wt * 128u;
-    const int rows = std::max(p.rows_box * p.Wt, p.mt * kTileM + dys * p.Wt + dxs);
+    const int rows = p.row_mode ? p.rows_box * p.Wt : std::max(p.rows_box * p.Wt, p.mt * kTileM + dys * p.Wt + dxs);
     p.a_stride = ((uint32_t)rows * 128u + 1023u) & ~1023u;
     const int64_t left = smem_budget - 1024 - 2 * (int64_t)p.a_stride;
     p.b_stages = (int)std::min<int64_t>(kHaloMaxB, left / p.b_bytes);
@@ -1726,6 +1843,10 @@ static int try_halo_conv(cudaStream_t stream, const ConvP& c, const char* what, 
     int max_slab = 0;
     for (int i = 0; i < c.ntaps; ++i) {
         p.tap_row[i] = (c.taps[i].dy - dymin) * p.Wt + (c.taps[i].dx - dxmin);
+        if (const char* e = getenv("CAGC_HALO_DEBUG_SHIFT")) {      // timing experiment only (wrong results)
+            const int m = atoi(e);
+            p.tap_row[i] = (m == 0) ? 0 : (p.tap_row[i] / m) * m;
+        }
         p.tap_slab[i] = c.taps[i].slab;
         max_slab = std::max(max_slab, c.taps[i].slab);
     }
@@ -1821,10 +1942,10 @@ int cagc_tc_conv(cudaStream_t stream, const ConvP& c, const char* what) {
     const uint32_t stage_bytes = (uint32_t)p.mt * kABytes + p.b_bytes;
     int tmem_need = 32;
     while (tmem_need < p.mt * p.n_tile) tmem_need <<= 1;
-    int budget = (tmem_need <= 256 && 2 * stage_bytes + 1024 <= (uint32_t)kSmemBudget) ? kSmemBudget : kSmemBudget1;
+    int budget = (tmem_need <= 256 && 2 * stage_bytes + 1024 <= (uint32_t)kConvBudget) ? kConvBudget : kConvBudget1;
     // grids smaller than the machine (4x4 .. 32x32 layers): one CTA per SM anyway, and the launch is bound by the
     // serial K loop's TMA latency -- give each CTA the whole shared memory for a deeper ring
-    if ((int64_t)ceil_div(p.tiles_total, p.mt) * ceil_div(p.n_rows, p.n_tile) <= kNumSMs) budget = kSmemBudget1;
+    if ((int64_t)ceil_div(p.tiles_total, p.mt) * ceil_div(p.n_rows, p.n_tile) <= kNumSMs) budget = kConvBudget1;
     p.stages = std::max(2, std::min(kMaxStages, (int)((budget - 1024) / stage_bytes)));
     const size_t smem = (size_t)p.stages * stage_bytes + 1024;
 
@@ -1860,9 +1981,9 @@ int cagc_tc_conv(cudaStream_t stream, const ConvP& c, const char* what) {
     }
     static DeviceOnce attr_set{0};
     if (device_once_needed(attr_set)) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget1);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvBudget1);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(conv_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget1);
+            e = cudaFuncSetAttribute(conv_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvBudget1);
         if (e != cudaSuccess) return fail((int)e, "%s: cudaFuncSetAttribute failed: %s", what, cudaGetErrorString(e));
         device_once_done(attr_set);
     }
@@ -1879,7 +2000,7 @@ int cagc_tc_conv(cudaStream_t stream, const ConvP& c, const char* what) {
         q.ph_Ho[0] = p.Ho; q.ph_Wo[0] = p.Wo; q.ph_oy[0] = p.out_oy; q.ph_ox[0] = p.out_ox;
         q.ph_tx[0] = p.tiles_x; q.ph_ty[0] = p.tiles_y; q.ph_tiles[0] = p.tiles_total;
         const uint32_t sb = (uint32_t)q.mt * kABytes + q.b_bytes;
-        q.stages = std::max(2, std::min(kMaxStages, (int)((kSmemBudget1 - 1024) / sb)));
+        q.stages = std::max(2, std::min(kMaxStages, (int)((kConvBudget1 - 1024) / sb)));
         const size_t smem_p = (size_t)q.stages * sb + 1024;
         const unsigned gridp = (unsigned)std::min<int64_t>(items, kNumSMs);
         conv_tc_persist_kernel<<<gridp, kThreads, smem_p, stream>>>(map_a, map_b, q);
@@ -1954,7 +2075,7 @@ int cagc_tc_conv_multi(cudaStream_t stream, const ConvP* ph, int nphase, const c
     p.ntaps = taps_total;
     if (items < 2 * kNumSMs || items > 0x7fffffff) return 0;   // tiny layers: the per-phase launches are latency-bound anyway
     const uint32_t sb = (uint32_t)p.mt * kABytes + p.b_bytes;
-    p.stages = std::max(2, std::min(kMaxStages, (int)((kSmemBudget1 - 1024) / sb)));
+    p.stages = std::max(2, std::min(kMaxStages, (int)((kConvBudget1 - 1024) / sb)));
     const size_t smem = (size_t)p.stages * sb + 1024;
     CUtensorMap map_a, map_b;
     {
@@ -1980,7 +2101,7 @@ int cagc_tc_conv_multi(cudaStream_t stream, const ConvP* ph, int nphase, const c
     }
     static DeviceOnce attr_set{0};
     if (device_once_needed(attr_set)) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget1);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvBudget1);
         if (e != cudaSuccess) { *rc = fail((int)e, "%s: cudaFuncSetAttribute failed: %s", what, cudaGetErrorString(e)); return 1; }
         device_once_done(attr_set);
     }

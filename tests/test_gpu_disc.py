@@ -53,7 +53,8 @@ def test_fir_resample_nhwc(up, down, pad, h, w, c):
 
 @pytest.mark.parametrize('algo', [0, 1])
 @pytest.mark.parametrize('cin,cout,k,mode,h', [(32, 48, 3, 0, 12), (64, 32, 1, 0, 9), (40, 64, 3, 1, 17), (128, 256, 3, 1, 33),
-                                               (520, 512, 3, 0, 4), (128, 128, 3, 0, 64)])
+                                               (520, 512, 3, 0, 4), (128, 128, 3, 0, 64), (128, 128, 3, 0, 128),
+                                               (96, 160, 3, 0, 256), (256, 256, 3, 0, 128)])
 def test_conv2d_modes_vs_torch(algo, cin, cout, k, mode, h):
     """cagc_conv2d (both engines) against F.conv2d in fp64: same-size and stride-2 convolutions, bias, activation
     gain, residual add after the activation."""
