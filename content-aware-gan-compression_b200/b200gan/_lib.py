@@ -16,7 +16,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), 'lib', 'libcagc_b200.so')
-ABI_VERSION = 15
+ABI_VERSION = 16
 
 _p = C.c_void_p
 _i = C.c_int
@@ -63,6 +63,8 @@ SIGNATURES = {
     'cagc_to_nhwc': (_i, [_p, _p, _l, _l, _l, _l, _p, _i, _i, _i, _i, _i]),
     'cagc_adam_step': (_i, [_p, _p, _p, _p, _p, _l, _f, _f, _f, _f, _f, _f, _f, _p]),
     'cagc_adam_ema_step': (_i, [_p, _p, _p, _p, _p, _l, _f, _f, _f, _f, _f, _f, _f, _p, _p, _f]),
+    'cagc_linear_fwd': (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _f, _f, _i, _f, _f]),
+    'cagc_linear_bwd': (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i]),
     'cagc_conv2d': (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i]),
     'cagc_fir_resample_nhwc': (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i]),
     'cagc_from_rgb_fwd': (_i, [_p, _p, _l, _l, _l, _l, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _i, _f]),

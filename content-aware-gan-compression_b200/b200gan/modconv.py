@@ -553,9 +553,12 @@ def style_affine(latent: torch.Tensor, mods, indices):
 
 
 # ------------------------------------------------------------------------------------------------
-# EqualLinear (model.py:137-171): library GEMM + ONE epilogue kernel (scale, bias*lr_mul, leaky ReLU)
+# EqualLinear (model.py:137-171): own skinny-GEMM kernels with the epilogue fused (csrc/linear.cu)
 # ------------------------------------------------------------------------------------------------
 class _EqualLinearFn(Function):
+    """y = [lrelu * sqrt2](scale * x W^T + bias * lr_mul), forward = ONE native launch (cagc_linear_fwd), backward =
+    activation/bias kernel + the two small products (cagc_linear_bwd); no library GEMM."""
+
     @staticmethod
     def forward(ctx, x, weight, bias, scale, lr_mul, act):
         require_cuda(x, 'EqualLinear')
@@ -564,13 +567,14 @@ class _EqualLinearFn(Function):
         if not x2.is_contiguous():
             x2 = x2.contiguous()
         w = weight.detach()
-        acc = torch.mm(x2, w.t())
-        m = acc.shape[0]
-        out = torch.empty_like(acc)
+        if not w.is_contiguous():
+            w = w.contiguous()
+        m = x2.shape[0]
+        out = torch.empty((m, n_out), device=x.device, dtype=torch.float32)
         bias_c = bias.detach().contiguous() if bias is not None else None
         with torch.cuda.device(x.device):
-            check(lib.cagc_linear_bias_act(stream_of(acc), acc.data_ptr(), ptr(bias_c), out.data_ptr(), m, n_out,
-                                           scale, lr_mul, int(act), 0.2, math.sqrt(2)), 'linear_bias_act')
+            check(lib.cagc_linear_fwd(stream_of(x2), x2.data_ptr(), w.data_ptr(), ptr(bias_c), out.data_ptr(), m, n_out,
+                                      n_in, scale, lr_mul, int(act), 0.2, math.sqrt(2)), 'linear_fwd')
         ctx.save_for_backward(x2, w, out if act else None)
         ctx.cfg = (scale, lr_mul, act, bias is not None, x.shape)
         return out.reshape(*x.shape[:-1], n_out)
@@ -586,13 +590,18 @@ class _EqualLinearFn(Function):
         g_acc = torch.empty_like(g2)
         g_bias = torch.empty((n_out,), device=g.device, dtype=torch.float32) \
             if (has_bias and ctx.needs_input_grad[2]) else None
+        need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        g_x = torch.empty((m, n_in), device=g.device, dtype=torch.float32) if need_x else None
+        g_w = torch.empty((n_out, n_in), device=g.device, dtype=torch.float32) if need_w else None
         with torch.cuda.device(g.device):
-            check(lib.cagc_linear_bias_act_bwd(stream_of(g2), g2.data_ptr(), ptr(out), g_acc.data_ptr(), ptr(g_bias),
+            st = stream_of(g2)
+            check(lib.cagc_linear_bias_act_bwd(st, g2.data_ptr(), ptr(out), g_acc.data_ptr(), ptr(g_bias),
                                                m, n_out, scale, lr_mul, int(act), 0.2, math.sqrt(2)),
                   'linear_bias_act_bwd')
-        g_x = torch.mm(g_acc, w).reshape(xshape) if ctx.needs_input_grad[0] else None
-        g_w = torch.mm(g_acc.t(), x2) if ctx.needs_input_grad[1] else None
-        return g_x, g_w, g_bias, None, None, None
+            if need_x or need_w:
+                check(lib.cagc_linear_bwd(st, g_acc.data_ptr(), x2.data_ptr(), w.data_ptr(), ptr(g_x), ptr(g_w), m, n_out,
+                                          n_in), 'linear_bwd')
+        return (g_x.reshape(xshape) if need_x else None), g_w, g_bias, None, None, None
 
 
 def equal_linear(x, weight, bias, scale, lr_mul, act):

@@ -34,10 +34,10 @@ constexpr int kSmemBudget = 110 * 1024;          // two CTAs per SM (weight-grad
 constexpr int kSmemBudget1 = 220 * 1024;         // one CTA per SM
 // convolution kernels: 16 KB of static shared memory per CTA belong to the epilogue's transpose staging
 constexpr int kEpiStageBytes = 4 * 32 * 32 * 4;
-constexpr int kConvBudget = kSmemBudget - kEpiStageBytes;     // two CTAs per SM
 constexpr int kConvBudget1 = kSmemBudget1 - kEpiStageBytes;   // one CTA per SM (two M sub-tiles, > 256 TMEM columns)
 
 struct TcParams {
+    uint32_t epi_off;           // byte offset of the epilogue staging tiles inside dynamic smem (transposing epilogue only)
     const float* out_scale;
     const float* noise;
     const float* noise_w;
@@ -192,43 +192,102 @@ __device__ __forceinline__ void epi_chunk(const EpiArgs& e, float* st, uint32_t 
     const bool uniform_b = __all_sync(0xffffffffu, rb == b0 || !rvalid);
     float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f);
     if (e.out_scale && uniform_b && cvalid) s4 = ldg4(e.out_scale + (int64_t)b0 * e.n_pitch + cn);
+    // pass 1: row descriptors through shuffles, and ALL residual loads of the chunk in flight at once (the stores
+    // of pass 2 may alias e.residual as far as the compiler knows, so loads issued inside pass 2 would each expose a
+    // full HBM round trip: measured 2x on the residual-carrying 1x1 / data-gradient convolutions)
+    int64_t offs[NSEG];
+    float nzs[NSEG];
+    int bs[NSEG];
+    bool oks[NSEG];
+    float4 rs[NSEG];
 #pragma unroll
     for (int i = 0; i < NSEG; ++i) {
         const int row = i * RI + rsub;
         const bool valid = __shfl_sync(0xffffffffu, (int)rvalid, row) != 0;
         const int off_lo = __shfl_sync(0xffffffffu, (int)(uint32_t)(roff & 0xffffffffll), row);
         const int off_hi = __shfl_sync(0xffffffffu, (int)(roff >> 32), row);
-        const float nz = e.has_noise ? __shfl_sync(0xffffffffu, rnz, row) : 0.f;
-        const int b = uniform_b ? b0 : __shfl_sync(0xffffffffu, rb, row);
-        if (!valid || !cvalid) continue;
-        const int64_t off = ((int64_t)off_hi << 32) | (uint32_t)off_lo;
+        nzs[i] = e.has_noise ? __shfl_sync(0xffffffffu, rnz, row) : 0.f;
+        bs[i] = uniform_b ? b0 : __shfl_sync(0xffffffffu, rb, row);
+        oks[i] = valid && cvalid;
+        offs[i] = ((int64_t)off_hi << 32) | (uint32_t)off_lo;
+        rs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e.residual && oks[i]) rs[i] = ldg4(e.residual + offs[i] + cn);
+    }
+#pragma unroll
+    for (int i = 0; i < NSEG; ++i) {
+        if (!oks[i]) continue;
+        const int row = i * RI + rsub;
         const float4 x = ld4(st + (row * NSEG + (seg ^ (row & (NSEG - 1)))) * 4);
         float o[4] = {x.x, x.y, x.z, x.w};
         if (e.out_scale) {
-            const float4 sc = uniform_b ? s4 : ldg4(e.out_scale + (int64_t)b * e.n_pitch + cn);
+            const float4 sc = uniform_b ? s4 : ldg4(e.out_scale + (int64_t)bs[i] * e.n_pitch + cn);
             o[0] *= sc.x; o[1] *= sc.y; o[2] *= sc.z; o[3] *= sc.w;
         }
-        if (e.has_noise) { o[0] += nz; o[1] += nz; o[2] += nz; o[3] += nz; }
+        if (e.has_noise) { o[0] += nzs[i]; o[1] += nzs[i]; o[2] += nzs[i]; o[3] += nzs[i]; }
         if (e.bias) { o[0] += b4.x; o[1] += b4.y; o[2] += b4.z; o[3] += b4.w; }
         if (e.act) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) o[j] = lrelu_gain(o[j], e.act_gain);
         }
-        if (e.residual) {
-            const float4 r4 = ldg4(e.residual + off + cn);
-            o[0] += r4.x; o[1] += r4.y; o[2] += r4.z; o[3] += r4.w;
-        }
+        if (e.residual) { o[0] += rs[i].x; o[1] += rs[i].y; o[2] += rs[i].z; o[3] += rs[i].w; }
 #pragma unroll
         for (int j = 0; j < 4; ++j)
             if (cn + j >= e.out_valid) o[j] = 0.f;
-        st4(e.out + off + cn, make_float4(o[0], o[1], o[2], o[3]));
+        st4(e.out + offs[i] + cn, make_float4(o[0], o[1], o[2], o[3]));
     }
     __syncwarp();          // the staging tile is rewritten by the next chunk
+}
+
+constexpr int kEpiTransposeMinN = 128;
+// Narrow layers (N < 128: the 39 / 77-channel student layers and their up-conv phases): a pixel's whole channel vector is only 160-320 bytes, the
+// per-lane row layout already writes it as a few adjacent 16-byte stores, and the transposing form's extra
+// shuffles / shared-memory round trip cost more issue slots than they save (measured: 39ch@256^2 222 -> 287 us, 154->77 up-conv 135 -> 165 us; 128ch@256^2 674 -> 506 us the other way).
+__device__ __forceinline__ void epi_rows_direct(const EpiArgs& e, uint32_t taddr, int n0, int n_mma, bool rvalid, int64_t roff,
+                                                float rnz, int rb) {
+    float* dst = e.out + roff;
+    const float* res = e.residual ? e.residual + roff : nullptr;
+    const float* sc = e.out_scale ? e.out_scale + (int64_t)rb * e.n_pitch : nullptr;
+    for (int c = 0; c < n_mma; c += 16) {
+        float v[16];
+        tc_ld16(taddr + (uint32_t)c, v);   // warp-collective
+        if (!rvalid) continue;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const int n = n0 + c + g * 4;
+            if (n >= e.n_pitch) break;
+            float o[4] = {v[g * 4 + 0], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]};
+            if (sc) {
+                const float4 s4 = ldg4(sc + n);
+                o[0] *= s4.x; o[1] *= s4.y; o[2] *= s4.z; o[3] *= s4.w;
+            }
+            if (e.has_noise) { o[0] += rnz; o[1] += rnz; o[2] += rnz; o[3] += rnz; }
+            if (e.bias) {
+                const float4 b4 = ldg4(e.bias + n);
+                o[0] += b4.x; o[1] += b4.y; o[2] += b4.z; o[3] += b4.w;
+            }
+            if (e.act) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) o[j] = lrelu_gain(o[j], e.act_gain);
+            }
+            if (res) {
+                const float4 r4 = ldg4(res + n);
+                o[0] += r4.x; o[1] += r4.y; o[2] += r4.z; o[3] += r4.w;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (n + j >= e.out_valid) o[j] = 0.f;
+            st4(dst + n, make_float4(o[0], o[1], o[2], o[3]));
+        }
+    }
 }
 
 // all column chunks of one 128-row sub-tile for this warp's 32 rows
 __device__ __forceinline__ void epi_rows(const EpiArgs& e, float* st, uint32_t taddr, int lane, int n0, int n_mma, bool rvalid,
                                          int64_t roff, float rnz, int rb) {
+    if (n_mma < kEpiTransposeMinN || st == nullptr) {
+        epi_rows_direct(e, taddr, n0, n_mma, rvalid, roff, rnz, rb);
+        return;
+    }
     int c = 0;
     for (; c + 32 <= n_mma; c += 32) epi_chunk<32>(e, st, taddr + (uint32_t)c, lane, n0 + c, rvalid, roff, rnz, rb);
     if (c < n_mma) epi_chunk<16>(e, st, taddr + (uint32_t)c, lane, n0 + c, rvalid, roff, rnz, rb);
@@ -339,12 +398,13 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
 __global__ void __launch_bounds__(kThreads, 2)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(16) float epi_stage[4][32 * 32];
     __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 1];
     __shared__ uint32_t tmem_base_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    float* const epi_stage_base = (p.epi_off == 0xffffffffu) ? nullptr
+        : reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + p.epi_off);
     const int S = p.stages;
     const int MT = p.mt;
     const uint32_t stage_bytes = (uint32_t)MT * kABytes + p.b_bytes;
@@ -458,7 +518,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (p.noise && pvalid)
             nz = __ldg(p.noise_w) * __ldg(p.noise + (int64_t)b * p.noise_bstride + (int64_t)yy * p.Wout + xx);
         const int64_t roff = (((int64_t)b * p.Hout + yy) * p.Wout + xx) * p.n_pitch;
-        epi_rows(ea, epi_stage[q], tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * n_mma), lane, n0, n_mma, pvalid,
+        epi_rows(ea, (epi_stage_base ? epi_stage_base + q * 1024 : nullptr), tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * n_mma), lane, n0, n_mma, pvalid,
                  roff, nz, b);
       }
     }
@@ -486,12 +546,13 @@ __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                        const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(16) float epi_stage[4][32 * 32];
     __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 4];
     __shared__ uint32_t tmem_base_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    float* const epi_stage_base = (p.epi_off == 0xffffffffu) ? nullptr
+        : reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + p.epi_off);
     const int S = p.stages, MT = p.mt;
     const uint32_t stage_bytes = (uint32_t)MT * kABytes + p.b_bytes;
     // stage s: [MT A tiles of 16 KB][B tile] at smem_base + s * stage_bytes
@@ -652,7 +713,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                 const int yy = oy * p.out_stride + p.ph_oy[f], xx = ox * p.out_stride + p.ph_ox[f];
                 const float nz = nzs[j];
                 const int64_t roff = (((int64_t)b * p.Hout + yy) * p.Wout + xx) * p.n_pitch;
-                epi_rows(ea, epi_stage[q], d0 + (uint32_t)(j * p.n_tile), lane, n0, n_mma, pvalid, roff, nz, b);
+                epi_rows(ea, (epi_stage_base ? epi_stage_base + q * 1024 : nullptr), d0 + (uint32_t)(j * p.n_tile), lane, n0, n_mma, pvalid, roff, nz, b);
             }
             // this warp has finished reading the accumulator buffer: hand it back to the MMA warp
             tc_fence_before();
@@ -684,6 +745,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
 // double buffered when 2*MT*N <= 512 columns.  Warp roles as above.
 // ================================================================================================
 struct HaloParams {
+    uint32_t epi_off;           // byte offset of the epilogue staging tiles inside dynamic smem (transposing epilogue only)
     const float* out_scale;
     const float* noise;
     const float* noise_w;
@@ -696,7 +758,6 @@ struct HaloParams {
     int dx_min, dy_min;
     int strips, ytiles;             // tiles per sample
     int mt;                         // 128-row M sub-tiles per tile: ceil(R*Wt / 128) (raster mode) or R (row mode)
-    int debug;                      // timing experiments only: bit0 skip epilogue work, bit1 skip MMA issue
     int row_mode;                   // 1: sub-tile j = output row j of the tile (TW <= 128 pixels, no halo columns in M)
     int sub_rows;                   // raster rows between consecutive sub-tiles: 128 (raster mode) or Wt (row mode)
     int k_valid, n_pitch, out_valid, n_tile, n_rows;
@@ -714,12 +775,13 @@ __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const __grid_constant__ HaloParams p) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(16) float epi_stage[4][32 * 32];
     __shared__ __align__(8) uint64_t bars[2 * kHaloMaxB + 8];
     __shared__ uint32_t tmem_base_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    float* const epi_stage_base = (p.epi_off == 0xffffffffu) ? nullptr
+        : reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + p.epi_off);
     const uint32_t b_base = smem_base + 2u * p.a_stride;
     const int SB = p.b_stages, MT = p.mt;
     const uint32_t bar0 = smem_u32(bars);
@@ -830,20 +892,22 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     mbar_wait(bf, ph);
                     tc_fence_after();
                     const uint32_t a_lo = a_buf_lo + (uint32_t)p.tap_row[tap] * 8u;      // 128-byte rows, >> 4
-                    {
+                    // (measured A/B on one box: in this kernel the divergent elect_one() region issues faster than the
+                    //  in-asm election that the persistent kernel uses -- 39ch@256^2 229 vs 264 us)
+                    if (elect_one()) {
                         uint32_t d = d0, a = a_lo;
-                        const bool fresh = (kc == 0) && (tap == 0);
                         for (int j = 0; j < MT; ++j) {          // next sub-tile: +sub_rows raster rows
-                            if (!(p.debug & 2)) mma_stage_k_uniform(d, a, b_lo, idesc, kk, fresh);
+                            mma_stage_k(d, a, b_lo, idesc, kk, kc == 0 && tap == 0);
                             d += n_tile;
                             a += sub_step;
                         }
-                        tc_commit_elect(bf + 8u * kHaloMaxB);
+                        tc_commit(bf + 8u * kHaloMaxB);
                         if (tap == ntaps - 1) {
-                            tc_commit_elect(aempty(ab));
-                            if (kc == nk - 1) tc_commit_elect(tfull(acc));
+                            tc_commit(aempty(ab));
+                            if (kc == nk - 1) tc_commit(tfull(acc));
                         }
                     }
+                    __syncwarp();
                     if (++s == SB) { s = 0; ph ^= 1u; b_lo = b_lo0; bf = bar0; }
                     else { b_lo += b_step; bf += 8u; }
                 }
@@ -889,7 +953,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 const int yy = oy * p.out_stride + p.out_oy, xx = ox * p.out_stride + p.out_ox;
                 const float nz = nzs[j];
                 const int64_t roff = (((int64_t)b * p.Hout + yy) * p.Wout + xx) * p.n_pitch;
-                if (!(p.debug & 1)) epi_rows(ea, epi_stage[q], d0 + (uint32_t)(j * p.n_tile), lane, n0, n_mma, pvalid, roff, nz, b);
+                epi_rows(ea, (epi_stage_base ? epi_stage_base + q * 1024 : nullptr), d0 + (uint32_t)(j * p.n_tile), lane, n0, n_mma, pvalid, roff, nz, b);
             }
             tc_fence_before();
             __syncwarp();
@@ -1764,14 +1828,14 @@ static int try_halo_conv(cudaStream_t stream, const ConvP& c, const char* what, 
     const int n_tiles = ceil_div(p.n_rows, p.n_tile);
     const int mt_max = std::min(8, 512 / p.n_tile);
     p.b_bytes = (uint32_t)p.n_tile * kChunkK * 4;
-    const int smem_budget = 222 * 1024 - kEpiStageBytes;
+    const int epi_bytes = (p.n_tile >= 128) ? kEpiStageBytes : 0;      // staging tiles of the transposing epilogue
+    const int smem_budget = 222 * 1024 - epi_bytes;
     // the weight ring must cover the TMA round trip of its per-tap stages: 8 small stages for narrow N, at least 4
     // of the large (>= 16 KB) stages of wide N
     const int b_min = (p.b_bytes >= 32768) ? 3 : (p.b_bytes >= 16384) ? 4 : std::min(kHaloMaxB, c.ntaps);
     // Row mode (wide layers, W >= 128): a tile is R full 128-pixel output rows; sub-tile j is output row j, its taps
     // are the R+dys input rows of the window shifted by dx -- no halo column ever enters the M dimension, weights are
     // shared by the R rows, every input row is loaded once per 32-channel chunk instead of once per tap.
-    if (const char* e = getenv("CAGC_HALO_DEBUG")) p.debug = atoi(e);
     p.row_mode = (c.n_cols > 80 && c.Wo >= 128 && c.Wo % 128 == 0) ? 1 : 0;
     if (const char* e = getenv("CAGC_TC_HALO_ROWMODE")) p.row_mode = atoi(e) && c.Wo >= 128;
     double best = 0;
@@ -1843,10 +1907,6 @@ static int try_halo_conv(cudaStream_t stream, const ConvP& c, const char* what, 
     int max_slab = 0;
     for (int i = 0; i < c.ntaps; ++i) {
         p.tap_row[i] = (c.taps[i].dy - dymin) * p.Wt + (c.taps[i].dx - dxmin);
-        if (const char* e = getenv("CAGC_HALO_DEBUG_SHIFT")) {      // timing experiment only (wrong results)
-            const int m = atoi(e);
-            p.tap_row[i] = (m == 0) ? 0 : (p.tap_row[i] / m) * m;
-        }
         p.tap_slab[i] = c.taps[i].slab;
         max_slab = std::max(max_slab, c.taps[i].slab);
     }
@@ -1875,11 +1935,12 @@ static int try_halo_conv(cudaStream_t stream, const ConvP& c, const char* what, 
     }
     static DeviceOnce attr_set{0};
     if (device_once_needed(attr_set)) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_budget);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024);
         if (e != cudaSuccess) { *rc = fail((int)e, "%s: cudaFuncSetAttribute failed: %s", what, cudaGetErrorString(e)); return 1; }
         device_once_done(attr_set);
     }
-    const size_t smem = 2 * (size_t)p.a_stride + (size_t)p.b_stages * p.b_bytes + 1024;
+    p.epi_off = 2u * p.a_stride + (uint32_t)p.b_stages * p.b_bytes;
+    const size_t smem = 2 * (size_t)p.a_stride + (size_t)p.b_stages * p.b_bytes + 1024 + epi_bytes;
     const int64_t items = (int64_t)p.strips * p.ytiles * c.B * n_tiles;
     const unsigned grid = (unsigned)std::min<int64_t>(items, kNumSMs);
     conv_tc_halo_kernel<<<grid, kThreads, smem, stream>>>(map_a, map_b, p);
@@ -1942,12 +2003,19 @@ int cagc_tc_conv(cudaStream_t stream, const ConvP& c, const char* what) {
     const uint32_t stage_bytes = (uint32_t)p.mt * kABytes + p.b_bytes;
     int tmem_need = 32;
     while (tmem_need < p.mt * p.n_tile) tmem_need <<= 1;
-    int budget = (tmem_need <= 256 && 2 * stage_bytes + 1024 <= (uint32_t)kConvBudget) ? kConvBudget : kConvBudget1;
+    // two CTAs per SM (110 KB each) when two stages fit; the transposing epilogue's staging tiles are dropped there if
+    // they do not fit beside the ring (n_tile = 256: 2 x 48 KB stages) -- the second CTA hides the epilogue instead
+    const bool two_ctas = tmem_need <= 256 && 2 * stage_bytes + 1024 <= (uint32_t)kSmemBudget;
+    const bool stage_fits = !two_ctas || 2 * stage_bytes + 1024 + kEpiStageBytes <= (uint32_t)kSmemBudget;
+    int budget = two_ctas ? (stage_fits ? kSmemBudget - kEpiStageBytes : kSmemBudget) : kConvBudget1;
     // grids smaller than the machine (4x4 .. 32x32 layers): one CTA per SM anyway, and the launch is bound by the
     // serial K loop's TMA latency -- give each CTA the whole shared memory for a deeper ring
     if ((int64_t)ceil_div(p.tiles_total, p.mt) * ceil_div(p.n_rows, p.n_tile) <= kNumSMs) budget = kConvBudget1;
     p.stages = std::max(2, std::min(kMaxStages, (int)((budget - 1024) / stage_bytes)));
-    const size_t smem = (size_t)p.stages * stage_bytes + 1024;
+    bool with_stage = stage_fits;
+    if ((int64_t)ceil_div(p.tiles_total, p.mt) * ceil_div(p.n_rows, p.n_tile) <= kNumSMs) with_stage = true;   // one CTA per SM
+    p.epi_off = with_stage ? (uint32_t)p.stages * stage_bytes : 0xffffffffu;
+    const size_t smem = (size_t)p.stages * stage_bytes + 1024 + (with_stage ? kEpiStageBytes : 0);
 
     // A: activations [B, Hin, Win, in_pitch] fp32, box (32 ch, bw, bh, bb), 128-byte swizzle, OOB -> 0
     CUtensorMap map_a, map_b;
@@ -1981,9 +2049,9 @@ int cagc_tc_conv(cudaStream_t stream, const ConvP& c, const char* what) {
     }
     static DeviceOnce attr_set{0};
     if (device_once_needed(attr_set)) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvBudget1);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget1);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(conv_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvBudget1);
+            e = cudaFuncSetAttribute(conv_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget1);
         if (e != cudaSuccess) return fail((int)e, "%s: cudaFuncSetAttribute failed: %s", what, cudaGetErrorString(e));
         device_once_done(attr_set);
     }
@@ -2001,7 +2069,8 @@ int cagc_tc_conv(cudaStream_t stream, const ConvP& c, const char* what) {
         q.ph_tx[0] = p.tiles_x; q.ph_ty[0] = p.tiles_y; q.ph_tiles[0] = p.tiles_total;
         const uint32_t sb = (uint32_t)q.mt * kABytes + q.b_bytes;
         q.stages = std::max(2, std::min(kMaxStages, (int)((kConvBudget1 - 1024) / sb)));
-        const size_t smem_p = (size_t)q.stages * sb + 1024;
+        q.epi_off = (uint32_t)q.stages * sb;
+        const size_t smem_p = (size_t)q.stages * sb + 1024 + kEpiStageBytes;
         const unsigned gridp = (unsigned)std::min<int64_t>(items, kNumSMs);
         conv_tc_persist_kernel<<<gridp, kThreads, smem_p, stream>>>(map_a, map_b, q);
         return launched(what);
@@ -2076,7 +2145,8 @@ int cagc_tc_conv_multi(cudaStream_t stream, const ConvP* ph, int nphase, const c
     if (items < 2 * kNumSMs || items > 0x7fffffff) return 0;   // tiny layers: the per-phase launches are latency-bound anyway
     const uint32_t sb = (uint32_t)p.mt * kABytes + p.b_bytes;
     p.stages = std::max(2, std::min(kMaxStages, (int)((kConvBudget1 - 1024) / sb)));
-    const size_t smem = (size_t)p.stages * sb + 1024;
+    p.epi_off = (uint32_t)p.stages * sb;
+    const size_t smem = (size_t)p.stages * sb + 1024 + kEpiStageBytes;
     CUtensorMap map_a, map_b;
     {
         cuuint64_t dims[4] = {(cuuint64_t)c.in_pitch, (cuuint64_t)c.Win, (cuuint64_t)c.Hin, (cuuint64_t)c.B};
@@ -2101,7 +2171,7 @@ int cagc_tc_conv_multi(cudaStream_t stream, const ConvP* ph, int nphase, const c
     }
     static DeviceOnce attr_set{0};
     if (device_once_needed(attr_set)) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvBudget1);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget1);
         if (e != cudaSuccess) { *rc = fail((int)e, "%s: cudaFuncSetAttribute failed: %s", what, cudaGetErrorString(e)); return 1; }
         device_once_done(attr_set);
     }

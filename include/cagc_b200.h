@@ -37,7 +37,7 @@ typedef void* cagc_stream_t; /* cudaStream_t */
 #define CAGC_E_UNSUPPORTED (-2) /* shape outside what the kernels implement */
 
 /* bump when a signature changes; the Python loader checks it */
-#define CAGC_ABI_VERSION 15
+#define CAGC_ABI_VERSION 16
 
 int cagc_abi_version(void);
 const char* cagc_last_error(void);
@@ -313,6 +313,17 @@ int cagc_from_rgb_fwd(cagc_stream_t stream, const float* img, int64_t sb, int64_
 int cagc_from_rgb_bwd(cagc_stream_t stream, const float* g, const float* yact, const float* w, float* gimg, int B,
                       int H, int W, int cin, int cout, int pitch, float wscale, int act, float gain);
 int cagc_act_mask_nhwc(cagc_stream_t stream, const float* g, const float* y, float* out, int64_t n, float gain);
+
+/* ----------------------------------------------------------------------
+ * EqualLinear (reference model.py:137-166: F.linear(x, W * scale) + fused_leaky_relu(bias * lr_mul)) as one launch:
+ *   out[M,N] = act(acc_scale * x[M,K] W[N,K]^T + bias[N] * bias_scale) (* gain when act != 0, leaky slope alpha)
+ * cagc_linear_bwd: g_x[M,K] = g_acc[M,N] W (nullable), g_w[N,K] = g_acc^T x (nullable); g_acc is the output of
+ * cagc_linear_bias_act_bwd (activation mask and acc_scale already applied).  Fixed summation order.
+ * ---------------------------------------------------------------------- */
+int cagc_linear_fwd(cagc_stream_t stream, const float* x, const float* w, const float* bias, float* out, int M, int N,
+                    int K, float acc_scale, float bias_scale, int act, float alpha, float gain);
+int cagc_linear_bwd(cagc_stream_t stream, const float* g_acc, const float* x, const float* w, float* g_x, float* g_w,
+                    int M, int N, int K);
 
 #ifdef __cplusplus
 }
