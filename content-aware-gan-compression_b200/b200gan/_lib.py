@@ -16,7 +16,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), 'lib', 'libcagc_b200.so')
-ABI_VERSION = 16
+ABI_VERSION = 17
 
 _p = C.c_void_p
 _i = C.c_int
@@ -70,6 +70,7 @@ SIGNATURES = {
     'cagc_from_rgb_fwd': (_i, [_p, _p, _l, _l, _l, _l, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _i, _f]),
     'cagc_from_rgb_bwd': (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _i, _f]),
     'cagc_act_mask_nhwc': (_i, [_p, _p, _p, _p, _l, _f]),
+    'cagc_fir_nhwc_mask': (_i, [_p, _p, _p, _p, _p, _f, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i]),
 }
 
 

@@ -150,16 +150,22 @@ class _ResBlockFn(Function):
                    lambda: check(lib.cagc_conv_up(st, gz2.data_ptr(), p2.w_dgrad.data_ptr(), None, gt.data_ptr(), b, ho, wo,
                                                   pout, pin, 3, algo2), 'resblock.conv2^T'))
             del gz2
-            ga1 = _empty(b, h, w, pin, dev)
             q0, q1 = 4 - pad2[0] - 1, h - ht + pad2[0]
-            _timed('fir_nhwc', 0.0, 4.0 * b * cin * (h * w + ht * wt),
-                   lambda: fir_nhwc(st, gt.data_ptr(), _flipped(fir2), None, None, None, None, ga1.data_ptr(), b, ht, wt,
-                                    pin, pin, (q0, q1, q0, q1), 0, 0, 'resblock.blur^T'))
+            firf = _flipped(fir2)
+            gz1 = _empty(b, h, w, pin, dev)
+            # Blur^T and the backward of conv1's activation in ONE pass (mask from the sign of a1, gain sqrt2)
+            rc = _timed('fir_nhwc', 0.0, 4.0 * b * cin * (2 * h * w + ht * wt),
+                        lambda: lib.cagc_fir_nhwc_mask(st, gt.data_ptr(), firf.data_ptr(), _taps(firf), a1.data_ptr(), SQRT2,
+                                                       gz1.data_ptr(), b, ht, wt, pin, pin, 4, 4, q0, q1, q0, q1))
+            if rc != 0:        # shape outside the row-ring kernel: two passes
+                ga1 = _empty(b, h, w, pin, dev)
+                _timed('fir_nhwc', 0.0, 4.0 * b * cin * (h * w + ht * wt),
+                       lambda: fir_nhwc(st, gt.data_ptr(), firf, None, None, None, None, ga1.data_ptr(), b, ht, wt,
+                                        pin, pin, (q0, q1, q0, q1), 0, 0, 'resblock.blur^T'))
+                check(lib.cagc_act_mask_nhwc(st, ga1.data_ptr(), a1.data_ptr(), gz1.data_ptr(), gz1.numel(), SQRT2),
+                      'resblock.act1^T')
+                del ga1
             del gt
-            gz1 = torch.empty_like(ga1)
-            check(lib.cagc_act_mask_nhwc(st, ga1.data_ptr(), a1.data_ptr(), gz1.data_ptr(), gz1.numel(), SQRT2),
-                  'resblock.act1^T')
-            del ga1
             gx = _empty(b, h, w, pin, dev)
             _conv(st, gz1, p1.w_dgrad, None, gxs, gx, b, h, w, pin, pin, cin, 3, 0, False, 1.0, tc1d, 'resblock.conv1^T')
         return (nhwc_view(gx, cin),) + (None,) * 13

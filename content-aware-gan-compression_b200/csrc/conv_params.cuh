@@ -47,4 +47,4 @@ int cagc_tc_wgrad(cudaStream_t stream, const float* a, const float* g, float* pa
 int cagc_tc_fir_nhwc(cudaStream_t stream, const float* in, const float* fir, const float* out_scale, const float* noise,
                      const float* noise_w, const float* bias, float* out, int B, int in_h, int in_w, int out_h, int out_w,
                      int pitch, int valid, int pad_x0, int pad_y0, int64_t noise_bstride, int act, const float* taps_host,
-                     int* rc);
+                     int* rc, const float* mask_ref = nullptr, float mask_gain = 1.f);

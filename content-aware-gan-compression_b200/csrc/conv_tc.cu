@@ -1482,6 +1482,8 @@ struct FirSP {
     const float* noise_w;
     const float* bias;
     float* out;
+    const float* mask_ref;       // optional, layout of out: v *= mask_ref > 0 ? mask_gain : 0.2 * mask_gain (activation backward)
+    float mask_gain;
     int out_h, out_w, pitch, valid, pad_x0, pad_y0, act;
     int64_t noise_bstride;
     int main_w, main_tx;         // channel width of a main chunk and its pixel strip (main_w * main_tx == PXT * 1024)
@@ -1620,6 +1622,15 @@ __global__ void __launch_bounds__(256, 2) fir_nhwc_stream_kernel(const __grid_co
                 if (ok[pp]) nz[pp] = __ldg(nptr + pp);
             nptr += p.out_w;
         }
+        // activation-mask reference of the same output row (fused FusedLeakyReLU backward): requested here as well
+        float4 mr[PXT];
+#pragma unroll
+        for (int pp = 0; pp < PXT; ++pp) mr[pp] = make_float4(1.f, 1.f, 1.f, 1.f);
+        if ((!FIRST || Q == KH - 1) && p.mask_ref) {
+#pragma unroll
+            for (int pp = 0; pp < PXT; ++pp)
+                if (ok[pp]) mr[pp] = ldg4(p.mask_ref + (optr - p.out) + (int64_t)pp * p.pitch);
+        }
         mbar_wait(full_bar(s), ph);
         const float* src = sbase + s * sstride;
         float4 win[PXT + KW - 1];
@@ -1651,6 +1662,12 @@ __global__ void __launch_bounds__(256, 2) fir_nhwc_stream_kernel(const __grid_co
                 if (p.act) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], kLreluSlope * v[j]);
+                }
+                if (p.mask_ref) {
+                    v[0] *= mr[pp].x > 0.f ? p.mask_gain : p.mask_gain * kLreluSlope;
+                    v[1] *= mr[pp].y > 0.f ? p.mask_gain : p.mask_gain * kLreluSlope;
+                    v[2] *= mr[pp].z > 0.f ? p.mask_gain : p.mask_gain * kLreluSlope;
+                    v[3] *= mr[pp].w > 0.f ? p.mask_gain : p.mask_gain * kLreluSlope;
                 }
                 if (edge) {
 #pragma unroll
@@ -2369,12 +2386,13 @@ int cagc_tc_wgrad(cudaStream_t stream, const float* a, const float* g, float* pa
 int cagc_tc_fir_nhwc(cudaStream_t stream, const float* in, const float* fir, const float* out_scale, const float* noise,
                      const float* noise_w, const float* bias, float* out, int B, int in_h, int in_w, int out_h, int out_w,
                      int pitch, int valid, int pad_x0, int pad_y0, int64_t noise_bstride, int act, const float* taps_host,
-                     int* rc) {
+                     int* rc, const float* mask_ref, float mask_gain) {
     using namespace cagc::tc;
     *rc = 0;
     if (pitch % 4 != 0 || B > 65535) return 0;
     const char* impl = getenv("CAGC_FIR_IMPL");          // tuning knobs (development)
     const bool use_ldg = (impl && impl[0] == 'l') || pitch % 8 != 0;
+    if (use_ldg && mask_ref) return 0;      // the fused activation mask lives in the TMA row-ring kernel only
     auto pick_segs = [&](int64_t per_seg, int min_rows) {
         // enough CTAs for ~4 waves of 2 CTAs per SM, but at least `min_rows` output rows per segment (3 halo rows each)
         int want = 8 * kNumSMs;
@@ -2402,6 +2420,7 @@ int cagc_tc_fir_nhwc(cudaStream_t stream, const float* in, const float* fir, con
     p.fir = fir; p.out_scale = out_scale; p.noise = noise; p.noise_w = noise_w; p.bias = bias; p.out = out;
     p.out_h = out_h; p.out_w = out_w; p.pitch = pitch; p.valid = valid;
     p.pad_x0 = pad_x0; p.pad_y0 = pad_y0; p.act = act; p.noise_bstride = noise_bstride;
+    p.mask_ref = mask_ref; p.mask_gain = mask_gain;
     constexpr int PXT = 2;
     // chunk width: the widest of 128 / 64 / 32 channels that divides the pitch (measured: +5..40% on 256..512
     // channel tensors, longer contiguous runs per TMA row); ragged pitches use 32 + a tail chunk

@@ -11,6 +11,8 @@
 //                       y = lrelu(W x + b) * sqrt2 written straight to NHWC; backward produces the image
 //                       gradient from (g, y) in one pass (activation mask from the sign of y)
 //   act_mask_nhwc       gz = g * gain * (y > 0 ? 1 : 0.2)   (fused_bias_act_kernel.cu:43 semantics, no bias)
+#include <algorithm>
+
 #include "conv_params.cuh"
 
 namespace cagc {
@@ -26,17 +28,18 @@ struct FirRsP {
 // tap is a fully coalesced row segment; the overlapping 4x4 windows of neighbouring outputs hit L1/L2.
 template <int UP, int DOWN>
 __global__ void __launch_bounds__(256) fir_resample_nhwc_kernel(const __grid_constant__ FirRsP p) {
+    // blockIdx.y = (b, oy) output row; threads walk (ox, c4) of that row: no 64-bit divisions, one 32-bit division
     const int c4n = p.pitch >> 2;
-    const int64_t total = (int64_t)p.B * p.out_h * p.out_w * c4n;
-    for (int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * 256) {
-        const int c4 = (int)(idx % c4n);
-        int64_t t = idx / c4n;
-        const int ox = (int)(t % p.out_w);
-        t /= p.out_w;
-        const int oy = (int)(t % p.out_h);
-        const int b = (int)(t / p.out_h);
-        const float* src = p.in + (int64_t)b * p.in_h * p.in_w * p.pitch + c4 * 4;
-        const int ay0 = oy * DOWN - p.pad_y0, ax0 = ox * DOWN - p.pad_x0;
+    const int row = blockIdx.y;
+    const int b = row / p.out_h, oy = row - b * p.out_h;
+    const int row_items = p.out_w * c4n;
+    const float* src_b = p.in + (int64_t)b * p.in_h * p.in_w * p.pitch;
+    float* dst_row = p.out + (int64_t)row * p.out_w * p.pitch;
+    const int ay0 = oy * DOWN - p.pad_y0;
+    for (int it = blockIdx.x * 256 + threadIdx.x; it < row_items; it += gridDim.x * 256) {
+        const int ox = it / c4n, c4 = it - ox * c4n;
+        const float* src = src_b + c4 * 4;
+        const int ax0 = ox * DOWN - p.pad_x0;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -58,7 +61,7 @@ __global__ void __launch_bounds__(256) fir_resample_nhwc_kernel(const __grid_con
                 acc.w = fmaf(k, v.w, acc.w);
             }
         }
-        st4(p.out + idx * 4, acc);
+        st4(dst_row + (int64_t)it * 4, acc);
     }
 }
 
@@ -80,29 +83,30 @@ __global__ void __launch_bounds__(256) from_rgb_fwd_kernel(const float* __restri
     for (int i = threadIdx.x; i < pitch; i += 256) sbias[i] = (bias && i < cout) ? __ldg(bias + i) : 0.f;
     __syncthreads();
     const int c4n = pitch >> 2;
-    const int64_t total = (int64_t)B * H * W * c4n;
-    for (int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * 256) {
-        const int c4 = (int)(idx % c4n);
-        int64_t pix = idx / c4n;
-        const int x = (int)(pix % W);
-        int64_t t = pix / W;
-        const int y = (int)(t % H);
-        const int b = (int)(t / H);
-        const float* ip = img + b * sb + y * sh + x * sw;
-        float4 acc = ld4(sbias + c4 * 4);
-        for (int c = 0; c < cin; ++c) {
-            const float v = __ldg(ip + c * sc);
-            const float4 wv = ld4(sw_ + c * pitch + c4 * 4);
-            acc.x = fmaf(v, wv.x, acc.x);
-            acc.y = fmaf(v, wv.y, acc.y);
-            acc.z = fmaf(v, wv.z, acc.z);
-            acc.w = fmaf(v, wv.w, acc.w);
+    const int rows = B * H;
+    for (int row = blockIdx.y; row < rows; row += gridDim.y) {
+        const int b = row / H, y = row - b * H;
+        const float* ip_row = img + b * sb + y * sh;
+        float* out_row = out + (int64_t)row * W * pitch;
+        const int row_items = W * c4n;
+        for (int it = blockIdx.x * 256 + threadIdx.x; it < row_items; it += gridDim.x * 256) {
+            const int x = it / c4n, c4 = it - x * c4n;
+            const float* ip = ip_row + x * sw;
+            float4 acc = ld4(sbias + c4 * 4);
+            for (int c = 0; c < cin; ++c) {
+                const float v = __ldg(ip + c * sc);
+                const float4 wv = ld4(sw_ + c * pitch + c4 * 4);
+                acc.x = fmaf(v, wv.x, acc.x);
+                acc.y = fmaf(v, wv.y, acc.y);
+                acc.z = fmaf(v, wv.z, acc.z);
+                acc.w = fmaf(v, wv.w, acc.w);
+            }
+            if (act) {
+                acc.x = lrelu_gain(acc.x, gain); acc.y = lrelu_gain(acc.y, gain);
+                acc.z = lrelu_gain(acc.z, gain); acc.w = lrelu_gain(acc.w, gain);
+            }
+            st4(out_row + (int64_t)it * 4, acc);
         }
-        if (act) {
-            acc.x = lrelu_gain(acc.x, gain); acc.y = lrelu_gain(acc.y, gain);
-            acc.z = lrelu_gain(acc.z, gain); acc.w = lrelu_gain(acc.w, gain);
-        }
-        st4(out + idx * 4, acc);
     }
 }
 
@@ -204,11 +208,14 @@ int cagc_fir_resample_nhwc(cagc_stream_t stream_, const float* in, const float* 
     p.out_h = num_h / down + 1; p.out_w = num_w / down + 1;
     for (int i = 0; i < 4; ++i)
         for (int j = 0; j < 4; ++j) p.kf[i * 4 + j] = taps_host[(3 - i) * 4 + (3 - j)];
-    const int64_t total = (int64_t)B * p.out_h * p.out_w * (pitch / 4);
+    const int64_t rows = (int64_t)B * p.out_h;
+    CAGC_REQUIRE(rows <= 65535, "fir_resample_nhwc: too many output rows (B * out_h <= 65535)");
+    const int row_items = p.out_w * (pitch / 4);
+    dim3 grid((unsigned)std::min(8, ceil_div(row_items, 256)), (unsigned)rows);
     if (up == 1)
-        fir_resample_nhwc_kernel<1, 2><<<grid_1d(total, 256), 256, 0, stream>>>(p);
+        fir_resample_nhwc_kernel<1, 2><<<grid, 256, 0, stream>>>(p);
     else
-        fir_resample_nhwc_kernel<2, 1><<<grid_1d(total, 256), 256, 0, stream>>>(p);
+        fir_resample_nhwc_kernel<2, 1><<<grid, 256, 0, stream>>>(p);
     return launched("fir_resample_nhwc_kernel");
 }
 
@@ -223,8 +230,9 @@ int cagc_from_rgb_fwd(cagc_stream_t stream_, const float* img, int64_t sb, int64
     const int64_t total = (int64_t)B * H * W * (pitch / 4);
     if (total == 0) return 0;
     const size_t smem = (size_t)(cin + 1) * pitch * sizeof(float);
-    from_rgb_fwd_kernel<<<grid_1d(total, 1024), 256, smem, stream>>>(img, sb, sc, sh, sw, w, bias, out, B, H, W, cin,
-                                                                     cout, pitch, wscale, act, gain);
+    dim3 grid((unsigned)std::min(8, ceil_div(W * (pitch / 4), 256)), (unsigned)std::min(B * H, kNumSMs * 8));
+    from_rgb_fwd_kernel<<<grid, 256, smem, stream>>>(img, sb, sc, sh, sw, w, bias, out, B, H, W, cin, cout, pitch, wscale,
+                                                     act, gain);
     return launched("from_rgb_fwd_kernel");
 }
 

@@ -503,6 +503,26 @@ int cagc_fir_nhwc_taps(cagc_stream_t stream, const float* in, const float* fir, 
                          kw, pad_x0, pad_x1, pad_y0, pad_y1, noise_bstride, act);
 }
 
+// FIR (4x4, up = down = 1) whose output is multiplied by the leaky-ReLU derivative of a reference activation:
+// out = FIR(in) * (mask_ref > 0 ? gain : 0.2 * gain) -- Blur^T followed by the backward of FusedLeakyReLU in one pass
+// (discriminator ResBlock backward).  CAGC_E_UNSUPPORTED when the TMA row-ring kernel cannot take the shape.
+int cagc_fir_nhwc_mask(cagc_stream_t stream_, const float* in, const float* fir, const float* taps_host,
+                       const float* mask_ref, float mask_gain, float* out, int B, int in_h, int in_w, int pitch, int valid,
+                       int kh, int kw, int pad_x0, int pad_x1, int pad_y0, int pad_y1) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CAGC_REQUIRE(in && fir && out && mask_ref && taps_host, "fir_nhwc_mask: null pointer");
+    CAGC_REQUIRE(pitch > 0 && pitch % 8 == 0, "fir_nhwc_mask: pitch must be a positive multiple of 8");
+    CAGC_REQUIRE(aligned16(in) && aligned16(out) && aligned16(mask_ref), "fir_nhwc_mask: pointers must be 16-byte aligned");
+    if (kh != 4 || kw != 4) return fail(CAGC_E_UNSUPPORTED, "fir_nhwc_mask: only 4x4 FIR kernels are implemented");
+    const int out_h = in_h + pad_y0 + pad_y1 - kh + 1, out_w = in_w + pad_x0 + pad_x1 - kw + 1;
+    if (B == 0 || out_h <= 0 || out_w <= 0) return 0;
+    int rc = 0;
+    if (cagc_tc_fir_nhwc(stream, in, fir, nullptr, nullptr, nullptr, nullptr, out, B, in_h, in_w, out_h, out_w, pitch, valid,
+                         pad_x0, pad_y0, 0, 0, taps_host, &rc, mask_ref, mask_gain))
+        return rc;
+    return fail(CAGC_E_UNSUPPORTED, "fir_nhwc_mask: shape not handled by the row-ring kernel");
+}
+
 int cagc_act_bwd_chunks(int H, int W) { return pixel_chunks(H * W); }
 
 int cagc_bias_grad_rows_chunks(int64_t rows, int C) {

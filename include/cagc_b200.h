@@ -37,7 +37,7 @@ typedef void* cagc_stream_t; /* cudaStream_t */
 #define CAGC_E_UNSUPPORTED (-2) /* shape outside what the kernels implement */
 
 /* bump when a signature changes; the Python loader checks it */
-#define CAGC_ABI_VERSION 16
+#define CAGC_ABI_VERSION 17
 
 int cagc_abi_version(void);
 const char* cagc_last_error(void);
@@ -313,6 +313,12 @@ int cagc_from_rgb_fwd(cagc_stream_t stream, const float* img, int64_t sb, int64_
 int cagc_from_rgb_bwd(cagc_stream_t stream, const float* g, const float* yact, const float* w, float* gimg, int B,
                       int H, int W, int cin, int cout, int pitch, float wscale, int act, float gain);
 int cagc_act_mask_nhwc(cagc_stream_t stream, const float* g, const float* y, float* out, int64_t n, float gain);
+/* Blur^T + FusedLeakyReLU backward in one pass: out = upfirdn2d(in, fir, pad) * (mask_ref > 0 ? gain : 0.2 * gain)
+ * (op/upfirdn2d.py:111-116 followed by fused_bias_act_kernel.cu:43); 4x4 kernels, up = down = 1, pitch % 8 == 0.
+ * Returns CAGC_E_UNSUPPORTED when the shape is not handled (caller then runs cagc_fir_nhwc + cagc_act_mask_nhwc). */
+int cagc_fir_nhwc_mask(cagc_stream_t stream, const float* in, const float* fir, const float* taps_host,
+                       const float* mask_ref, float mask_gain, float* out, int B, int in_h, int in_w, int pitch, int valid,
+                       int kh, int kw, int pad_x0, int pad_x1, int pad_y0, int pad_y1);
 
 /* ----------------------------------------------------------------------
  * EqualLinear (reference model.py:137-166: F.linear(x, W * scale) + fused_leaky_relu(bias * lr_mul)) as one launch:
