@@ -16,7 +16,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), 'lib', 'libcagc_b200.so')
-ABI_VERSION = 17
+ABI_VERSION = 18
 
 _p = C.c_void_p
 _i = C.c_int
@@ -63,6 +63,10 @@ SIGNATURES = {
     'cagc_to_nhwc': (_i, [_p, _p, _l, _l, _l, _l, _p, _i, _i, _i, _i, _i]),
     'cagc_adam_step': (_i, [_p, _p, _p, _p, _p, _l, _f, _f, _f, _f, _f, _f, _f, _p]),
     'cagc_adam_ema_step': (_i, [_p, _p, _p, _p, _p, _l, _f, _f, _f, _f, _f, _f, _f, _p, _p, _f]),
+    'cagc_conv_workspace_bytes': (_l, [_i, _i, _i, _i]),
+    'cagc_conv_same_ws': (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _l, _i, _i, _p, _l]),
+    'cagc_conv_up_dgrad_ws': (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _l]),
+    'cagc_conv2d_ws': (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _p, _l]),
     'cagc_linear_fwd': (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _f, _f, _i, _f, _f]),
     'cagc_linear_bwd': (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i]),
     'cagc_conv2d': (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i]),
@@ -122,6 +126,15 @@ def require_cuda(t: torch.Tensor, what: str):
                            'The CPU restatement lives in oracle/ and is test infrastructure.')
     if t.dtype != torch.float32:
         raise RuntimeError(f'{what}: only float32 tensors are supported, got {t.dtype}')
+
+
+def conv_workspace(b: int, ho: int, wo: int, pitch: int, device):
+    """Split-K scratch for a small convolution (None when the shape never splits).  Allocated per call from torch's
+    caching allocator: stream-ordered, safe under CUDA-graph capture and with the teacher on a parallel branch."""
+    n = int(lib.cagc_conv_workspace_bytes(b, ho, wo, pitch))
+    if n <= 0:
+        return None, 0
+    return torch.empty(n // 4, device=device, dtype=torch.float32), n
 
 
 def launch_count() -> int:

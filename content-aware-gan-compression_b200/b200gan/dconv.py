@@ -27,7 +27,7 @@ import torch
 from torch.autograd import Function
 from torch.autograd.function import once_differentiable
 
-from ._lib import lib, check, stream_of, require_cuda, ptr, host_taps, fir_nhwc
+from ._lib import lib, check, stream_of, require_cuda, ptr, host_taps, fir_nhwc, conv_workspace
 from . import config
 from .modconv import (_frozen, _weight_prep, _use_tc, _flipped, as_nhwc_buf, nhwc_view, pitch_of, _timed)
 
@@ -57,9 +57,11 @@ def _conv(st, x_buf, slab, bias_p, residual, out, b, h, w, pin, pout, cout, k, m
     algo = config.ALGO_TCGEN05_TF32 if tc else config.ALGO_SIMT_FP32
     ho, wo = (h, w) if mode == 0 else ((h - k) // 2 + 1, (w - k) // 2 + 1)
     flops = 2.0 * b * ho * wo * pin * cout * k * k
+    ws, ws_bytes = conv_workspace(b, ho, wo, pout, out.device) if tc else (None, 0)
     _timed(f'dconv[algo{algo}]', flops, 4.0 * b * (h * w * pin + ho * wo * pout),
-           lambda: check(lib.cagc_conv2d(st, x_buf.data_ptr(), slab.data_ptr(), ptr(bias_p), ptr(residual),
-                                         out.data_ptr(), b, h, w, pin, pout, cout, k, mode, int(act), gain, algo), name),
+           lambda: check(lib.cagc_conv2d_ws(st, x_buf.data_ptr(), slab.data_ptr(), ptr(bias_p), ptr(residual),
+                                            out.data_ptr(), b, h, w, pin, pout, cout, k, mode, int(act), gain, algo,
+                                            ptr(ws), ws_bytes), name),
            shape=f'{pin}->{cout}x{ho}x{wo}k{k}s{1 + mode}')
 
 

@@ -28,7 +28,7 @@ import torch.nn.functional as F
 from torch.autograd import Function
 from torch.autograd.function import once_differentiable
 
-from ._lib import lib, check, stream_of, require_cuda, ptr, fir_nhwc, TensorCache
+from ._lib import lib, check, stream_of, require_cuda, ptr, fir_nhwc, TensorCache, conv_workspace
 from . import config
 
 
@@ -242,11 +242,14 @@ class _StyledConvFn(Function):
                 out = torch.empty((b, h, w, pout), device=dev, dtype=torch.float32)
                 if out.numel():
                     flops = 2.0 * b * h * w * cin * cout * k * k          # Util/Calculators.py convention x2
+                    ws, ws_bytes = conv_workspace(b, h, w, pout, dev) if tc else (None, 0)
                     _timed(f'conv_same[algo{falgo}]', flops, 4.0 * b * h * w * (cin + cout),
-                           lambda: check(lib.cagc_conv_same(st, x_in.data_ptr(), w_fwd.data_ptr(), s_arg,
-                                                            ptr(d_p), ptr(noise), ptr(nw), ptr(bias_p), out.data_ptr(),
-                                                            b, h, w, pin, pout, cout, k, nstride, int(act), falgo),
+                           lambda: check(lib.cagc_conv_same_ws(st, x_in.data_ptr(), w_fwd.data_ptr(), s_arg,
+                                                               ptr(d_p), ptr(noise), ptr(nw), ptr(bias_p), out.data_ptr(),
+                                                               b, h, w, pin, pout, cout, k, nstride, int(act), falgo,
+                                                               ptr(ws), ws_bytes),
                                          'conv_same'), shape=f'{cin}->{cout}x{h}x{w}')
+                    del ws
             else:
                 hu, wu = 2 * h + k - 2, 2 * w + k - 2
                 ut = torch.empty((b, hu, wu, pout), device=dev, dtype=torch.float32)
@@ -324,15 +327,18 @@ class _StyledConvFn(Function):
                 gxt = torch.empty((b, h, w, pin), device=dev, dtype=torch.float32)
                 dalgo = config.ALGO_TCGEN05_TF32 if _use_tc(algo, pout) else config.ALGO_SIMT_FP32
                 flops, nbytes = 2.0 * b * h * w * cin * cout * k * k, 4.0 * b * h * w * (cin + cout)
+                ws, ws_bytes = conv_workspace(b, h, w, pin, dev) if dalgo == config.ALGO_TCGEN05_TF32 else (None, 0)
                 if upsample:
                     _timed(f'conv_up_dgrad[algo{dalgo}]', flops, 4.0 * b * (h * w * cin + hu * wu * cout),
-                           lambda: check(lib.cagc_conv_up_dgrad(st, g_conv.data_ptr(), w_d.data_ptr(), gxt.data_ptr(),
-                                                                b, h, w, pout, pin, k, dalgo), 'conv_up_dgrad'))
+                           lambda: check(lib.cagc_conv_up_dgrad_ws(st, g_conv.data_ptr(), w_d.data_ptr(), gxt.data_ptr(),
+                                                                   b, h, w, pout, pin, k, dalgo, ptr(ws), ws_bytes),
+                                         'conv_up_dgrad'))
                 else:
                     _timed(f'conv_same[algo{dalgo}]', flops, nbytes,
-                           lambda: check(lib.cagc_conv_same(st, g_conv.data_ptr(), w_d.data_ptr(), None, None, None,
-                                                            None, None, gxt.data_ptr(), b, h, w, pout, pin, pin, k, 0,
-                                                            0, dalgo), 'conv_same(dgrad)'))
+                           lambda: check(lib.cagc_conv_same_ws(st, g_conv.data_ptr(), w_d.data_ptr(), None, None, None,
+                                                               None, None, gxt.data_ptr(), b, h, w, pout, pin, pin, k, 0,
+                                                               0, dalgo, ptr(ws), ws_bytes), 'conv_same(dgrad)'))
+                del ws
                 mchunks = lib.cagc_act_bwd_chunks(h, w)
                 mpartial = torch.empty((b, mchunks, pin), device=dev, dtype=torch.float32)
                 check(lib.cagc_mod_bwd(st, gxt.data_ptr(), xb.data_ptr(), s_p.data_ptr(), mpartial.data_ptr(),

@@ -20,6 +20,8 @@ struct ConvP {
     const float* bias;
     const float* residual;   // optional tensor of the output's layout, added AFTER the activation (ResBlock skip)
     float* out;
+    float* workspace;        // optional scratch for split-K of small layers (cagc_conv_workspace_bytes); null: never split
+    int64_t workspace_bytes;
     int B, Hin, Win, in_pitch;
     int Ho, Wo, in_stride;
     int n_cols;  // weight slab leading dimension == out pitch

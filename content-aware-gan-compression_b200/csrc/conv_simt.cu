@@ -289,10 +289,26 @@ static int check_nhwc(const char* what, int B, int H, int W, int in_pitch, int o
 
 extern "C" {
 
-int cagc_conv_same(cagc_stream_t stream_, const float* in, const float* w_slabs, const float* in_scale,
+int64_t cagc_conv_workspace_bytes(int B, int Ho, int Wo, int out_pitch) {
+    // split-K scratch of the tensor-pipe engine: up to 8 partial slabs of the output; only layers too small to fill the
+    // machine ever use it (<= 64 pixel tiles), so anything large answers 0 and is never split
+    const int64_t pixels = (int64_t)B * Ho * Wo;
+    if (pixels <= 0 || pixels > 64 * 128) return 0;
+    return 8 * pixels * out_pitch * (int64_t)sizeof(float);
+}
+
+int cagc_conv_same(cagc_stream_t stream, const float* in, const float* w_slabs, const float* in_scale,
                    const float* out_scale, const float* noise, const float* noise_w, const float* bias, float* out,
                    int B, int H, int W, int in_pitch, int out_pitch, int out_valid, int ksize, int64_t noise_bstride,
                    int act, int algo) {
+    return cagc_conv_same_ws(stream, in, w_slabs, in_scale, out_scale, noise, noise_w, bias, out, B, H, W, in_pitch,
+                             out_pitch, out_valid, ksize, noise_bstride, act, algo, nullptr, 0);
+}
+
+int cagc_conv_same_ws(cagc_stream_t stream_, const float* in, const float* w_slabs, const float* in_scale,
+                      const float* out_scale, const float* noise, const float* noise_w, const float* bias, float* out,
+                      int B, int H, int W, int in_pitch, int out_pitch, int out_valid, int ksize, int64_t noise_bstride,
+                      int act, int algo, float* workspace, int64_t workspace_bytes) {
     cudaStream_t stream = (cudaStream_t)stream_;
     CAGC_TRY(check_nhwc("conv_same", B, H, W, in_pitch, out_pitch, ksize));
     CAGC_REQUIRE(in && w_slabs && out, "conv_same: null pointer");
@@ -301,7 +317,7 @@ int cagc_conv_same(cagc_stream_t stream_, const float* in, const float* w_slabs,
     CAGC_REQUIRE(aligned16(in) && aligned16(w_slabs) && aligned16(out), "conv_same: pointers must be 16-byte aligned");
     ConvP p{};
     p.in = in; p.w = w_slabs; p.in_scale = in_scale; p.out_scale = out_scale; p.noise = noise; p.noise_w = noise_w;
-    p.bias = bias; p.out = out;
+    p.bias = bias; p.out = out; p.workspace = workspace; p.workspace_bytes = workspace_bytes;
     p.B = B; p.Hin = H; p.Win = W; p.in_pitch = in_pitch; p.Ho = H; p.Wo = W; p.in_stride = 1;
     p.n_cols = out_pitch; p.out_valid = out_valid; p.Hout = H; p.Wout = W; p.out_stride = 1; p.out_oy = 0; p.out_ox = 0;
     p.noise_bstride = noise_bstride; p.act = act; p.ntaps = ksize * ksize;
@@ -350,13 +366,18 @@ int cagc_conv_up(cagc_stream_t stream_, const float* in, const float* w_slabs, c
     return 0;
 }
 
-int cagc_conv_up_dgrad(cagc_stream_t stream_, const float* g_t, const float* w_slabs, float* g_in, int B, int H, int W,
+int cagc_conv_up_dgrad(cagc_stream_t stream, const float* g_t, const float* w_slabs, float* g_in, int B, int H, int W,
                        int g_pitch, int in_pitch, int ksize, int algo) {
+    return cagc_conv_up_dgrad_ws(stream, g_t, w_slabs, g_in, B, H, W, g_pitch, in_pitch, ksize, algo, nullptr, 0);
+}
+
+int cagc_conv_up_dgrad_ws(cagc_stream_t stream_, const float* g_t, const float* w_slabs, float* g_in, int B, int H, int W,
+                          int g_pitch, int in_pitch, int ksize, int algo, float* workspace, int64_t workspace_bytes) {
     cudaStream_t stream = (cudaStream_t)stream_;
     CAGC_TRY(check_nhwc("conv_up_dgrad", B, H, W, g_pitch, in_pitch, ksize));
     CAGC_REQUIRE(g_t && w_slabs && g_in, "conv_up_dgrad: null pointer");
     ConvP p{};
-    p.in = g_t; p.w = w_slabs; p.out = g_in;
+    p.in = g_t; p.w = w_slabs; p.out = g_in; p.workspace = workspace; p.workspace_bytes = workspace_bytes;
     p.B = B; p.Hin = 2 * H + ksize - 2; p.Win = 2 * W + ksize - 2; p.in_pitch = g_pitch; p.in_stride = 2;
     p.Ho = H; p.Wo = W; p.n_cols = in_pitch; p.out_valid = in_pitch; p.Hout = H; p.Wout = W; p.out_stride = 1;
     p.act = 0; p.ntaps = ksize * ksize;

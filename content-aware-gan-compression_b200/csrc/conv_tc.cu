@@ -56,6 +56,9 @@ struct TcParams {
     int64_t noise_bstride;
     int act, ntaps, stages, in_stride;
     int mt, tiles_total;        // M sub-tiles (128 pixels each) per CTA sharing one weight tile; number of pixel tiles
+    int it_per_split;           // conv_tc_kernel split-K: (tap, chunk) iterations per blockIdx.z (0: no split)
+    float* ws;                  // split-K: raw partial sums, slab z at ws + z * ws_slab (layout of out)
+    int64_t ws_slab;
     uint32_t b_bytes;           // bytes of one B stage
     Tap taps[kMaxTaps];
     // persistent kernel only: several "phases" (the four output parities of the stride-2 transposed convolution)
@@ -459,13 +462,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const uint32_t tmem_acc = tmem_base_slot;
 
     const int nk = (p.k_valid + kChunkK - 1) / kChunkK;
-    const int total = p.ntaps * nk;
+    // split-K (small layers): blockIdx.z owns the (tap, chunk) iterations [it0, total) of the full K loop and leaves raw
+    // partial sums in its workspace slab; splitk_epilogue_kernel adds the slabs in a fixed order and applies the epilogue
+    const int it0 = p.it_per_split ? (int)blockIdx.z * p.it_per_split : 0;
+    const int total = p.it_per_split ? min(p.ntaps * nk, it0 + p.it_per_split) : p.ntaps * nk;
 
     if (warp == 0) {
         // =============================== TMA producer ===============================
-        for (int it = 0; it < total; ++it) {
-            const int s = it % S;
-            const uint32_t ph = (uint32_t)(it / S) & 1u;
+        for (int it = it0; it < total; ++it) {
+            const int s = (it - it0) % S;
+            const uint32_t ph = (uint32_t)((it - it0) / S) & 1u;
             mbar_wait(empty_bar(s), ph ^ 1u);
             const int tap = it / nk, kc = it - tap * nk;
             const Tap tp = p.taps[tap];
@@ -483,9 +489,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32, K-major both, N>>3, M>>4
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n_mma >> 3) << 17) |
                                ((uint32_t)(kTileM >> 4) << 24);
-        for (int it = 0; it < total; ++it) {
-            const int s = it % S;
-            const uint32_t ph = (uint32_t)(it / S) & 1u;
+        for (int it = it0; it < total; ++it) {
+            const int s = (it - it0) % S;
+            const uint32_t ph = (uint32_t)((it - it0) / S) & 1u;
             mbar_wait(full_bar(s), ph);
             tc_fence_after();
             const int kc = it % nk;
@@ -494,7 +500,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const uint32_t b_lo = desc_lo_sw128(b_addr(s));
             if (elect_one()) {
                 for (int j = 0; j < MT; ++j)
-                    mma_stage_k(tmem_acc + (uint32_t)(j * n_mma), desc_lo_sw128(a_addr(s, j)), b_lo, idesc, kk, it == 0);
+                    mma_stage_k(tmem_acc + (uint32_t)(j * n_mma), desc_lo_sw128(a_addr(s, j)), b_lo, idesc, kk, it == it0);
                 tc_commit(empty_bar(s));   // frees the smem stage once these MMAs have read it
                 if (it == total - 1) tc_commit(acc_bar);            // accumulator complete
             }
@@ -509,7 +515,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int lb = m / (p.bw * p.bh);
         mbar_wait(acc_bar, 0);
         tc_fence_after();
-        const EpiArgs ea{p.out_scale, p.bias, p.residual, p.out, p.n_pitch, p.out_valid, p.act, p.noise != nullptr, p.act_gain};
+        const EpiArgs ea = p.it_per_split
+            ? EpiArgs{nullptr, nullptr, nullptr, p.ws + (int64_t)blockIdx.z * p.ws_slab, p.n_pitch, p.n_pitch, 0, 0, 1.f}
+            : EpiArgs{p.out_scale, p.bias, p.residual, p.out, p.n_pitch, p.out_valid, p.act, p.noise != nullptr, p.act_gain};
       for (int j = 0; j < MT; ++j) {
         const int ox = x0s[j] + lx, oy = y0s[j] + ly, b = b0s[j] + lb;
         const bool pvalid = (ox < p.Wo) && (oy < p.Ho) && (b < p.B);
@@ -1811,6 +1819,63 @@ static int encode_act_map(EncodeTiledFn encode, CUtensorMap* map, const float* p
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 }
 
+// Split-K second pass: out = epilogue(sum_z ws[z]) -- slabs added in the fixed order z = 0 .. nsplit-1 (deterministic).
+struct SplitKEpiP {
+    const float* ws;
+    int64_t slab;              // floats per slab = B * H * W * n_pitch
+    int nsplit;
+    const float* out_scale;
+    const float* noise;
+    const float* noise_w;
+    const float* bias;
+    const float* residual;
+    float* out;
+    int HW, n_pitch, out_valid, act;
+    int64_t noise_bstride;
+    float act_gain;
+};
+
+__global__ void __launch_bounds__(256) splitk_epilogue_kernel(const SplitKEpiP p) {
+    const int c4n = p.n_pitch >> 2;
+    const int64_t n4 = p.slab >> 2;
+    const float nw = p.noise ? __ldg(p.noise_w) : 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256) {
+        float4 a = ld4(p.ws + i * 4);
+        for (int z = 1; z < p.nsplit; ++z) {
+            const float4 v = ld4(p.ws + (int64_t)z * p.slab + i * 4);
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+        const int64_t pix = i / c4n;
+        const int n = (int)(i - pix * c4n) * 4;
+        const int b = (int)(pix / p.HW);
+        float o[4] = {a.x, a.y, a.z, a.w};
+        if (p.out_scale) {
+            const float4 s4 = ldg4(p.out_scale + (int64_t)b * p.n_pitch + n);
+            o[0] *= s4.x; o[1] *= s4.y; o[2] *= s4.z; o[3] *= s4.w;
+        }
+        if (p.noise) {
+            const float nz = nw * __ldg(p.noise + (int64_t)b * p.noise_bstride + (pix - (int64_t)b * p.HW));
+            o[0] += nz; o[1] += nz; o[2] += nz; o[3] += nz;
+        }
+        if (p.bias) {
+            const float4 b4 = ldg4(p.bias + n);
+            o[0] += b4.x; o[1] += b4.y; o[2] += b4.z; o[3] += b4.w;
+        }
+        if (p.act) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = lrelu_gain(o[j], p.act_gain);
+        }
+        if (p.residual) {
+            const float4 r4 = ldg4(p.residual + i * 4);
+            o[0] += r4.x; o[1] += r4.y; o[2] += r4.z; o[3] += r4.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (n + j >= p.out_valid) o[j] = 0.f;
+        st4(p.out + i * 4, make_float4(o[0], o[1], o[2], o[3]));
+    }
+}
+
 static int next_pow2(int v) {
     int p = 1;
     while (p < v) p <<= 1;
@@ -2004,7 +2069,9 @@ int cagc_tc_conv(cudaStream_t stream, const ConvP& c, const char* what) {
     if ((int64_t)p.tiles_total * ceil_div(p.n_rows, p.n_tile) >= 4 * kNumSMs) {
         if (p.n_tile <= 128) p.mt = 2;
     } else {
-        while (p.n_tile > 32 && (int64_t)p.tiles_total * ceil_div(p.n_rows, p.n_tile) < kNumSMs) {
+        // (with a split-K workspace the K loop is dealt to up to 8 CTAs per tile: keep wider N tiles, fewer A re-reads)
+        const int want_ctas = (c.workspace && c.out_stride == 1) ? kNumSMs / 4 : kNumSMs;
+        while (p.n_tile > 32 && (int64_t)p.tiles_total * ceil_div(p.n_rows, p.n_tile) < want_ctas) {
             int nt = (p.n_tile / 2 + 15) & ~15;
             if (nt < 32) nt = 32;
             p.n_tile = nt;
@@ -2093,6 +2160,34 @@ int cagc_tc_conv(cudaStream_t stream, const ConvP& c, const char* what) {
         return launched(what);
     }
     const int64_t gx = ceil_div<int64_t>(p.tiles_total, p.mt);
+    // split-K for layers that cannot fill the machine (4x4 .. 16x16 images, per-rank batch 2): every CTA walks the whole
+    // K loop (9 taps x 16 chunks = 144 stages at ~0.5 us) on a handful of SMs; deal the (tap, chunk) iterations to
+    // up to 8 CTAs per tile instead and add their partial sums in a second, elementwise pass
+    {
+        const int nk_h = ceil_div(c.in_pitch, kChunkK);
+        const int total_it = c.ntaps * nk_h;
+        const int64_t ctas = gx * ceil_div(p.n_rows, p.n_tile);
+        const int64_t slab = (int64_t)c.B * c.Ho * c.Wo * c.n_cols;
+        static const int split_env = [] { const char* e = getenv("CAGC_TC_SPLITK"); return e ? atoi(e) : 1; }();
+        int ns = (int)std::min<int64_t>(std::min<int64_t>(8, kNumSMs / std::max<int64_t>(ctas, 1)), total_it / 8);
+        if (split_env && c.workspace && c.out_stride == 1 && c.Hout == c.Ho && c.Wout == c.Wo && ns >= 2 &&
+            (int64_t)ns * slab * 4 <= c.workspace_bytes) {
+            p.it_per_split = ceil_div(total_it, ns);
+            ns = ceil_div(total_it, p.it_per_split);
+            p.ws = c.workspace; p.ws_slab = slab;
+            dim3 grid((unsigned)gx, (unsigned)ceil_div(p.n_rows, p.n_tile), (unsigned)ns);
+            conv_tc_kernel<<<grid, kThreads, smem, stream>>>(map_a, map_b, p);
+            CAGC_TRY(launched(what));
+            SplitKEpiP q{};
+            q.ws = c.workspace; q.slab = slab; q.nsplit = ns;
+            q.out_scale = c.out_scale; q.noise = c.noise; q.noise_w = c.noise_w; q.bias = c.bias; q.residual = c.residual;
+            q.out = c.out; q.HW = c.Ho * c.Wo; q.n_pitch = c.n_cols; q.out_valid = c.out_valid; q.act = c.act;
+            q.noise_bstride = c.noise_bstride; q.act_gain = (c.act_gain != 0.f) ? c.act_gain : kSqrt2;
+            const int64_t blocks = std::min<int64_t>(ceil_div<int64_t>(slab / 4, 256), kNumSMs * 4);
+            splitk_epilogue_kernel<<<(unsigned)std::max<int64_t>(blocks, 1), 256, 0, stream>>>(q);
+            return launched("splitk_epilogue_kernel");
+        }
+    }
     CAGC_REQUIRE(gx <= 0x7fffffffLL, "%s: too many tiles", what);
     dim3 grid((unsigned)gx, ceil_div(p.n_rows, p.n_tile));
     conv_tc_kernel<<<grid, kThreads, smem, stream>>>(map_a, map_b, p);

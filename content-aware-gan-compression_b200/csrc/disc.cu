@@ -267,9 +267,16 @@ int cagc_act_mask_nhwc(cagc_stream_t stream_, const float* g, const float* y, fl
 //           model.py:683-700)
 // Weight slabs as produced by cagc_weight_prep (tensor pipe: K-major [tap][roundup16(out_pitch)][in_pitch], TF32;
 // SIMT: [tap][in_pitch][out_pitch]).  The data gradient of mode 1 is cagc_conv_up (transposed convolution).
-int cagc_conv2d(cagc_stream_t stream_, const float* in, const float* w_slabs, const float* bias, const float* residual,
+int cagc_conv2d(cagc_stream_t stream, const float* in, const float* w_slabs, const float* bias, const float* residual,
                 float* out, int B, int Hin, int Win, int in_pitch, int out_pitch, int out_valid, int ksize, int mode,
                 int act, float act_gain, int algo) {
+    return cagc_conv2d_ws(stream, in, w_slabs, bias, residual, out, B, Hin, Win, in_pitch, out_pitch, out_valid, ksize, mode,
+                          act, act_gain, algo, nullptr, 0);
+}
+
+int cagc_conv2d_ws(cagc_stream_t stream_, const float* in, const float* w_slabs, const float* bias, const float* residual,
+                   float* out, int B, int Hin, int Win, int in_pitch, int out_pitch, int out_valid, int ksize, int mode,
+                   int act, float act_gain, int algo, float* workspace, int64_t workspace_bytes) {
     cudaStream_t stream = (cudaStream_t)stream_;
     CAGC_REQUIRE(in && w_slabs && out, "conv2d: null pointer");
     CAGC_REQUIRE(B >= 0 && Hin >= 0 && Win >= 0, "conv2d: negative size");
@@ -283,6 +290,7 @@ int cagc_conv2d(cagc_stream_t stream_, const float* in, const float* w_slabs, co
     CAGC_REQUIRE(residual != out, "conv2d: residual must not alias the output");
     ConvP p{};
     p.in = in; p.w = w_slabs; p.bias = bias; p.residual = residual; p.out = out;
+    p.workspace = workspace; p.workspace_bytes = workspace_bytes;
     p.B = B; p.Hin = Hin; p.Win = Win; p.in_pitch = in_pitch;
     p.n_cols = out_pitch; p.out_valid = out_valid; p.out_stride = 1; p.out_oy = 0; p.out_ox = 0;
     p.act = act ? 1 : 0; p.act_gain = act_gain; p.ntaps = ksize * ksize;

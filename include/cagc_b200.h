@@ -37,7 +37,7 @@ typedef void* cagc_stream_t; /* cudaStream_t */
 #define CAGC_E_UNSUPPORTED (-2) /* shape outside what the kernels implement */
 
 /* bump when a signature changes; the Python loader checks it */
-#define CAGC_ABI_VERSION 17
+#define CAGC_ABI_VERSION 18
 
 int cagc_abi_version(void);
 const char* cagc_last_error(void);
@@ -319,6 +319,24 @@ int cagc_act_mask_nhwc(cagc_stream_t stream, const float* g, const float* y, flo
 int cagc_fir_nhwc_mask(cagc_stream_t stream, const float* in, const float* fir, const float* taps_host,
                        const float* mask_ref, float mask_gain, float* out, int B, int in_h, int in_w, int pitch, int valid,
                        int kh, int kw, int pad_x0, int pad_x1, int pad_y0, int pad_y1);
+
+/* ----------------------------------------------------------------------
+ * Split-K for layers too small to fill the machine (4x4 .. 16x16 images, or a per-rank batch of 2 under strong
+ * scaling): the `_ws` forms of the convolution entry points take a caller-owned scratch buffer
+ * (cagc_conv_workspace_bytes; 0 = this shape never splits).  The tensor-pipe engine may then deal the (tap, channel
+ * chunk) iterations of the K loop to up to 8 CTAs per tile and add the partial sums in a fixed order in a second
+ * pass that also applies the epilogue (deterministic).  Same results contract as the plain forms.
+ * ---------------------------------------------------------------------- */
+int64_t cagc_conv_workspace_bytes(int B, int Ho, int Wo, int out_pitch);
+int cagc_conv_same_ws(cagc_stream_t stream, const float* in, const float* w_slabs, const float* in_scale,
+                      const float* out_scale, const float* noise, const float* noise_w, const float* bias, float* out,
+                      int B, int H, int W, int in_pitch, int out_pitch, int out_valid, int ksize, int64_t noise_bstride,
+                      int act, int algo, float* workspace, int64_t workspace_bytes);
+int cagc_conv_up_dgrad_ws(cagc_stream_t stream, const float* g_t, const float* w_slabs, float* g_in, int B, int H, int W,
+                          int g_pitch, int in_pitch, int ksize, int algo, float* workspace, int64_t workspace_bytes);
+int cagc_conv2d_ws(cagc_stream_t stream, const float* in, const float* w_slabs, const float* bias, const float* residual,
+                   float* out, int B, int Hin, int Win, int in_pitch, int out_pitch, int out_valid, int ksize, int mode,
+                   int act, float act_gain, int algo, float* workspace, int64_t workspace_bytes);
 
 /* ----------------------------------------------------------------------
  * EqualLinear (reference model.py:137-166: F.linear(x, W * scale) + fused_leaky_relu(bias * lr_mul)) as one launch:
