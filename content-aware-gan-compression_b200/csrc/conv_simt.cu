@@ -7,6 +7,8 @@
 // kernel is validated against them.  GEMM view: M = pixels (linearised over b, y, x), N = output
 // channels, K = taps x input channels; style modulation is applied to the A operand while it is
 // staged (no per-sample weights are ever materialised, unlike model.py:249-257).
+#include <algorithm>
+
 #include "conv_params.cuh"
 
 namespace cagc {
@@ -290,11 +292,12 @@ static int check_nhwc(const char* what, int B, int H, int W, int in_pitch, int o
 extern "C" {
 
 int64_t cagc_conv_workspace_bytes(int B, int Ho, int Wo, int out_pitch) {
-    // split-K scratch of the tensor-pipe engine: up to 8 partial slabs of the output; only layers too small to fill the
+    // split-K scratch of the tensor-pipe engine: up to 16 partial slabs of the output (at most 64 MB); only layers too small to fill the
     // machine ever use it (<= 64 pixel tiles), so anything large answers 0 and is never split
     const int64_t pixels = (int64_t)B * Ho * Wo;
     if (pixels <= 0 || pixels > 64 * 128) return 0;
-    return 8 * pixels * out_pitch * (int64_t)sizeof(float);
+    const int64_t slab = pixels * out_pitch * (int64_t)sizeof(float);
+    return std::min<int64_t>(16 * slab, std::max<int64_t>(2 * slab, 64ll << 20));
 }
 
 int cagc_conv_same(cagc_stream_t stream, const float* in, const float* w_slabs, const float* in_scale,

@@ -2070,7 +2070,7 @@ int cagc_tc_conv(cudaStream_t stream, const ConvP& c, const char* what) {
         if (p.n_tile <= 128) p.mt = 2;
     } else {
         // (with a split-K workspace the K loop is dealt to up to 8 CTAs per tile: keep wider N tiles, fewer A re-reads)
-        const int want_ctas = (c.workspace && c.out_stride == 1) ? kNumSMs / 4 : kNumSMs;
+        const int want_ctas = (c.workspace && c.out_stride == 1) ? kNumSMs / 8 : kNumSMs;
         while (p.n_tile > 32 && (int64_t)p.tiles_total * ceil_div(p.n_rows, p.n_tile) < want_ctas) {
             int nt = (p.n_tile / 2 + 15) & ~15;
             if (nt < 32) nt = 32;
@@ -2162,14 +2162,15 @@ int cagc_tc_conv(cudaStream_t stream, const ConvP& c, const char* what) {
     const int64_t gx = ceil_div<int64_t>(p.tiles_total, p.mt);
     // split-K for layers that cannot fill the machine (4x4 .. 16x16 images, per-rank batch 2): every CTA walks the whole
     // K loop (9 taps x 16 chunks = 144 stages at ~0.5 us) on a handful of SMs; deal the (tap, chunk) iterations to
-    // up to 8 CTAs per tile instead and add their partial sums in a second, elementwise pass
+    // up to 16 CTAs per tile instead and add their partial sums in a second, elementwise pass
     {
         const int nk_h = ceil_div(c.in_pitch, kChunkK);
         const int total_it = c.ntaps * nk_h;
         const int64_t ctas = gx * ceil_div(p.n_rows, p.n_tile);
         const int64_t slab = (int64_t)c.B * c.Ho * c.Wo * c.n_cols;
         static const int split_env = [] { const char* e = getenv("CAGC_TC_SPLITK"); return e ? atoi(e) : 1; }();
-        int ns = (int)std::min<int64_t>(std::min<int64_t>(8, kNumSMs / std::max<int64_t>(ctas, 1)), total_it / 8);
+        int ns = (int)std::min<int64_t>(std::min<int64_t>(16, kNumSMs / std::max<int64_t>(ctas, 1)), total_it / 4);
+        if (slab > 0) ns = (int)std::min<int64_t>(ns, c.workspace_bytes / (slab * 4));
         if (split_env && c.workspace && c.out_stride == 1 && c.Hout == c.Ho && c.Wout == c.Wo && ns >= 2 &&
             (int64_t)ns * slab * 4 <= c.workspace_bytes) {
             p.it_per_split = ceil_div(total_it, ns);
