@@ -25,6 +25,7 @@ namespace cagc {
 namespace tc {
 
 constexpr int kThreads = 192;
+constexpr int kThreadsPersist = 320;             // persistent conv kernel: TMA + MMA + 8 epilogue warps
 constexpr int kTileM = 128;
 constexpr int kChunkK = 32;                      // fp32 elements per 128-byte swizzle row
 constexpr int kABytes = kTileM * kChunkK * 4;    // 16 KB
@@ -296,6 +297,22 @@ __device__ __forceinline__ void epi_rows(const EpiArgs& e, float* st, uint32_t t
     if (c < n_mma) epi_chunk<16>(e, st, taddr + (uint32_t)c, lane, n0 + c, rvalid, roff, rnz, rb);
 }
 
+// Two epilogue warps per TMEM lane quarter (persistent kernel): warp `part` of the pair takes every other 16-column
+// chunk.  One warp per scheduler runs the epilogue's dependent chain (TMEM load -> transpose -> math -> store) at
+// a few instructions per 10 cycles; layers with little K per output (1x1 convolutions, the up-convolutions' large
+// outputs) were bound by it.  16-column chunks keep the staging at 2 KB per warp (8 warps: the same 16 KB).
+__device__ __forceinline__ void epi_rows_pair(const EpiArgs& e, float* st, uint32_t taddr, int lane, int n0, int n_mma,
+                                              bool rvalid, int64_t roff, float rnz, int rb, int part) {
+    if (n_mma < kEpiTransposeMinN || st == nullptr) {
+        // direct form: the pair splits the column range in halves (multiples of 16)
+        const int half = ((n_mma >> 4) + 1) >> 1 << 4;
+        const int c0 = part ? half : 0, c1 = part ? n_mma : half;
+        if (c1 > c0) epi_rows_direct(e, taddr + (uint32_t)c0, n0 + c0, c1 - c0, rvalid, roff, rnz, rb);
+        return;
+    }
+    for (int c = part * 16; c < n_mma; c += 32) epi_chunk<16>(e, st, taddr + (uint32_t)c, lane, n0 + c, rvalid, roff, rnz, rb);
+}
+
 // One elected lane of a converged warp.  The TMA / MMA warps keep their control flow warp-uniform and put only
 // the asynchronous instruction itself under the election: every address / descriptor computation then stays on
 // the uniform datapath, and the single-thread issue loop (the real bound of narrow-N tcgen05 tiles: ~150 cycles
@@ -550,7 +567,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreadsPersist, 1)
 conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                        const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -581,7 +598,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
-            mbar_init(tempty_bar(a), 4);            // one arrival per epilogue warp
+            mbar_init(tempty_bar(a), 8);            // one arrival per epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -687,7 +704,9 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
             if (++acc == 2) { acc = 0; aph ^= 1u; }
         }
     } else {
-        const int q = warp & 3;
+        const int q = warp & 3;                   // TMEM lane quarter; warps w and w + 4 share it
+        const int part = (warp - 2) >> 2;         // which 16-column chunks of the pair this warp takes
+        float* const my_stage = epi_stage_base ? epi_stage_base + (warp - 2) * 512 : nullptr;     // 2 KB per warp
         const int m = q * 32 + lane;
         const int lx = m % p.bw;
         const int ly = (m / p.bw) % p.bh;
@@ -721,7 +740,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                 const int yy = oy * p.out_stride + p.ph_oy[f], xx = ox * p.out_stride + p.ph_ox[f];
                 const float nz = nzs[j];
                 const int64_t roff = (((int64_t)b * p.Hout + yy) * p.Wout + xx) * p.n_pitch;
-                epi_rows(ea, (epi_stage_base ? epi_stage_base + q * 1024 : nullptr), d0 + (uint32_t)(j * p.n_tile), lane, n0, n_mma, pvalid, roff, nz, b);
+                epi_rows_pair(ea, my_stage, d0 + (uint32_t)(j * p.n_tile), lane, n0, n_mma, pvalid, roff, nz, b, part);
             }
             // this warp has finished reading the accumulator buffer: hand it back to the MMA warp
             tc_fence_before();
@@ -2156,7 +2175,7 @@ int cagc_tc_conv(cudaStream_t stream, const ConvP& c, const char* what) {
         q.epi_off = (uint32_t)q.stages * sb;
         const size_t smem_p = (size_t)q.stages * sb + 1024 + kEpiStageBytes;
         const unsigned gridp = (unsigned)std::min<int64_t>(items, kNumSMs);
-        conv_tc_persist_kernel<<<gridp, kThreads, smem_p, stream>>>(map_a, map_b, q);
+        conv_tc_persist_kernel<<<gridp, kThreadsPersist, smem_p, stream>>>(map_a, map_b, q);
         return launched(what);
     }
     const int64_t gx = ceil_div<int64_t>(p.tiles_total, p.mt);
@@ -2288,7 +2307,7 @@ int cagc_tc_conv_multi(cudaStream_t stream, const ConvP* ph, int nphase, const c
         if (e != cudaSuccess) { *rc = fail((int)e, "%s: cudaFuncSetAttribute failed: %s", what, cudaGetErrorString(e)); return 1; }
         device_once_done(attr_set);
     }
-    conv_tc_persist_kernel<<<kNumSMs, kThreads, smem, stream>>>(map_a, map_b, p);
+    conv_tc_persist_kernel<<<kNumSMs, kThreadsPersist, smem, stream>>>(map_a, map_b, p);
     *rc = launched(what);
     return 1;
 }
