@@ -798,7 +798,7 @@ struct HaloParams {
 
 constexpr int kHaloMaxB = 8;
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreadsPersist, 1)
 conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const __grid_constant__ HaloParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -827,7 +827,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         for (int s = 0; s < SB; ++s) { mbar_init(bfull(s), 1); mbar_init(bempty(s), 1); }
         for (int a = 0; a < 2; ++a) {
             mbar_init(afull(a), 1); mbar_init(aempty(a), 1);
-            mbar_init(tfull(a), 1); mbar_init(tempty(a), 4);
+            mbar_init(tfull(a), 1); mbar_init(tempty(a), 8);      // 8 epilogue warps
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -943,7 +943,9 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             if (++acc == p.acc_bufs) { acc = 0; tph ^= 1u; }
         }
     } else {
-        const int q = warp & 3;
+        const int q = warp & 3;                   // TMEM lane quarter; warps w and w + 4 share it (see epi_rows_pair)
+        const int part = (warp - 2) >> 2;
+        float* const my_stage = epi_stage_base ? epi_stage_base + (warp - 2) * 512 : nullptr;
         const int m = q * 32 + lane;
         const float nwv = p.noise ? __ldg(p.noise_w) : 0.f;
         const EpiArgs ea{p.out_scale, p.bias, p.residual, p.out, p.n_pitch, p.out_valid, p.act, p.noise != nullptr, p.act_gain};
@@ -980,7 +982,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 const int yy = oy * p.out_stride + p.out_oy, xx = ox * p.out_stride + p.out_ox;
                 const float nz = nzs[j];
                 const int64_t roff = (((int64_t)b * p.Hout + yy) * p.Wout + xx) * p.n_pitch;
-                epi_rows(ea, (epi_stage_base ? epi_stage_base + q * 1024 : nullptr), d0 + (uint32_t)(j * p.n_tile), lane, n0, n_mma, pvalid, roff, nz, b);
+                epi_rows_pair(ea, my_stage, d0 + (uint32_t)(j * p.n_tile), lane, n0, n_mma, pvalid, roff, nz, b, part);
             }
             tc_fence_before();
             __syncwarp();
@@ -2044,7 +2046,7 @@ static int try_halo_conv(cudaStream_t stream, const ConvP& c, const char* what, 
     const size_t smem = 2 * (size_t)p.a_stride + (size_t)p.b_stages * p.b_bytes + 1024 + epi_bytes;
     const int64_t items = (int64_t)p.strips * p.ytiles * c.B * n_tiles;
     const unsigned grid = (unsigned)std::min<int64_t>(items, kNumSMs);
-    conv_tc_halo_kernel<<<grid, kThreads, smem, stream>>>(map_a, map_b, p);
+    conv_tc_halo_kernel<<<grid, kThreadsPersist, smem, stream>>>(map_a, map_b, p);
     *rc = launched(what);
     return 1;
 }
