@@ -583,6 +583,7 @@ class _EqualLinearFn(Function):
                                       n_in, scale, lr_mul, int(act), 0.2, math.sqrt(2)), 'linear_fwd')
         ctx.save_for_backward(x2, w, out if act else None)
         ctx.cfg = (scale, lr_mul, act, bias is not None, x.shape)
+        ctx.weight_param = weight        # identity key of the transposed copy the backward caches for frozen weights
         return out.reshape(*x.shape[:-1], n_out)
 
     @staticmethod
@@ -604,9 +605,15 @@ class _EqualLinearFn(Function):
             check(lib.cagc_linear_bias_act_bwd(st, g2.data_ptr(), ptr(out), g_acc.data_ptr(), ptr(g_bias),
                                                m, n_out, scale, lr_mul, int(act), 0.2, math.sqrt(2)),
                   'linear_bias_act_bwd')
-            if need_x or need_w:
-                check(lib.cagc_linear_bwd(st, g_acc.data_ptr(), x2.data_ptr(), w.data_ptr(), ptr(g_x), ptr(g_w), m, n_out,
-                                          n_in), 'linear_bwd')
+            if need_x:
+                # g_x = g_acc @ W is the forward kernel on W^T (one warp per output feature streaming a contiguous row);
+                # the column-strided form (cagc_linear_bwd's g_x) left 16 blocks walking 512 dependent steps: 86 us
+                wt = cached_frozen(ctx.weight_param, ('eqlin_t',), lambda: w.t().contiguous())
+                check(lib.cagc_linear_fwd(st, g_acc.data_ptr(), wt.data_ptr(), None, g_x.data_ptr(), m, n_in, n_out,
+                                          1.0, 0.0, 0, 0.2, 1.0), 'linear_bwd_x')
+            if need_w:
+                check(lib.cagc_linear_bwd(st, g_acc.data_ptr(), x2.data_ptr(), w.data_ptr(), None, ptr(g_w), m, n_out,
+                                          n_in), 'linear_bwd_w')
         return (g_x.reshape(xshape) if need_x else None), g_w, g_bias, None, None, None
 
 
