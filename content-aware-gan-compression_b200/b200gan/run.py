@@ -200,9 +200,30 @@ def _patch_saliency(synthetic_mask: bool, engine: str):
     from b200gan import config
     import Util.content_aware_pruning as cap
     if synthetic_mask:
-        # parsing > 0 and != 16 inside the ellipse (prune.py -> :236), 512x512 as Extract_Face_Mask returns (:38-58)
-        cap.Get_Parsing_Net = lambda device: (None, None)
-        cap.Extract_Face_Mask = lambda pil_image, parsing_net, to_tensor, device: _ellipse(512).astype(np.int64)
+        # A stand-in for BiSeNet with the same call contract (`parsing_net(x)[0]` = class scores [B,19,H,W]): class 1
+        # inside the centred ellipse, class 0 outside.  Extract_Face_Mask (:38-58), Batch_Img_Parsing (:61-88) and
+        # Get_Masked_Tensor (:90-117) then run unmodified on it.
+        import torch
+        from torchvision import transforms
+
+        class SyntheticParser:
+            def __call__(self, x):
+                b, _, h, w = x.shape
+                inside = torch.from_numpy(_ellipse(h)).to(x.device)
+                out = torch.zeros(b, 19, h, w, device=x.device)
+                out[:, 1] = inside
+                out[:, 0] = ~inside
+                return (out,)
+
+            def eval(self):
+                return self
+
+            def to(self, *a, **k):
+                return self
+
+        to_tensor = transforms.Compose([transforms.ToTensor(),
+                                        transforms.Normalize((0.485, 0.456, 0.406), (0.229, 0.224, 0.225))])
+        cap.Get_Parsing_Net = lambda device: (SyntheticParser(), to_tensor)
     if engine != 'default':
         algo = {'fp32': config.ALGO_SIMT_FP32, 'tf32': config.ALGO_TCGEN05_TF32,
                 '3xtf32': getattr(config, 'ALGO_TCGEN05_3XTF32', config.ALGO_SIMT_FP32)}[engine]
@@ -244,7 +265,7 @@ def main(argv=None):
     if args.synthetic_fid_stats:
         _synthetic_fid_stats(script_dir)
     name = os.path.basename(script)
-    if name in ('prune.py',) or args.synthetic_mask:
+    if name in ('prune.py', 'train.py') or args.synthetic_mask:
         _patch_saliency(args.synthetic_mask, args.saliency_engine)
     if args.seed is not None:
         import numpy as np

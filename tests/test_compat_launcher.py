@@ -112,3 +112,37 @@ def test_unmodified_get_fid_and_get_ppl_run(tmp_path):
                       '--batch_size', '8'], tmp)
     ppl_line = [ln for ln in out.splitlines() if ln.startswith('PPL Scores:')]
     assert ppl_line and np.isfinite(float(ppl_line[0].split(':')[1])), out[-500:]
+
+
+def test_unmodified_train_py_two_iterations(tmp_path):
+    """train.py (D step, R1 with double backward at iteration 0, G/KD step with the content mask glue and LPIPS,
+    path-length regulariser at iteration 0, EMA, sample grid) for two iterations on a synthetic image folder and
+    synthetic checkpoints; VGG16 / the parser are random-init / synthetic (no network)."""
+    import model
+    from PIL import Image
+    tmp = str(tmp_path)
+    size, shape = 64, [48, 48, 48, 48, 48, 48, 40, 40, 32, 32]
+    student = synth.load_synth(model.Generator(size, 512, 8, generator_net_shape=shape), 71)
+    teacher = synth.load_synth(model.Generator(size, 512, 8, generator_net_shape=[64] * 10), 72)
+    disc = synth.load_synth(model.Discriminator(size), 73)
+    torch.save({'g': student.state_dict(), 'g_ema': student.state_dict(), 'd': disc.state_dict()}, os.path.join(tmp, 'student.pt'))
+    torch.save({'g_ema': teacher.state_dict()}, os.path.join(tmp, 'teacher.pt'))
+    data = os.path.join(tmp, 'data')
+    os.makedirs(data)
+    rs = np.random.RandomState(0)
+    for i in range(8):
+        Image.fromarray(rs.randint(0, 255, (size, size, 3), dtype=np.uint8)).save(os.path.join(data, f'{i:03d}.png'))
+    out, err = _launch(['--seed', '3', '--synthetic-mask', '--cwd', tmp, os.path.join(REF, 'train.py'), '--path', data,
+                        '--size', str(size), '--ckpt', os.path.join(tmp, 'student.pt'), '--teacher_ckpt',
+                        os.path.join(tmp, 'teacher.pt'), '--iter', '2', '--batch_size', '4', '--n_sample', '4'], tmp,
+                       timeout=1200)
+    logs = glob.glob(os.path.join(tmp, 'Exp_*', '*_training_log.out'))
+    assert len(logs) == 1, (out[-1000:], err[-2000:])
+    text = open(logs[0]).read()
+    lines = [ln for ln in text.splitlines() if ln.startswith('Iter #:')]
+    assert len(lines) == 2, text[-1500:]
+    for ln in lines:
+        vals = [float(tok) for tok in ln.replace(':', ' ').split() if tok.replace('.', '', 1).replace('-', '', 1).isdigit()]
+        assert all(np.isfinite(v) for v in vals), ln
+    assert 'Total training time' in text
+    assert glob.glob(os.path.join(tmp, 'Exp_*', 'sample', '000000.png'))
