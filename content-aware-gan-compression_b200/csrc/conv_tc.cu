@@ -1658,6 +1658,38 @@ __global__ void __launch_bounds__(256, 2) fir_nhwc_stream_kernel(const __grid_co
     int s = 0, prev_s = 0;
     uint32_t ph = 0, prev_ph = 0;
 
+    // register rings of the per-row side inputs: output row o (completed by input row r = o + KH - 1, Q = r mod KH) uses
+    // noise slot Q and mask slot Q mod 2
+    float nzr[4][PXT];
+    float4 mrr[2][PXT];
+#pragma unroll
+    for (int pp = 0; pp < PXT; ++pp) {
+        nzr[0][pp] = nzr[1][pp] = nzr[2][pp] = nzr[3][pp] = 0.f;
+        mrr[0][pp] = mrr[1][pp] = make_float4(1.f, 1.f, 1.f, 1.f);
+    }
+    int nz_left = p.noise ? rows_out : 0, mr_left = p.mask_ref ? rows_out : 0;
+    const float* mptr = p.mask_ref ? p.mask_ref + (optr - p.out) : nullptr;
+    auto nz_req = [&](float (&dst)[PXT]) {
+        if (nz_left > 0) {
+#pragma unroll
+            for (int pp = 0; pp < PXT; ++pp)
+                if (ok[pp]) dst[pp] = __ldg(nptr + pp);
+            nptr += p.out_w;
+            --nz_left;
+        }
+    };
+    auto mr_req = [&](float4 (&dst)[PXT]) {
+        if (mr_left > 0) {
+#pragma unroll
+            for (int pp = 0; pp < PXT; ++pp)
+                if (ok[pp]) dst[pp] = ldg4(mptr + (int64_t)pp * p.pitch);
+            mptr += orow;
+            --mr_left;
+        }
+    };
+    nz_req(nzr[3]); nz_req(nzr[0]); nz_req(nzr[1]);       // output rows 0, 1, 2
+    mr_req(mrr[1]);                                       // output row 0
+
     // one input row; Q = r mod KH (compile time), FIRST = the first KH rows of the segment (r == Q)
     auto row = [&](int r, auto qc, auto firstc) {
         constexpr int Q = decltype(qc)::value;
@@ -1668,24 +1700,12 @@ __global__ void __launch_bounds__(256, 2) fir_nhwc_stream_kernel(const __grid_co
             mbar_expect_tx(full_bar(st), stage_bytes);
             tma_load_4d(base_u32 + (uint32_t)st * p.stage_stride, map, full_bar(st), c0, tx_c, ty_c + r + S - 1, b);
         }
-        // noise of the output row this input row completes: requested before the wait, consumed after the FMAs
-        float nz[PXT];
-#pragma unroll
-        for (int pp = 0; pp < PXT; ++pp) nz[pp] = 0.f;
-        if ((!FIRST || Q == KH - 1) && p.noise) {
-#pragma unroll
-            for (int pp = 0; pp < PXT; ++pp)
-                if (ok[pp]) nz[pp] = __ldg(nptr + pp);
-            nptr += p.out_w;
-        }
-        // activation-mask reference of the same output row (fused FusedLeakyReLU backward): requested here as well
-        float4 mr[PXT];
-#pragma unroll
-        for (int pp = 0; pp < PXT; ++pp) mr[pp] = make_float4(1.f, 1.f, 1.f, 1.f);
-        if ((!FIRST || Q == KH - 1) && p.mask_ref) {
-#pragma unroll
-            for (int pp = 0; pp < PXT; ++pp)
-                if (ok[pp]) mr[pp] = ldg4(p.mask_ref + (optr - p.out) + (int64_t)pp * p.pitch);
+        // noise / activation-mask reference of LATER output rows: a row of this loop lasts about one DRAM latency, so
+        // the loads are requested three rows (noise) / one row (mask) before the epilogue that consumes them
+        constexpr bool EMIT = !FIRST || Q == KH - 1;
+        if (EMIT) {
+            nz_req(nzr[(Q + 3) % 4]);
+            mr_req(mrr[(Q + 1) % 2]);
         }
         mbar_wait(full_bar(s), ph);
         const float* src = sbase + s * sstride;
@@ -1713,17 +1733,19 @@ __global__ void __launch_bounds__(256, 2) fir_nhwc_stream_kernel(const __grid_co
             for (int pp = 0; pp < PXT; ++pp) {
                 const float2 a0 = acc[(Q + 1) % KH][pp][0], a1 = acc[(Q + 1) % KH][pp][1];
                 acc[(Q + 1) % KH][pp][0] = acc[(Q + 1) % KH][pp][1] = make_float2(0.f, 0.f);
-                float v[4] = {fmaf(a0.x, scale4.x, fmaf(nz[pp], nw, bias4.x)), fmaf(a0.y, scale4.y, fmaf(nz[pp], nw, bias4.y)),
-                              fmaf(a1.x, scale4.z, fmaf(nz[pp], nw, bias4.z)), fmaf(a1.y, scale4.w, fmaf(nz[pp], nw, bias4.w))};
+                const float nzv = nzr[Q][pp];
+                float v[4] = {fmaf(a0.x, scale4.x, fmaf(nzv, nw, bias4.x)), fmaf(a0.y, scale4.y, fmaf(nzv, nw, bias4.y)),
+                              fmaf(a1.x, scale4.z, fmaf(nzv, nw, bias4.z)), fmaf(a1.y, scale4.w, fmaf(nzv, nw, bias4.w))};
                 if (p.act) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], kLreluSlope * v[j]);
                 }
                 if (p.mask_ref) {
-                    v[0] *= mr[pp].x > 0.f ? p.mask_gain : p.mask_gain * kLreluSlope;
-                    v[1] *= mr[pp].y > 0.f ? p.mask_gain : p.mask_gain * kLreluSlope;
-                    v[2] *= mr[pp].z > 0.f ? p.mask_gain : p.mask_gain * kLreluSlope;
-                    v[3] *= mr[pp].w > 0.f ? p.mask_gain : p.mask_gain * kLreluSlope;
+                    const float4 m = mrr[Q % 2][pp];
+                    v[0] *= m.x > 0.f ? p.mask_gain : p.mask_gain * kLreluSlope;
+                    v[1] *= m.y > 0.f ? p.mask_gain : p.mask_gain * kLreluSlope;
+                    v[2] *= m.z > 0.f ? p.mask_gain : p.mask_gain * kLreluSlope;
+                    v[3] *= m.w > 0.f ? p.mask_gain : p.mask_gain * kLreluSlope;
                 }
                 if (edge) {
 #pragma unroll
