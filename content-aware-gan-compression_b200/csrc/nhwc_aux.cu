@@ -132,47 +132,60 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const float* __restrict__ 
     constexpr float kInvNeg = 0.70710678118654752440f / 0.2f;     // 1/(0.2*sqrt2)
 
     const bool flat = (sh == (int64_t)W * sw);      // rows of ga follow each other: no per-pixel division
-#pragma unroll 2
-    for (int p = p_lo + py; p < p_hi; p += PY) {
-        const int64_t off = ((int64_t)b * HW + p) * pitch + c;
-        const float4 a4 = ldg4(a + off);
-        float gav[4];
-        const float* gp;
-        if (flat) {
-            gp = ga + b * sb + (int64_t)p * sw + (int64_t)c * sc;
-        } else {
-            const int y = p / W, x = p - y * W;
-            gp = ga + b * sb + y * sh + x * sw + (int64_t)c * sc;
-        }
-        if (ga_vec) {
-            const float4 t = ld4(gp);
-            gav[0] = t.x; gav[1] = t.y; gav[2] = t.z; gav[3] = t.w;
-        } else {
+    // U pixels per trip: all of their loads are issued before the first use (the kernel is bound by load latency, not
+    // by bytes, when a thread has a single pixel in flight); pixels past the chunk end re-read the thread's first one
+    constexpr int U = 4;
+    for (int p0 = p_lo + py; p0 < p_hi; p0 += U * PY) {
+        float4 a4[U];
+        float gav[U][4], nraw[U];
+        int64_t off[U];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) gav[j] = (c + j < valid) ? gp[j * sc] : 0.f;
-        }
-        const float nz = noise ? nw * __ldg(noise + (int64_t)b * noise_bstride + p) : 0.f;
-        const float nraw = noise ? __ldg(noise + (int64_t)b * noise_bstride + p) : 0.f;
-        const float av[4] = {a4.x, a4.y, a4.z, a4.w};
-        float guv[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float gz, yv;
-            if (act) {
-                const bool pos = av[j] > 0.f;
-                gz = gav[j] * (pos ? kSqrt2 : kSqrt2 * kLreluSlope);
-                yv = av[j] * (pos ? kInvPos : kInvNeg) - nz - bv[j];
+        for (int u = 0; u < U; ++u) {
+            const int pu = p0 + u * PY;
+            const int p = pu < p_hi ? pu : p0;
+            off[u] = ((int64_t)b * HW + p) * pitch + c;
+            a4[u] = ldg4(a + off[u]);
+            const float* gp;
+            if (flat) {
+                gp = ga + b * sb + (int64_t)p * sw + (int64_t)c * sc;
             } else {
-                gz = gav[j];
-                yv = av[j] - nz - bv[j];
+                const int y = p / W, x = p - y * W;
+                gp = ga + b * sb + y * sh + x * sw + (int64_t)c * sc;
             }
-            if (c + j >= valid) gz = 0.f;
-            guv[j] = gz * dv[j];
-            s1[j] += gz;
-            s2[j] = fmaf(gz * yv, rdv[j], s2[j]);
-            s3[j] = fmaf(gz, nraw, s3[j]);
+            if (ga_vec) {
+                const float4 t = ld4(gp);
+                gav[u][0] = t.x; gav[u][1] = t.y; gav[u][2] = t.z; gav[u][3] = t.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) gav[u][j] = (c + j < valid) ? gp[j * sc] : 0.f;
+            }
+            nraw[u] = noise ? __ldg(noise + (int64_t)b * noise_bstride + p) : 0.f;
         }
-        st4(gu + off, make_float4(guv[0], guv[1], guv[2], guv[3]));
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (p0 + u * PY >= p_hi) break;
+            const float nz = nw * nraw[u];
+            const float av[4] = {a4[u].x, a4[u].y, a4[u].z, a4[u].w};
+            float guv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float gz, yv;
+                if (act) {
+                    const bool pos = av[j] > 0.f;
+                    gz = gav[u][j] * (pos ? kSqrt2 : kSqrt2 * kLreluSlope);
+                    yv = av[j] * (pos ? kInvPos : kInvNeg) - nz - bv[j];
+                } else {
+                    gz = gav[u][j];
+                    yv = av[j] - nz - bv[j];
+                }
+                if (c + j >= valid) gz = 0.f;
+                guv[j] = gz * dv[j];
+                s1[j] += gz;
+                s2[j] = fmaf(gz * yv, rdv[j], s2[j]);
+                s3[j] = fmaf(gz, nraw[u], s3[j]);
+            }
+            st4(gu + off[u], make_float4(guv[0], guv[1], guv[2], guv[3]));
+        }
     }
     red[(py * 3 + 0) * c4n + cx] = make_float4(s1[0], s1[1], s1[2], s1[3]);
     red[(py * 3 + 1) * c4n + cx] = make_float4(s2[0], s2[1], s2[2], s2[3]);
@@ -199,17 +212,26 @@ __global__ void __launch_bounds__(256) mod_bwd_kernel(float* __restrict__ gxt, c
     const int p_lo = chunk * per, p_hi = min(HW, p_lo + per);
     const float4 s4 = ldg4(s + (int64_t)b * pitch + c);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-    for (int p = p_lo + py; p < p_hi; p += PY) {
-        const int64_t off = ((int64_t)b * HW + p) * pitch + c;
-        float4 g = ld4(gxt + off);
-        const float4 xv = ldg4(x + off);
-        acc.x = fmaf(g.x, xv.x, acc.x);
-        acc.y = fmaf(g.y, xv.y, acc.y);
-        acc.z = fmaf(g.z, xv.z, acc.z);
-        acc.w = fmaf(g.w, xv.w, acc.w);
-        g.x *= s4.x; g.y *= s4.y; g.z *= s4.z; g.w *= s4.w;
-        st4(gxt + off, g);
+    constexpr int U = 4;        // pixels in flight per thread (in-place update: the loads cannot be hoisted by the compiler)
+    for (int p0 = p_lo + py; p0 < p_hi; p0 += U * PY) {
+        float4 g[U], xv[U];
+        int64_t off[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int pu = p0 + u * PY;
+            off[u] = ((int64_t)b * HW + (pu < p_hi ? pu : p0)) * pitch + c;
+            g[u] = ld4(gxt + off[u]);
+            xv[u] = ldg4(x + off[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (p0 + u * PY >= p_hi) break;
+            acc.x = fmaf(g[u].x, xv[u].x, acc.x);
+            acc.y = fmaf(g[u].y, xv[u].y, acc.y);
+            acc.z = fmaf(g[u].z, xv[u].z, acc.z);
+            acc.w = fmaf(g[u].w, xv[u].w, acc.w);
+            st4(gxt + off[u], make_float4(g[u].x * s4.x, g[u].y * s4.y, g[u].z * s4.z, g[u].w * s4.w));
+        }
     }
     red[py * c4n + cx] = acc;
     __syncthreads();
@@ -224,11 +246,15 @@ __global__ void __launch_bounds__(256) mod_bwd_kernel(float* __restrict__ gxt, c
 }
 
 // ------------------------------------------------------------------------------------------------
-// ToRGB forward: 8 lanes per pixel, 4 pixels per warp step, effective weights in shared memory
+// ToRGB forward: L lanes per pixel (a power of two, chosen so that a lane owns at most 8 float4 of its pixel), one
+// pixel per lane group and step.  All of a lane's loads are issued before the first FMA (the op is bound by load
+// latency, not by bytes or math); the effective weights (c * W * s, per sample) sit in shared memory and are read as
+// broadcasts; the lane groups of a warp cover consecutive pixels, so the NCHW stores are coalesced.
 // ------------------------------------------------------------------------------------------------
 constexpr int kRgbMaxOut = 4;
-constexpr int kRgbChunk = 256;  // pixels per CTA
+constexpr int kRgbLoads = 8;    // float4 per lane and pixel
 
+template <int L>
 __global__ void __launch_bounds__(256) torgb_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                         const float* __restrict__ s, const float* __restrict__ bias,
                                                         const float* __restrict__ skip, const float* __restrict__ fir,
@@ -248,91 +274,127 @@ __global__ void __launch_bounds__(256) torgb_fwd_kernel(const float* __restrict_
             sfir[i] = fir[(fh - 1 - ky) * fw + (fw - 1 - kx)];
         }
     __syncthreads();
-    const int lane8 = threadIdx.x & 7;
-    const int grp = threadIdx.x >> 3;  // 32 pixel groups per CTA
+    constexpr int G = 256 / L;                     // pixels per CTA step
+    const int li = threadIdx.x & (L - 1), grp = threadIdx.x / L;
     const int c4n = pitch >> 2;
     const int p_lo = blockIdx.x * chunk;
     const int p_hi = min(HW, p_lo + chunk);
     const int Hs = H >> 1, Ws = W >> 1;
-    // two pixels per 8-lane group and step: 8 independent 128-bit loads in flight per lane before the first FMA
-    // (the kernel is bound by load latency, not by bytes), and each effective-weight read serves both pixels
-    for (int pbase = p_lo; pbase < p_hi; pbase += 64) {  // warp-uniform trip count (shuffles below)
-        const int pa = pbase + grp, pb = pbase + 32 + grp;
-        const bool va = pa < p_hi, vb = pb < p_hi;
-        const float* xa = x + ((int64_t)b * HW + (va ? pa : p_lo)) * pitch;
-        const float* xb = x + ((int64_t)b * HW + (vb ? pb : p_lo)) * pitch;
-        float acc[2][kRgbMaxOut] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-        for (int c4b = lane8; c4b < c4n; c4b += 32) {
-            float4 ra[4], rb[4];
+    constexpr int NO = (kRgbMaxOut + L - 1) / L;   // outputs finished by one lane: o = li + L * k
+    const bool fast_skip = skip && fh <= 4 && fw <= 4;
+
+    // everything one pixel needs from global memory
+    struct Px {
+        float4 r[kRgbLoads];
+        float skw[4], skv[NO][4];
+    };
+    // request pixel p: the lane's float4s of the activation, and the 2 x 2 skip samples per output that meet a non-zero tap
+    // (Upsample(skip): zero-insert x2, pad (pad0, .), true convolution with fir, model.py:38-56 -- only every other tap of
+    // a 4 x 4 kernel meets a sample of the zero-inserted signal)
+    auto request = [&](int p, Px& q) {
+        const bool pv = p < p_hi;
+        const float* xp = x + ((int64_t)b * HW + (pv ? p : p_lo)) * pitch;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int c4 = c4b + 8 * u;
-                ra[u] = c4 < c4n ? ldg4(xa + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-                rb[u] = c4 < c4n ? ldg4(xb + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int u = 0; u < kRgbLoads; ++u) {
+            const int c4 = li + L * u;
+            q.r[u] = c4 < c4n ? ldg4(xp + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int k = 0; k < NO; ++k) q.skv[k][0] = q.skv[k][1] = q.skv[k][2] = q.skv[k][3] = 0.f;
+        q.skw[0] = q.skw[1] = q.skw[2] = q.skw[3] = 0.f;
+        if (fast_skip && pv) {
+            const int y = p / W, xx = p - y * W;
+            const int i0 = (pad0 - y) & 1, j0 = (pad0 - xx) & 1;
+            int idx[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int i = i0 + 2 * (t >> 1), j = j0 + 2 * (t & 1);
+                const int sy = (y + i - pad0) >> 1, sx = (xx + j - pad0) >> 1;   // arithmetic shift: negative stays negative
+                const bool ok = i < fh && j < fw && sy >= 0 && sy < Hs && sx >= 0 && sx < Ws;
+                q.skw[t] = ok ? sfir[i * fw + j] : 0.f;
+                idx[t] = ok ? sy * Ws + sx : 0;
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int c4 = c4b + 8 * u;
-                if (c4 < c4n) {
+            for (int k = 0; k < NO; ++k) {
+                const int o = li + L * k;
+                if (o < nout) {
+                    const float* sp = skip + ((int64_t)b * nout + o) * Hs * Ws;
 #pragma unroll
-                    for (int o = 0; o < kRgbMaxOut; ++o) {
-                        if (o < nout) {
-                            const float4 wv = ld4(&weff[o * pitch + c4 * 4]);
-                            acc[0][o] = fmaf(ra[u].x, wv.x, acc[0][o]);
-                            acc[0][o] = fmaf(ra[u].y, wv.y, acc[0][o]);
-                            acc[0][o] = fmaf(ra[u].z, wv.z, acc[0][o]);
-                            acc[0][o] = fmaf(ra[u].w, wv.w, acc[0][o]);
-                            acc[1][o] = fmaf(rb[u].x, wv.x, acc[1][o]);
-                            acc[1][o] = fmaf(rb[u].y, wv.y, acc[1][o]);
-                            acc[1][o] = fmaf(rb[u].z, wv.z, acc[1][o]);
-                            acc[1][o] = fmaf(rb[u].w, wv.w, acc[1][o]);
-                        }
+                    for (int t = 0; t < 4; ++t) q.skv[k][t] = __ldg(sp + idx[t]);
+                }
+            }
+        }
+    };
+    // dot products, reduction over the pixel's lanes, bias, skip, store
+    auto finish = [&](int p, const Px& q) {
+        float acc[kRgbMaxOut] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int u = 0; u < kRgbLoads; ++u) {
+            const int c4 = li + L * u;
+            if (c4 < c4n) {
+#pragma unroll
+                for (int o = 0; o < kRgbMaxOut; ++o) {
+                    if (o < nout) {
+                        const float4 wv = ld4(&weff[o * pitch + c4 * 4]);
+                        acc[o] = fmaf(q.r[u].x, wv.x, acc[o]);
+                        acc[o] = fmaf(q.r[u].y, wv.y, acc[o]);
+                        acc[o] = fmaf(q.r[u].z, wv.z, acc[o]);
+                        acc[o] = fmaf(q.r[u].w, wv.w, acc[o]);
                     }
                 }
             }
         }
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
+        for (int o = 0; o < kRgbMaxOut; ++o)
 #pragma unroll
-            for (int o = 0; o < kRgbMaxOut; ++o) {
-                acc[h][o] += __shfl_xor_sync(0xffffffffu, acc[h][o], 4);
-                acc[h][o] += __shfl_xor_sync(0xffffffffu, acc[h][o], 2);
-                acc[h][o] += __shfl_xor_sync(0xffffffffu, acc[h][o], 1);
-            }
-        // lanes 0 .. nout-1 of a group finish pixel a, lanes 4 .. 4+nout-1 pixel b
-        const int half = lane8 >> 2, o = lane8 & 3;
-        const int p = half ? pb : pa;
-        if ((half ? vb : va) && o < nout) {
-            float v = acc[0][0];
+            for (int m = L >> 1; m >= 1; m >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], m);
+        if (p >= p_hi) return;
 #pragma unroll
-            for (int h = 0; h < 2; ++h)
+        for (int k = 0; k < NO; ++k) {
+            const int o = li + L * k;
+            if (o >= nout) continue;
+            float v = acc[0];
 #pragma unroll
-                for (int q = 0; q < kRgbMaxOut; ++q)
-                    if (half == h && o == q) v = acc[h][q];
+            for (int qo = 1; qo < kRgbMaxOut; ++qo)
+                if (o == qo) v = acc[qo];
             if (bias) v += __ldg(bias + o);
-            const int y = p / W, xx = p - y * W;
-            if (skip) {
-                // Upsample(skip): zero-insert x2, pad (pad0, .), true convolution with fir (model.py:38-56)
+            if (fast_skip) {
+                float uacc = 0.f;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) uacc = fmaf(q.skw[t], q.skv[k][t], uacc);
+                v += uacc;
+            } else if (skip) {
+                const int y = p / W, xx = p - y * W;
                 const float* sp = skip + ((int64_t)b * nout + o) * Hs * Ws;
-                // only every other tap meets a non-zero sample of the zero-inserted signal: start at the first
-                // tap index of the right parity and step by 2 (fh x fw = 4 x 4 -> 2 x 2 loads per output)
-                float u = 0.f;
+                float uacc = 0.f;
                 const int i0 = (pad0 - y) & 1, j0 = (pad0 - xx) & 1;
                 for (int i = i0; i < fh; i += 2) {
-                    const int sy = (y + i - pad0) >> 1;          // arithmetic shift: negative stays negative
+                    const int sy = (y + i - pad0) >> 1;
                     if (sy < 0) continue;
                     if (sy >= Hs) break;
                     for (int j = j0; j < fw; j += 2) {
                         const int sx = (xx + j - pad0) >> 1;
                         if (sx < 0) continue;
                         if (sx >= Ws) break;
-                        u = fmaf(sfir[i * fw + j], __ldg(sp + sy * Ws + sx), u);
+                        uacc = fmaf(sfir[i * fw + j], __ldg(sp + sy * Ws + sx), uacc);
                     }
                 }
-                v += u;
+                v += uacc;
             }
             out[((int64_t)b * nout + o) * HW + p] = v;
         }
+    };
+
+    // two pixels in flight per lane group: the loads of step k+1 are requested before step k is finished, into the buffer
+    // step k-1 has released (no register moves that would wait for a pending load); trip counts are warp-uniform
+    Px qa, qb;
+    request(p_lo + grp, qa);
+    for (int pbase = p_lo; pbase < p_hi; pbase += 2 * G) {
+        if (pbase + G < p_hi) request(pbase + G + grp, qb);
+        finish(pbase + grp, qa);
+        if (pbase + G >= p_hi) break;
+        if (pbase + 2 * G < p_hi) request(pbase + 2 * G + grp, qa);
+        finish(pbase + G + grp, qb);
     }
 }
 
@@ -362,29 +424,42 @@ __global__ void __launch_bounds__(256) torgb_bwd_kernel(const float* __restrict_
         we[o] = make_float4(t[0], t[1], t[2], t[3]);
         T[o] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    for (int p = p_lo + py; p < p_hi; p += PY) {
-        const int64_t off = ((int64_t)b * HW + p) * pitch + c;
-        const float4 xv = ld4(x + off);
-        float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    constexpr int U = 4;        // pixels in flight per thread
+    for (int p0 = p_lo + py; p0 < p_hi; p0 += U * PY) {
+        float4 xv[U], ev[U];
+        float gv[U][kRgbMaxOut];
+        int64_t off[U];
 #pragma unroll
-        for (int o = 0; o < kRgbMaxOut; ++o) {
-            if (o < nout) {
-                const float gv = __ldg(g + ((int64_t)b * nout + o) * HW + p);
-                o4.x = fmaf(we[o].x, gv, o4.x);
-                o4.y = fmaf(we[o].y, gv, o4.y);
-                o4.z = fmaf(we[o].z, gv, o4.z);
-                o4.w = fmaf(we[o].w, gv, o4.w);
-                T[o].x = fmaf(gv, xv.x, T[o].x);
-                T[o].y = fmaf(gv, xv.y, T[o].y);
-                T[o].z = fmaf(gv, xv.z, T[o].z);
-                T[o].w = fmaf(gv, xv.w, T[o].w);
+        for (int u = 0; u < U; ++u) {
+            const int pu = p0 + u * PY;
+            const int p = pu < p_hi ? pu : p0;
+            off[u] = ((int64_t)b * HW + p) * pitch + c;
+            xv[u] = ld4(x + off[u]);
+            ev[u] = gx_add ? ld4(gx_add + off[u]) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int o = 0; o < kRgbMaxOut; ++o) gv[u][o] = o < nout ? __ldg(g + ((int64_t)b * nout + o) * HW + p) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (p0 + u * PY >= p_hi) break;
+            float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int o = 0; o < kRgbMaxOut; ++o) {
+                if (o < nout) {
+                    o4.x = fmaf(we[o].x, gv[u][o], o4.x);
+                    o4.y = fmaf(we[o].y, gv[u][o], o4.y);
+                    o4.z = fmaf(we[o].z, gv[u][o], o4.z);
+                    o4.w = fmaf(we[o].w, gv[u][o], o4.w);
+                    T[o].x = fmaf(gv[u][o], xv[u].x, T[o].x);
+                    T[o].y = fmaf(gv[u][o], xv[u].y, T[o].y);
+                    T[o].z = fmaf(gv[u][o], xv[u].z, T[o].z);
+                    T[o].w = fmaf(gv[u][o], xv[u].w, T[o].w);
+                }
             }
+            // gradient that reached the same activation through its other consumer (the next conv)
+            o4.x += ev[u].x; o4.y += ev[u].y; o4.z += ev[u].z; o4.w += ev[u].w;
+            st4(gx + off[u], o4);
         }
-        if (gx_add) {   // gradient that reached the same activation through its other consumer (the next conv)
-            const float4 e = ld4(gx_add + off);
-            o4.x += e.x; o4.y += e.y; o4.z += e.z; o4.w += e.w;
-        }
-        st4(gx + off, o4);
     }
 #pragma unroll
     for (int o = 0; o < kRgbMaxOut; ++o)
@@ -438,7 +513,10 @@ __global__ void __launch_bounds__(256) bias_act_bwd_rows_kernel(const float* __r
 }
 
 static inline int pixel_chunks(int HW) {
-    int c = ceil_div(HW, HW >= 16384 ? kChunkPixels : 256);
+    // pixels per CTA: 1024 at >= 256^2, shrinking with the image so that the low-resolution layers still fill the GPU
+    // (16 CTAs x 1024-pixel serial loops made the 4^2 .. 32^2 layers 30-50 us each: pure latency)
+    const int per = HW >= 65536 ? kChunkPixels : HW >= 16384 ? 512 : HW >= 4096 ? 256 : 64;
+    int c = ceil_div(HW, per);
     if (c < 1) c = 1;
     if (c > 128) c = 128;
     return c;
@@ -598,13 +676,28 @@ int cagc_torgb_fwd(cagc_stream_t stream_, const float* x, const float* w, const 
     CAGC_REQUIRE(B <= 65535, "torgb_fwd: batch too large");
     const size_t smem = sizeof(float) * nout * pitch;
     CAGC_REQUIRE(smem <= 48 * 1024, "torgb_fwd: pitch too large");
-    // pixels per CTA: enough to amortise the per-CTA effective-weight set-up, while keeping >= ~4 CTAs per SM
-    int chunk = kRgbChunk;
-    static const int max_chunk = [] { const char* e = getenv("CAGC_RGB_CHUNK"); return e ? atoi(e) : 2048; }();
-    while (chunk < max_chunk && (int64_t)ceil_div(H * W, chunk * 2) * B >= 4 * kNumSMs) chunk *= 2;
+    // lanes per pixel: at most kRgbLoads float4 per lane
+    int L = 1;
+    while (L < 32 && (pitch / 4 + L - 1) / L > kRgbLoads) L *= 2;
+    // pixels per CTA: a multiple of the 256 / L pixels of one step, up to 16 steps (amortises the per-CTA effective-weight
+    // set-up) while the grid keeps >= ~4 CTAs per SM
+    const int G = 256 / L;
+    int64_t steps = ((int64_t)H * W * B) / ((int64_t)G * 4 * kNumSMs);
+    steps = steps < 1 ? 1 : steps > 16 ? 16 : steps;
+    const int chunk = G * (int)steps;
     dim3 grid(ceil_div(H * W, chunk), B);
-    torgb_fwd_kernel<<<grid, 256, smem, stream>>>(x, w, s, bias, skip, fir, out, H, W, pitch, cin, nout, wscale, fh, fw,
-                                                  pad0, chunk);
+#define CAGC_RGB_LAUNCH(LL)                                                                                              \
+    torgb_fwd_kernel<LL><<<grid, 256, smem, stream>>>(x, w, s, bias, skip, fir, out, H, W, pitch, cin, nout, wscale, fh, \
+                                                      fw, pad0, chunk)
+    switch (L) {
+        case 1: CAGC_RGB_LAUNCH(1); break;
+        case 2: CAGC_RGB_LAUNCH(2); break;
+        case 4: CAGC_RGB_LAUNCH(4); break;
+        case 8: CAGC_RGB_LAUNCH(8); break;
+        case 16: CAGC_RGB_LAUNCH(16); break;
+        default: CAGC_RGB_LAUNCH(32); break;
+    }
+#undef CAGC_RGB_LAUNCH
     return launched("torgb_fwd_kernel");
 }
 
