@@ -15,8 +15,9 @@ import weakref
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), 'lib', 'libcagc_b200.so')
-ABI_VERSION = 18
+# CAGC_LIB: another build of the same library (A/B timing of two revisions on one box, scripts/build_rev.sh)
+LIB_PATH = os.environ.get('CAGC_LIB') or os.path.join(os.path.dirname(_HERE), 'lib', 'libcagc_b200.so')
+ABI_VERSION = 19
 
 _p = C.c_void_p
 _i = C.c_int
@@ -38,6 +39,7 @@ SIGNATURES = {
     'cagc_conv_same': (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _l, _i, _i]),
     'cagc_modulate': (_i, [_p, _p, _p, _p, _i, _i, _i, _i]),
     'cagc_conv_up': (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i]),
+    'cagc_conv_up_ws': (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _l]),
     'cagc_conv_up_dgrad': (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i]),
     'cagc_conv_wgrad_splits': (_i, [_i, _i, _i, _i, _i, _i, _i]),
     'cagc_conv_wgrad': (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i]),

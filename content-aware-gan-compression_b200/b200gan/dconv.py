@@ -148,9 +148,11 @@ class _ResBlockFn(Function):
                   'resblock.act2^T')
             gt = _empty(b, ht, wt, pin, dev)
             algo2 = config.ALGO_TCGEN05_TF32 if tc2d else config.ALGO_SIMT_FP32
+            ws, ws_bytes = conv_workspace(b, ht, wt, pin, dev) if tc2d else (None, 0)
             _timed(f'dconv_up[algo{algo2}]', 2.0 * b * ho * wo * pin * cout * 9, 4.0 * b * (ho * wo * pout + ht * wt * pin),
-                   lambda: check(lib.cagc_conv_up(st, gz2.data_ptr(), p2.w_dgrad.data_ptr(), None, gt.data_ptr(), b, ho, wo,
-                                                  pout, pin, 3, algo2), 'resblock.conv2^T'))
+                   lambda: check(lib.cagc_conv_up_ws(st, gz2.data_ptr(), p2.w_dgrad.data_ptr(), None, gt.data_ptr(), b, ho, wo,
+                                                     pout, pin, 3, algo2, ptr(ws), ws_bytes), 'resblock.conv2^T'))
+            del ws
             del gz2
             q0, q1 = 4 - pad2[0] - 1, h - ht + pad2[0]
             firf = _flipped(fir2)

@@ -259,10 +259,13 @@ class _StyledConvFn(Function):
                 out = torch.empty((b, ho, wo, pout), device=dev, dtype=torch.float32)
                 if out.numel():
                     flops = 2.0 * b * h * w * cin * cout * k * k          # transposed conv counted at input res
+                    ws, ws_bytes = conv_workspace(b, hu, wu, pout, dev) if tc else (None, 0)
                     _timed(f'conv_up[algo{falgo}]', flops, 4.0 * b * (h * w * cin + hu * wu * cout),
-                           lambda: check(lib.cagc_conv_up(st, x_in.data_ptr(), w_fwd.data_ptr(), s_arg,
-                                                          ut.data_ptr(), b, h, w, pin, pout, k, falgo), 'conv_up'),
+                           lambda: check(lib.cagc_conv_up_ws(st, x_in.data_ptr(), w_fwd.data_ptr(), s_arg,
+                                                             ut.data_ptr(), b, h, w, pin, pout, k, falgo, ptr(ws), ws_bytes),
+                                         'conv_up'),
                            shape=f'{cin}->{cout}x{h}x{w}')
+                    del ws
                     _timed('fir_nhwc', 0.0, 4.0 * b * cout * (hu * wu + ho * wo),
                            lambda: fir_nhwc(st, ut.data_ptr(), fir, d_p, noise, nw, bias_p, out.data_ptr(), b, hu, wu,
                                             pout, cout, (pad[0], pad[1], pad[0], pad[1]), nstride, int(act), 'fir_nhwc'),

@@ -40,6 +40,8 @@ struct ConvP {
 int cagc_tc_conv(cudaStream_t stream, const cagc::ConvP& p, const char* what);
 // several phases (output parities of the transposed convolution) in one persistent launch; 1 = handled (*rc)
 int cagc_tc_conv_multi(cudaStream_t stream, const cagc::ConvP* phases, int nphase, const char* what, int* rc);
+int cagc_tc_conv_multi_splitk(cudaStream_t stream, const cagc::ConvP* phases, int nphase, float* workspace,
+                              int64_t workspace_bytes, const char* what, int* rc);
 // weight gradient on the tensor pipe; `a` is the pre-modulated layer input; returns the number of splits used
 int cagc_tc_wgrad_splits(int B, int H, int W, int a_pitch, int g_pitch, int ksize);
 int cagc_tc_wgrad(cudaStream_t stream, const float* a, const float* g, float* partial, int* nsplits_io, int B, int H,

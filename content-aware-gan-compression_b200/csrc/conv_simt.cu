@@ -293,9 +293,9 @@ extern "C" {
 
 int64_t cagc_conv_workspace_bytes(int B, int Ho, int Wo, int out_pitch) {
     // split-K scratch of the tensor-pipe engine: up to 16 partial slabs of the output (at most 64 MB); only layers too small to fill the
-    // machine ever use it (<= 64 pixel tiles), so anything large answers 0 and is never split
+    // machine ever use it (<= 256 pixel tiles), so anything large answers 0 and is never split
     const int64_t pixels = (int64_t)B * Ho * Wo;
-    if (pixels <= 0 || pixels > 64 * 128) return 0;
+    if (pixels <= 0 || pixels > 256 * 128) return 0;
     const int64_t slab = pixels * out_pitch * (int64_t)sizeof(float);
     return std::min<int64_t>(16 * slab, std::max<int64_t>(2 * slab, 64ll << 20));
 }
@@ -330,8 +330,14 @@ int cagc_conv_same_ws(cagc_stream_t stream_, const float* in, const float* w_sla
     return launch_conv(stream, p, "conv_same[simt]");
 }
 
-int cagc_conv_up(cagc_stream_t stream_, const float* in, const float* w_slabs, const float* in_scale, float* out_t,
+int cagc_conv_up(cagc_stream_t stream, const float* in, const float* w_slabs, const float* in_scale, float* out_t,
                  int B, int H, int W, int in_pitch, int out_pitch, int ksize, int algo) {
+    return cagc_conv_up_ws(stream, in, w_slabs, in_scale, out_t, B, H, W, in_pitch, out_pitch, ksize, algo, nullptr, 0);
+}
+
+int cagc_conv_up_ws(cagc_stream_t stream_, const float* in, const float* w_slabs, const float* in_scale, float* out_t,
+                    int B, int H, int W, int in_pitch, int out_pitch, int ksize, int algo, float* workspace,
+                    int64_t workspace_bytes) {
     cudaStream_t stream = (cudaStream_t)stream_;
     CAGC_TRY(check_nhwc("conv_up", B, H, W, in_pitch, out_pitch, ksize));
     CAGC_REQUIRE(in && w_slabs && out_t, "conv_up: null pointer");
@@ -354,9 +360,12 @@ int cagc_conv_up(cagc_stream_t stream_, const float* in, const float* w_slabs, c
         }
     // wide layers on the tensor pipe: all four phases as one persistent launch; narrow ones (halo-tile kernel) and
     // the SIMT engine: phase by phase
-    if (algo == 1 && out_pitch > 80) {
+    if (algo == 1) {
         int rc = 0;
-        if (cagc_tc_conv_multi(stream, phases, nph, "conv_up[tc,multi]", &rc)) return rc;
+        // low-resolution layers with a workspace: all phases and a split of their K loops in one launch
+        if (workspace && cagc_tc_conv_multi_splitk(stream, phases, nph, workspace, workspace_bytes, "conv_up[tc,splitk]", &rc))
+            return rc;
+        if (out_pitch > 80 && cagc_tc_conv_multi(stream, phases, nph, "conv_up[tc,multi]", &rc)) return rc;
     }
     for (int i = 0; i < nph; ++i) {
         if (phases[i].ntaps == 0) continue;

@@ -70,6 +70,7 @@ struct TcParams {
     int ph_gmin;                // smallest item count of a phase (tile-group-major enumeration, see decode)
     int ph_Ho[kMaxPhases], ph_Wo[kMaxPhases], ph_oy[kMaxPhases], ph_ox[kMaxPhases];
     int ph_tx[kMaxPhases], ph_ty[kMaxPhases], ph_tiles[kMaxPhases];
+    int ph_z0[kMaxPhases + 1], ph_itper[kMaxPhases];   // conv_tc_kernel, phased split-K: blockIdx.z range and iterations per split of each phase
 };
 
 // ---------------------------------------------------------------- PTX helpers
@@ -436,17 +437,31 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     auto empty_bar = [&](int s) { return bar0 + 8u * (kMaxStages + s); };
     const uint32_t acc_bar = bar0 + 8u * (2 * kMaxStages);
 
+    // ---- phased split-K (all output parities of a small transposed convolution in one launch): blockIdx.z selects the
+    // phase -- its taps, output lattice and extent -- and the split of that phase's K loop
+    int f_tap0 = 0, f_ntaps = p.ntaps, f_Ho = p.Ho, f_Wo = p.Wo, f_oy = p.out_oy, f_ox = p.out_ox;
+    int f_tx = p.tiles_x, f_ty = p.tiles_y, f_tiles = p.tiles_total, f_itper = p.it_per_split, zs = blockIdx.z;
+    if (p.nphase > 1) {
+        int f = 0;
+        while (f + 1 < p.nphase && (int)blockIdx.z >= p.ph_z0[f + 1]) ++f;
+        zs = (int)blockIdx.z - p.ph_z0[f];
+        f_tap0 = p.ph_tap0[f]; f_ntaps = p.ph_ntaps[f];
+        f_Ho = p.ph_Ho[f]; f_Wo = p.ph_Wo[f]; f_oy = p.ph_oy[f]; f_ox = p.ph_ox[f];
+        f_tx = p.ph_tx[f]; f_ty = p.ph_ty[f]; f_tiles = p.ph_tiles[f]; f_itper = p.ph_itper[f];
+        if ((int)blockIdx.x * MT >= f_tiles) return;      // the grid is sized for the largest phase
+    }
+
     // ---- tile coordinates of the (up to two) 128-pixel sub-tiles; a sub-tile past the end is parked
     // at batch index B (fully out of bounds: TMA zero-fills, the epilogue stores nothing)
     int x0s[2], y0s[2], b0s[2];
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
         int t = blockIdx.x * MT + j;
-        if (j < MT && t < p.tiles_total) {
-            x0s[j] = (t % p.tiles_x) * p.bw;
-            t /= p.tiles_x;
-            y0s[j] = (t % p.tiles_y) * p.bh;
-            b0s[j] = (t / p.tiles_y) * p.bb;
+        if (j < MT && t < f_tiles) {
+            x0s[j] = (t % f_tx) * p.bw;
+            t /= f_tx;
+            y0s[j] = (t % f_ty) * p.bh;
+            b0s[j] = (t / f_ty) * p.bb;
         } else {
             x0s[j] = 0; y0s[j] = 0; b0s[j] = p.B;
         }
@@ -482,8 +497,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int nk = (p.k_valid + kChunkK - 1) / kChunkK;
     // split-K (small layers): blockIdx.z owns the (tap, chunk) iterations [it0, total) of the full K loop and leaves raw
     // partial sums in its workspace slab; splitk_epilogue_kernel adds the slabs in a fixed order and applies the epilogue
-    const int it0 = p.it_per_split ? (int)blockIdx.z * p.it_per_split : 0;
-    const int total = p.it_per_split ? min(p.ntaps * nk, it0 + p.it_per_split) : p.ntaps * nk;
+    const int it0 = f_itper ? zs * f_itper : 0;
+    const int total = f_itper ? min(f_ntaps * nk, it0 + f_itper) : f_ntaps * nk;
 
     if (warp == 0) {
         // =============================== TMA producer ===============================
@@ -492,7 +507,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const uint32_t ph = (uint32_t)((it - it0) / S) & 1u;
             mbar_wait(empty_bar(s), ph ^ 1u);
             const int tap = it / nk, kc = it - tap * nk;
-            const Tap tp = p.taps[tap];
+            const Tap tp = p.taps[f_tap0 + tap];
             if (elect_one()) {
                 mbar_expect_tx(full_bar(s), stage_bytes);
                 for (int j = 0; j < MT; ++j)
@@ -533,13 +548,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int lb = m / (p.bw * p.bh);
         mbar_wait(acc_bar, 0);
         tc_fence_after();
-        const EpiArgs ea = p.it_per_split
-            ? EpiArgs{nullptr, nullptr, nullptr, p.ws + (int64_t)blockIdx.z * p.ws_slab, p.n_pitch, p.n_pitch, 0, 0, 1.f}
+        const EpiArgs ea = f_itper
+            ? EpiArgs{nullptr, nullptr, nullptr, p.ws + (int64_t)zs * p.ws_slab, p.n_pitch, p.n_pitch, 0, 0, 1.f}
             : EpiArgs{p.out_scale, p.bias, p.residual, p.out, p.n_pitch, p.out_valid, p.act, p.noise != nullptr, p.act_gain};
       for (int j = 0; j < MT; ++j) {
         const int ox = x0s[j] + lx, oy = y0s[j] + ly, b = b0s[j] + lb;
-        const bool pvalid = (ox < p.Wo) && (oy < p.Ho) && (b < p.B);
-        const int yy = oy * p.out_stride + p.out_oy, xx = ox * p.out_stride + p.out_ox;
+        const bool pvalid = (ox < f_Wo) && (oy < f_Ho) && (b < p.B);
+        const int yy = oy * p.out_stride + f_oy, xx = ox * p.out_stride + f_ox;
         float nz = 0.f;
         if (p.noise && pvalid)
             nz = __ldg(p.noise_w) * __ldg(p.noise + (int64_t)b * p.noise_bstride + (int64_t)yy * p.Wout + xx);
@@ -1903,21 +1918,29 @@ struct SplitKEpiP {
     int HW, n_pitch, out_valid, act;
     int64_t noise_bstride;
     float act_gain;
+    int W;                     // phased form (W > 0): pixel (y, x) was produced by ns_par[(y & 1) * 2 + (x & 1)] splits
+    int ns_par[4];
 };
 
-__global__ void __launch_bounds__(256) splitk_epilogue_kernel(const SplitKEpiP p) {
+__global__ void __launch_bounds__(256) splitk_epilogue_kernel(const __grid_constant__ SplitKEpiP p) {
     const int c4n = p.n_pitch >> 2;
     const int64_t n4 = p.slab >> 2;
     const float nw = p.noise ? __ldg(p.noise_w) : 0.f;
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256) {
-        float4 a = ld4(p.ws + i * 4);
-        for (int z = 1; z < p.nsplit; ++z) {
-            const float4 v = ld4(p.ws + (int64_t)z * p.slab + i * 4);
-            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
-        }
         const int64_t pix = i / c4n;
         const int n = (int)(i - pix * c4n) * 4;
         const int b = (int)(pix / p.HW);
+        int ns = p.nsplit;
+        if (p.W > 0) {
+            const int r = (int)(pix - (int64_t)b * p.HW);
+            const int y = r / p.W, x = r - y * p.W;
+            ns = p.ns_par[((y & 1) << 1) | (x & 1)];
+        }
+        float4 a = ld4(p.ws + i * 4);
+        for (int z = 1; z < ns; ++z) {
+            const float4 v = ld4(p.ws + (int64_t)z * p.slab + i * 4);
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
         float o[4] = {a.x, a.y, a.z, a.w};
         if (p.out_scale) {
             const float4 s4 = ldg4(p.out_scale + (int64_t)b * p.n_pitch + n);
@@ -2362,6 +2385,143 @@ int cagc_tc_conv_multi(cudaStream_t stream, const ConvP* ph, int nphase, const c
     }
     conv_tc_persist_kernel<<<kNumSMs, kThreadsPersist, smem, stream>>>(map_a, map_b, p);
     *rc = launched(what);
+    return 1;
+}
+
+// Small transposed convolutions (4x4 .. 16x16 inputs; per-rank batch 2): all phases AND a split of each phase's K loop in
+// one conv_tc_kernel launch (blockIdx.z = (phase, split)), raw partial sums into workspace slabs laid out like the
+// output, then one elementwise pass that adds the slabs of every pixel's phase in a fixed order.  Launched phase by
+// phase these layers cost 4 x ~25 us of serial TMA latency for a few MFLOP.
+// Returns 1 when it took the call (result in *rc), 0 when the caller should use another form.
+int cagc_tc_conv_multi_splitk(cudaStream_t stream, const ConvP* ph, int nphase, float* workspace, int64_t workspace_bytes,
+                              const char* what, int* rc) {
+    using namespace cagc::tc;
+    *rc = 0;
+    static const int env = [] { const char* e = getenv("CAGC_TC_MULTI_SPLITK"); return e ? atoi(e) : 1; }();
+    if (!env || !workspace || nphase < 2 || nphase > kMaxPhases) return 0;
+    const ConvP& c = ph[0];
+    if (c.in_scale != nullptr || c.in_stride != 1 || c.out_stride != 2 || c.in_pitch % 8 != 0 || c.n_cols % 8 != 0) return 0;
+    if (c.out_scale || c.noise || c.bias || c.residual || c.act) return 0;      // the transposed convolution has a plain epilogue
+    EncodeTiledFn encode = get_encode();
+    if (!encode) return 0;
+    int Hmax = 0, Wmax = 0, taps_total = 0, par_seen = 0;
+    for (int f = 0; f < nphase; ++f) {
+        if (ph[f].ntaps == 0) return 0;
+        Hmax = std::max(Hmax, ph[f].Ho); Wmax = std::max(Wmax, ph[f].Wo);
+        taps_total += ph[f].ntaps;
+        par_seen |= 1 << (((ph[f].out_oy & 1) << 1) | (ph[f].out_ox & 1));
+    }
+    if (nphase != 4 || par_seen != 15 || taps_total > kMaxTaps) return 0;       // every output pixel written by exactly one phase
+    const int64_t slab = (int64_t)c.B * c.Hout * c.Wout * c.n_cols;
+    if ((int64_t)c.B * Hmax * Wmax == 0 || slab <= 0 || workspace_bytes < 2 * slab * 4) return 0;
+    TcParams p{};
+    p.out = c.out;
+    p.B = c.B; p.Ho = Hmax; p.Wo = Wmax;
+    p.bw = std::min(16, next_pow2(Wmax));
+    p.bh = std::min(kTileM / p.bw, next_pow2(Hmax));
+    p.bb = kTileM / (p.bw * p.bh);
+    const int tiles_b = ceil_div(c.B, p.bb);
+    p.k_valid = c.in_pitch;
+    p.n_pitch = c.n_cols; p.out_valid = c.out_valid;
+    p.n_rows = (c.n_cols + 15) & ~15;
+    p.n_tile = std::min(256, p.n_rows);
+    p.mt = 1;
+    int tiles_max = 0;
+    p.nphase = nphase;
+    int tap0 = 0, max_slab = 0;
+    for (int k = 0; k < nphase; ++k) {
+        const ConvP& q = ph[k];
+        p.ph_tap0[k] = tap0; p.ph_ntaps[k] = q.ntaps;
+        for (int i = 0; i < q.ntaps; ++i) {
+            p.taps[tap0 + i] = q.taps[i];
+            max_slab = std::max(max_slab, q.taps[i].slab);
+        }
+        tap0 += q.ntaps;
+        p.ph_Ho[k] = q.Ho; p.ph_Wo[k] = q.Wo; p.ph_oy[k] = q.out_oy; p.ph_ox[k] = q.out_ox;
+        p.ph_tx[k] = ceil_div(q.Wo, p.bw); p.ph_ty[k] = ceil_div(q.Ho, p.bh);
+        p.ph_tiles[k] = p.ph_tx[k] * p.ph_ty[k] * tiles_b;
+        tiles_max = std::max(tiles_max, p.ph_tiles[k]);
+    }
+    // only layers that cannot fill the machine phase by phase
+    if ((int64_t)tiles_max * ceil_div(p.n_rows, p.n_tile) * nphase >= 3 * kNumSMs) return 0;
+    // narrower N tiles -> more CTAs and a deeper ring per CTA (as in cagc_tc_conv)
+    while (p.n_tile > 32 && (int64_t)tiles_max * ceil_div(p.n_rows, p.n_tile) < kNumSMs / 8) {
+        int nt = (p.n_tile / 2 + 15) & ~15;
+        if (nt < 32) nt = 32;
+        p.n_tile = nt;
+    }
+    const int n_tiles = ceil_div(p.n_rows, p.n_tile);
+    // iterations ((tap, 32-channel chunk) steps) per CTA: about two CTAs per SM over all phases, at least 4
+    const int nk_h = ceil_div(c.in_pitch, kChunkK);
+    int64_t work = 0;
+    for (int k = 0; k < nphase; ++k) work += (int64_t)p.ph_tiles[k] * n_tiles * p.ph_ntaps[k] * nk_h;
+    int ipc = (int)std::max<int64_t>(4, ceil_div<int64_t>(work, 2 * kNumSMs));
+    const int max_slabs = (int)std::min<int64_t>(16, workspace_bytes / (slab * 4));
+    int z = 0, ns_max = 0;
+    for (;;) {
+        z = 0; ns_max = 0;
+        for (int k = 0; k < nphase; ++k) {
+            const int total_it = p.ph_ntaps[k] * nk_h;
+            p.ph_itper[k] = std::min(ipc, total_it);
+            const int ns = ceil_div(total_it, p.ph_itper[k]);
+            p.ph_z0[k] = z;
+            z += ns;
+            ns_max = std::max(ns_max, ns);
+        }
+        p.ph_z0[nphase] = z;
+        if (ns_max <= max_slabs) break;
+        ipc += std::max(1, ipc / 4);
+    }
+    p.ws = workspace; p.ws_slab = slab;
+    p.Hout = c.Hout; p.Wout = c.Wout; p.out_stride = c.out_stride;
+    p.in_stride = 1; p.ntaps = taps_total;
+    p.b_bytes = (uint32_t)p.n_tile * kChunkK * 4;
+    const uint32_t stage_bytes = (uint32_t)kABytes + p.b_bytes;
+    p.stages = std::max(2, std::min(kMaxStages, (int)((kConvBudget1 - 1024) / stage_bytes)));
+    p.epi_off = (uint32_t)p.stages * stage_bytes;
+    const size_t smem = (size_t)p.stages * stage_bytes + 1024 + kEpiStageBytes;
+    CUtensorMap map_a, map_b;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)c.in_pitch, (cuuint64_t)c.Win, (cuuint64_t)c.Hin, (cuuint64_t)c.B};
+        cuuint64_t strides[3] = {(cuuint64_t)c.in_pitch * 4, (cuuint64_t)c.Win * c.in_pitch * 4,
+                                 (cuuint64_t)c.Hin * c.Win * c.in_pitch * 4};
+        cuuint32_t box[4] = {(cuuint32_t)kChunkK, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bb};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        CUresult r = encode(&map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(c.in), dims, strides, box, es,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { *rc = fail(CAGC_E_INVALID, "%s: cuTensorMapEncodeTiled(A) failed with %d", what, (int)r); return 1; }
+    }
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)c.in_pitch, (cuuint64_t)p.n_rows, (cuuint64_t)(max_slab + 1)};
+        cuuint64_t strides[2] = {(cuuint64_t)c.in_pitch * 4, (cuuint64_t)p.n_rows * c.in_pitch * 4};
+        cuuint32_t box[3] = {(cuuint32_t)kChunkK, (cuuint32_t)p.n_tile, 1};
+        cuuint32_t es[3] = {1, 1, 1};
+        CUresult r = encode(&map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(c.w), dims, strides, box, es,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { *rc = fail(CAGC_E_INVALID, "%s: cuTensorMapEncodeTiled(B) failed with %d", what, (int)r); return 1; }
+    }
+    static DeviceOnce attr_set{0};
+    if (device_once_needed(attr_set)) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget1);
+        if (e != cudaSuccess) { *rc = fail((int)e, "%s: cudaFuncSetAttribute failed: %s", what, cudaGetErrorString(e)); return 1; }
+        device_once_done(attr_set);
+    }
+    dim3 grid((unsigned)tiles_max, (unsigned)n_tiles, (unsigned)z);
+    conv_tc_kernel<<<grid, kThreads, smem, stream>>>(map_a, map_b, p);
+    *rc = launched(what);
+    if (*rc) return 1;
+    SplitKEpiP q{};
+    q.ws = workspace; q.slab = slab; q.nsplit = 1;
+    q.out = c.out; q.HW = c.Hout * c.Wout; q.n_pitch = c.n_cols; q.out_valid = c.out_valid; q.act = 0;
+    q.act_gain = kSqrt2;
+    q.W = c.Wout;
+    for (int k = 0; k < nphase; ++k)
+        q.ns_par[((p.ph_oy[k] & 1) << 1) | (p.ph_ox[k] & 1)] = p.ph_z0[k + 1] - p.ph_z0[k];
+    const int64_t blocks = std::min<int64_t>(ceil_div<int64_t>(slab / 4, 256), kNumSMs * 4);
+    splitk_epilogue_kernel<<<(unsigned)std::max<int64_t>(blocks, 1), 256, 0, stream>>>(q);
+    *rc = launched("splitk_epilogue_kernel");
     return 1;
 }
 

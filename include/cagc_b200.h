@@ -37,7 +37,7 @@ typedef void* cagc_stream_t; /* cudaStream_t */
 #define CAGC_E_UNSUPPORTED (-2) /* shape outside what the kernels implement */
 
 /* bump when a signature changes; the Python loader checks it */
-#define CAGC_ABI_VERSION 18
+#define CAGC_ABI_VERSION 19
 
 int cagc_abi_version(void);
 const char* cagc_last_error(void);
@@ -334,6 +334,11 @@ int cagc_conv_same_ws(cagc_stream_t stream, const float* in, const float* w_slab
                       int act, int algo, float* workspace, int64_t workspace_bytes);
 int cagc_conv_up_dgrad_ws(cagc_stream_t stream, const float* g_t, const float* w_slabs, float* g_in, int B, int H, int W,
                           int g_pitch, int in_pitch, int ksize, int algo, float* workspace, int64_t workspace_bytes);
+/* cagc_conv_up with a workspace sized for the TRANSPOSED output (cagc_conv_workspace_bytes(B, 2H+k-2, 2W+k-2, out_pitch)):
+ * low-resolution layers run all four phases and a split of their K loops as one launch plus a fixed-order reduction. */
+int cagc_conv_up_ws(cagc_stream_t stream, const float* in, const float* w_slabs, const float* in_scale, float* out_t,
+                    int B, int H, int W, int in_pitch, int out_pitch, int ksize, int algo, float* workspace,
+                    int64_t workspace_bytes);
 int cagc_conv2d_ws(cagc_stream_t stream, const float* in, const float* w_slabs, const float* bias, const float* residual,
                    float* out, int B, int Hin, int Win, int in_pitch, int out_pitch, int out_valid, int ksize, int mode,
                    int act, float act_gain, int algo, float* workspace, int64_t workspace_bytes);
