@@ -25,7 +25,19 @@ namespace cagc {
 namespace tc {
 
 constexpr int kThreads = 192;
-constexpr int kThreadsPersist = 320;             // persistent conv kernel: TMA + MMA + 8 epilogue warps
+constexpr int kThreadsPersist = 320;             // halo-tile conv kernel: TMA + MMA + 8 epilogue warps
+constexpr int kPersistEpiWarps = 16;             // persistent conv kernel: at most 16 epilogue warps (4 per TMEM lane quarter)
+constexpr int kThreadsPersistP = 64 + 32 * kPersistEpiWarps;
+// Epilogue warps of one persistent launch: the epilogue is a dependent chain per 16-column chunk (TMEM load -> transpose ->
+// math -> store, ~300 instructions), so its throughput scales with the number of warps running it.  Layers with few K
+// iterations per work item (1x1 convolutions, the up-convolutions of the narrow end) are bound by it and take 16 warps
+// (measured: 128->256 1x1 @128^2 with residual 216 -> 150 us); the compute-bound ones keep 8 and the deeper ring
+// (512ch @64^2: 386 us with 8 warps / 4 stages, 440 us with 16 warps / 3 stages).
+static inline int persist_epi_warps(int k_iters) {
+    static const int env = [] { const char* e = getenv("CAGC_TC_EPI_WARPS"); return e ? atoi(e) : 0; }();
+    if (env == 8 || env == 16) return env;
+    return k_iters <= 24 ? 16 : 8;
+}
 constexpr int kTileM = 128;
 constexpr int kChunkK = 32;                      // fp32 elements per 128-byte swizzle row
 constexpr int kABytes = kTileM * kChunkK * 4;    // 16 KB
@@ -304,15 +316,15 @@ __device__ __forceinline__ void epi_rows(const EpiArgs& e, float* st, uint32_t t
 // a few instructions per 10 cycles; layers with little K per output (1x1 convolutions, the up-convolutions' large
 // outputs) were bound by it.  16-column chunks keep the staging at 2 KB per warp (8 warps: the same 16 KB).
 __device__ __forceinline__ void epi_rows_pair(const EpiArgs& e, float* st, uint32_t taddr, int lane, int n0, int n_mma,
-                                              bool rvalid, int64_t roff, float rnz, int rb, int part) {
+                                              bool rvalid, int64_t roff, float rnz, int rb, int part, int nparts = 2) {
     if (n_mma < kEpiTransposeMinN || st == nullptr) {
-        // direct form: the pair splits the column range in halves (multiples of 16)
-        const int half = ((n_mma >> 4) + 1) >> 1 << 4;
-        const int c0 = part ? half : 0, c1 = part ? n_mma : half;
+        // direct form: the warps of a lane quarter split the column range in pieces (multiples of 16)
+        const int per = (((n_mma >> 4) + nparts - 1) / nparts) << 4;
+        const int c0 = part * per, c1 = min(n_mma, c0 + per);
         if (c1 > c0) epi_rows_direct(e, taddr + (uint32_t)c0, n0 + c0, c1 - c0, rvalid, roff, rnz, rb);
         return;
     }
-    for (int c = part * 16; c < n_mma; c += 32) epi_chunk<16>(e, st, taddr + (uint32_t)c, lane, n0 + c, rvalid, roff, rnz, rb);
+    for (int c = part * 16; c < n_mma; c += 16 * nparts) epi_chunk<16>(e, st, taddr + (uint32_t)c, lane, n0 + c, rvalid, roff, rnz, rb);
 }
 
 // One elected lane of a converged warp.  The TMA / MMA warps keep their control flow warp-uniform and put only
@@ -583,7 +595,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-__global__ void __launch_bounds__(kThreadsPersist, 1)
+__global__ void __launch_bounds__(kThreadsPersistP, 1)
 conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                        const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -614,7 +626,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
-            mbar_init(tempty_bar(a), 8);            // one arrival per epilogue warp
+            mbar_init(tempty_bar(a), (blockDim.x >> 5) - 2);   // one arrival per epilogue warp (8 or 16, chosen by the host)            // one arrival per epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -747,7 +759,8 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         }
     } else {
         const int q = warp & 3;                   // TMEM lane quarter; warps w and w + 4 share it
-        const int part = (warp - 2) >> 2;         // which 16-column chunks of the pair this warp takes
+        const int part = (warp - 2) >> 2;         // which 16-column chunks this warp takes among the warps of its quarter
+        const int nparts = ((int)(blockDim.x >> 5) - 2) >> 2;
         float* const my_stage = epi_stage_base ? epi_stage_base + (warp - 2) * 512 : nullptr;     // 2 KB per warp
         const int m = q * 32 + lane;
         const int lx = m % p.bw;
@@ -782,7 +795,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                 const int yy = oy * p.out_stride + p.ph_oy[f], xx = ox * p.out_stride + p.ph_ox[f];
                 const float nz = nzs[j];
                 const int64_t roff = (((int64_t)b * p.Hout + yy) * p.Wout + xx) * p.n_pitch;
-                epi_rows_pair(ea, my_stage, d0 + (uint32_t)(j * p.n_tile), lane, n0, n_mma, pvalid, roff, nz, b, part);
+                epi_rows_pair(ea, my_stage, d0 + (uint32_t)(j * p.n_tile), lane, n0, n_mma, pvalid, roff, nz, b, part, nparts);
             }
             // this warp has finished reading the accumulator buffer: hand it back to the MMA warp
             tc_fence_before();
@@ -2245,11 +2258,13 @@ int cagc_tc_conv(cudaStream_t stream, const ConvP& c, const char* what) {
         q.ph_Ho[0] = p.Ho; q.ph_Wo[0] = p.Wo; q.ph_oy[0] = p.out_oy; q.ph_ox[0] = p.out_ox;
         q.ph_tx[0] = p.tiles_x; q.ph_ty[0] = p.tiles_y; q.ph_tiles[0] = p.tiles_total;
         const uint32_t sb = (uint32_t)q.mt * kABytes + q.b_bytes;
-        q.stages = std::max(2, std::min(kMaxStages, (int)((kConvBudget1 - 1024) / sb)));
+        const int ew = persist_epi_warps(c.ntaps * ceil_div(c.in_pitch, kChunkK));
+        const int epi_bytes = ew * 2048;            // 2 KB (32 rows x 16 columns) of staging per epilogue warp
+        q.stages = std::max(2, std::min(kMaxStages, (int)((kSmemBudget1 - epi_bytes - 1024) / sb)));
         q.epi_off = (uint32_t)q.stages * sb;
-        const size_t smem_p = (size_t)q.stages * sb + 1024 + kEpiStageBytes;
+        const size_t smem_p = (size_t)q.stages * sb + 1024 + epi_bytes;
         const unsigned gridp = (unsigned)std::min<int64_t>(items, kNumSMs);
-        conv_tc_persist_kernel<<<gridp, kThreadsPersist, smem_p, stream>>>(map_a, map_b, q);
+        conv_tc_persist_kernel<<<gridp, 64 + 32 * ew, smem_p, stream>>>(map_a, map_b, q);
         return launched(what);
     }
     const int64_t gx = ceil_div<int64_t>(p.tiles_total, p.mt);
@@ -2352,9 +2367,11 @@ int cagc_tc_conv_multi(cudaStream_t stream, const ConvP* ph, int nphase, const c
     p.ntaps = taps_total;
     if (items < 2 * kNumSMs || items > 0x7fffffff) return 0;   // tiny layers: the per-phase launches are latency-bound anyway
     const uint32_t sb = (uint32_t)p.mt * kABytes + p.b_bytes;
-    p.stages = std::max(2, std::min(kMaxStages, (int)((kConvBudget1 - 1024) / sb)));
+    const int ew = persist_epi_warps(ceil_div(taps_total * ceil_div(c.in_pitch, kChunkK), nphase));
+    const int epi_bytes = ew * 2048;
+    p.stages = std::max(2, std::min(kMaxStages, (int)((kSmemBudget1 - epi_bytes - 1024) / sb)));
     p.epi_off = (uint32_t)p.stages * sb;
-    const size_t smem = (size_t)p.stages * sb + 1024 + kEpiStageBytes;
+    const size_t smem = (size_t)p.stages * sb + 1024 + epi_bytes;
     CUtensorMap map_a, map_b;
     {
         cuuint64_t dims[4] = {(cuuint64_t)c.in_pitch, (cuuint64_t)c.Win, (cuuint64_t)c.Hin, (cuuint64_t)c.B};
@@ -2383,7 +2400,7 @@ int cagc_tc_conv_multi(cudaStream_t stream, const ConvP* ph, int nphase, const c
         if (e != cudaSuccess) { *rc = fail((int)e, "%s: cudaFuncSetAttribute failed: %s", what, cudaGetErrorString(e)); return 1; }
         device_once_done(attr_set);
     }
-    conv_tc_persist_kernel<<<kNumSMs, kThreadsPersist, smem, stream>>>(map_a, map_b, p);
+    conv_tc_persist_kernel<<<kNumSMs, 64 + 32 * ew, smem, stream>>>(map_a, map_b, p);
     *rc = launched(what);
     return 1;
 }
