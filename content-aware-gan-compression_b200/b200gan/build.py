@@ -14,7 +14,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, 'csrc')
 LIB = os.path.join(PKG, 'lib', 'libcagc_b200.so')
 STAMP = LIB + '.stamp'
-SOURCES = ['ops.cu', 'conv_simt.cu', 'nhwc_aux.cu', 'conv_tc.cu', 'prep.cu', 'disc.cu', 'linear.cu']
+SOURCES = ['ops.cu', 'conv_simt.cu', 'nhwc_aux.cu', 'conv_tc.cu', 'prep.cu', 'disc.cu', 'linear.cu', 'lpips.cu', 'kdloss.cu']
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
          '-Xcompiler', '-fPIC', '-shared']
 

@@ -1,10 +1,12 @@
 """The knowledge-distillation generator step (reference train.py:280-308, `G_Loss_BackProp`) as a
 reusable driver: student forward (RGB list) -> discriminator -> non-saturating GAN loss; teacher
-forward; masked L1 KD loss (train.py:145-164, 'Output_Only'); backward; one flat-bucket gradient
-all-reduce over the data-parallel ranks; fused Adam (train.py:528-532 hyper-parameters).
+forward; content mask (train.py:154-158); masked L1 + LPIPS KD losses (train.py:145-184); backward; one flat-bucket
+gradient all-reduce over the data-parallel ranks; fused Adam (train.py:528-532 hyper-parameters).
 
-LPIPS (VGG16) and the BiSeNet face parser are third-party networks outside the hot path
-(SURVEY.md §2 #8/#9); a caller supplies the content mask.  Public API used by bench.py's e2e leg.
+The LPIPS-VGG16 distance runs on the package's own kernels (b200gan/lpips.PerceptualLossVGG; any callable with
+`lpips.PerceptualLoss`'s contract is accepted); the face parser (BiSeNet) is a caller-supplied module
+with BiSeNet's call contract -- what goes in and what comes out of it is the device-side glue of b200gan/maskglue.py.
+Without a parser a constant content mask can be given.  Public API used by bench.py's e2e leg.
 """
 from __future__ import annotations
 
@@ -15,14 +17,19 @@ import torch
 import torch.nn.functional as F
 
 from . import dist as D
+from . import maskglue
 from ._lib import lib, check
 
 
 class KDStep:
     def __init__(self, student, teacher, discriminator, lr: float = 0.002 * 0.8, betas=(0.0, 0.99 ** 0.8),
                  eps: float = 1e-8, kd_l1_lambda: float = 3.0, mask: Optional[torch.Tensor] = None,
-                 kd_mode: str = 'Output_Only', g_ema=None, ema_decay: float = 0.5 ** (32 / (10 * 1000))):
+                 kd_mode: str = 'Output_Only', g_ema=None, ema_decay: float = 0.5 ** (32 / (10 * 1000)),
+                 percept_loss=None, kd_lpips_lambda: float = 3.0, parsing_net=None, lpips_image_size: int = 256):
         self.student, self.teacher, self.disc = student, teacher, discriminator
+        # train.py:509-520: percept_loss(pred, target) -> [N,1,1,1] (LPIPS-VGG), parsing_net(x)[0] -> class scores
+        self.percept_loss, self.kd_lpips_lambda = percept_loss, float(kd_lpips_lambda)
+        self.parsing_net, self.lpips_image_size = parsing_net, int(lpips_image_size)
         for p in teacher.parameters():
             p.requires_grad_(False)
         for p in discriminator.parameters():
@@ -74,15 +81,28 @@ class KDStep:
         g_loss = F.softplus(-self.disc(fake[-1])).mean()
         if self.teacher_stream is not None:
             main.wait_stream(self.teacher_stream)
+        # content-aware adjustment (train.py:154-158): the mask comes from parsing the TEACHER image and multiplies both
+        s_img, t_img = fake[-1], real[-1]
+        mask = self.mask
+        if self.parsing_net is not None:
+            mask = maskglue.content_mask(t_img, self.parsing_net)
+        if mask is not None:
+            s_img, t_img = s_img * mask, t_img * mask
         if self.kd_mode == 'Output_Only':                      # train.py:163-164
-            s_img, t_img = fake[-1], real[-1]
-            if self.mask is not None:
-                s_img, t_img = s_img * self.mask, t_img * self.mask
             kd = self.kd_l1_lambda * torch.mean(torch.abs(t_img - s_img))
         else:
-            # train.py:165-169: every resolution of the two rgb lists; the comprehension re-binds both names to the
-            # list entries, so the content mask (applied to the last pair only, :157-158) does not enter this mode
+            # train.py:165-169: every resolution of the two rgb lists.  The list comprehension has its own scope, so the L1
+            # terms pair the UNMASKED list entries; the `for fake_img_teacher in fake_img_teacher_list` loop before it,
+            # however, leaves `fake_img_teacher` bound to the last (unmasked) teacher image, which is what LPIPS then sees
             kd = self.kd_l1_lambda * sum(torch.mean(torch.abs(t - f)) for t, f in zip(real, fake))
+            t_img = real[-1]
+        if self.percept_loss is not None:                      # train.py:172-182
+            p_s, p_t = s_img, t_img
+            if s_img.shape[-1] > self.lpips_image_size:         # "pooled the image for LPIPS for memory saving"
+                size = (self.lpips_image_size, self.lpips_image_size)
+                p_s = F.interpolate(s_img, size=size, mode='bilinear', align_corners=False)
+                p_t = F.interpolate(t_img, size=size, mode='bilinear', align_corners=False)
+            kd = kd + self.kd_lpips_lambda * torch.mean(self.percept_loss(p_s, p_t))
         return g_loss, kd
 
     def step(self, z: List[torch.Tensor], inject_index: int, s_noise=None, t_noise=None) -> torch.Tensor:

@@ -71,7 +71,11 @@ constexpr int kNumSMs = 148;  // B200
 
 __device__ __forceinline__ float lrelu_sqrt2(float v) { return (v > 0.f ? v : v * kLreluSlope) * kSqrt2; }
 // leaky ReLU with an explicit output gain (sqrt2 for StyleGAN2's scaled activation; 1 where a following 1/sqrt2 is folded in)
-__device__ __forceinline__ float lrelu_gain(float v, float gain) { return (v > 0.f ? v : v * kLreluSlope) * gain; }
+// gain < 0 selects a plain ReLU scaled by |gain| (the VGG layers of the LPIPS loss); the branch is uniform per launch
+__device__ __forceinline__ float lrelu_gain(float v, float gain) {
+    if (gain < 0.f) return v > 0.f ? v * -gain : 0.f;
+    return (v > 0.f ? v : v * kLreluSlope) * gain;
+}
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }

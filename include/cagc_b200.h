@@ -37,7 +37,7 @@ typedef void* cagc_stream_t; /* cudaStream_t */
 #define CAGC_E_UNSUPPORTED (-2) /* shape outside what the kernels implement */
 
 /* bump when a signature changes; the Python loader checks it */
-#define CAGC_ABI_VERSION 19
+#define CAGC_ABI_VERSION 20
 
 int cagc_abi_version(void);
 const char* cagc_last_error(void);
@@ -292,7 +292,8 @@ int cagc_adam_ema_step(cagc_stream_t stream, float* param, const float* grad, fl
  *           downsample; with flipped / transposed slabs it is also its data gradient)
  *   mode 1: stride 2, no padding, H = 2*Ho + ksize - 2 (the EqualConv2d after Blur, model.py:683-700); its data
  *           gradient is cagc_conv_up (transposed convolution)
- *   act != 0: leaky ReLU(0.2) * act_gain (FusedLeakyReLU, op/fused_act.py:104-119; act_gain 0 means sqrt2)
+ *   act != 0: leaky ReLU(0.2) * act_gain (FusedLeakyReLU, op/fused_act.py:104-119; act_gain 0 means sqrt2);
+ *           act_gain < 0: plain ReLU * |act_gain| (nn.ReLU of the VGG16 layers, lpips/pretrained_networks.py:100-114)
  *   residual (optional, layout of out, must not alias it) is added after the activation (ResBlock, model.py:731-737)
  *   w_slabs: as written by cagc_weight_prep for the engine `algo` (0 SIMT fp32, 1 tcgen05 TF32)
  * cagc_fir_resample_nhwc: upfirdn2d (op/upfirdn2d.py:145-156) with a 4x4 kernel and (up, down) = (1, 2) or (2, 1) on
@@ -353,6 +354,49 @@ int cagc_linear_fwd(cagc_stream_t stream, const float* x, const float* w, const 
                     int K, float acc_scale, float bias_scale, int act, float alpha, float gain);
 int cagc_linear_bwd(cagc_stream_t stream, const float* g_acc, const float* x, const float* w, float* g_x, float* g_w,
                     int M, int N, int K);
+
+/* ----------------------------------------------------------------------
+ * LPIPS-VGG16 perceptual distance of the KD loss (reference train.py:172-182 -> lpips/__init__.py:13-41 ->
+ * lpips/networks_basic.py:26-92 -> lpips/pretrained_networks.py:97-137), frozen network, NHWC-p activations.
+ * The 3x3 convolutions with >= 64 input channels are cagc_conv2d[_ws] calls with act_gain = -1 (ReLU); these are the
+ * remaining pieces (replacing ATen / cuDNN launches of the reference: F.conv2d on 3 channels, max_pool2d and its
+ * backward, threshold_backward, the normalize / square / 1x1-conv / mean chain of networks_basic.py:66-84).
+ *   cagc_rgb_conv3x3_fwd: out[B,H,W,pitch] = relu(conv3x3((img - shift) / scale, w[cout,3,3,3], pad 1) + bias); img through
+ *       element strides (sb, sc, sh, sw); shift_host / scale_host: 3 floats in HOST memory (ScalingLayer,
+ *       networks_basic.py:94-101; null = identity).  _bwd: NCHW-contiguous image gradient from gz[B,H,W,pitch] (the
+ *       gradient w.r.t. the pre-activation, i.e. already masked).
+ *   cagc_maxpool2_nhwc: nn.MaxPool2d(kernel_size=2, stride=2); H, W even.
+ *   cagc_relu_pool_bwd: out = ((act wins its 2x2 window ? g_pool[B,H/2,W/2,pitch] : 0) + g_direct) * (act > 0); the first
+ *       maximum in row-major order wins (ATen).  g_pool null: out = g_direct * (act > 0).  g_direct may be null.
+ *   cagc_lpips_head_fwd: val[b] (+)= mean_p sum_c lin_w[c] (fs/(|fs|+1e-10) - ft/(|ft|+1e-10))^2 for feature maps
+ *       [B,HW,C] (C in {64,128,256,512}); partial: scratch of B * cagc_lpips_head_blocks(B, HW) floats; fixed summation
+ *       order.  _bwd: gs = gval[b] * d val[b] / d fs.
+ * ---------------------------------------------------------------------- */
+int cagc_rgb_conv3x3_fwd(cagc_stream_t stream, const float* img, int64_t sb, int64_t sc, int64_t sh, int64_t sw,
+                         const float* w, const float* bias, const float* shift_host, const float* scale_host, float* out,
+                         int B, int H, int W, int cout, int pitch);
+int cagc_rgb_conv3x3_bwd(cagc_stream_t stream, const float* gz, const float* w, const float* scale_host, float* gimg, int B,
+                         int H, int W, int cout, int pitch);
+int cagc_maxpool2_nhwc(cagc_stream_t stream, const float* in, float* out, int B, int H, int W, int pitch);
+int cagc_relu_pool_bwd(cagc_stream_t stream, const float* act, const float* g_pool, const float* g_direct, float* out,
+                       int B, int H, int W, int pitch);
+int cagc_lpips_head_blocks(int B, int HW);
+int cagc_lpips_head_fwd(cagc_stream_t stream, const float* fs, const float* ft, const float* lin_w, float* partial,
+                        float* val, int B, int HW, int C, int accumulate);
+int cagc_lpips_head_bwd(cagc_stream_t stream, const float* fs, const float* ft, const float* lin_w, const float* gval,
+                        float* gs, int B, int HW, int C);
+
+/* ----------------------------------------------------------------------
+ * Content-mask glue of the KD loss (reference Util/content_aware_pruning.py:61-117, train.py:154-158).
+ *   cagc_parse_preprocess: out[N,3,P,P] (contiguous) = (bilinear(clamp((img + 1) / 2, 0, 1), S -> P) - mean) / std with
+ *       the ImageNet statistics of Batch_Img_Parsing (:71-82); img [N,3,S,S] through element strides.
+ *   cagc_parsing_mask: mask[N,S,S] = bilinear(float(argmax_k logits[N,K,P,P] not in {0, 16}), P -> S) > 0.5
+ *       (`Batch_Img_Parsing` :87 + `Get_Masked_Tensor` :103-109, without the host round trip).
+ * Bilinear = F.interpolate(align_corners=False, scale_factor = out / in).
+ * ---------------------------------------------------------------------- */
+int cagc_parse_preprocess(cagc_stream_t stream, const float* img, int64_t sb, int64_t sc, int64_t sh, int64_t sw,
+                          float* out, int N, int S, int P);
+int cagc_parsing_mask(cagc_stream_t stream, const float* logits, float* mask, int N, int K, int P, int S);
 
 #ifdef __cplusplus
 }

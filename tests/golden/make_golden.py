@@ -387,12 +387,171 @@ def gen_config3(max_batches=None):
         np.savez_compressed(os.path.join(HERE, 'config3_saliency.npz'), **out)
 
 
+# ------------------------------------------------------------------ LPIPS-VGG16 + content-mask glue (rest of the KD loss)
+def _import_ref_lpips():
+    """`import lpips` of the reference needs skimage / IPython at import time (lpips/__init__.py:7,
+    lpips/networks_basic.py:11-12; none of it is used by the net-lin VGG distance) and downloads the torchvision
+    VGG16 weights (lpips/pretrained_networks.py:100): empty stub modules, and a VGG16 that keeps its random init."""
+    import types
+    for name in ('skimage', 'skimage.measure', 'skimage.color', 'skimage.transform', 'IPython'):
+        if name not in sys.modules:
+            try:
+                __import__(name)
+            except Exception:
+                m = types.ModuleType(name)
+                m.__path__ = []
+                sys.modules[name] = m
+    sys.modules['skimage.measure'].__dict__.setdefault('compare_ssim', None)
+    sys.modules['IPython'].__dict__.setdefault('embed', lambda *a, **k: None)
+    import torchvision.models as tvm
+    real = tvm.vgg16
+    tvm.vgg16 = lambda pretrained=True, **k: real(weights=None)
+    import lpips as ref_lpips
+    return ref_lpips
+
+
+def gen_lpips():
+    """The reference's own `lpips.PerceptualLoss(model='net-lin', net='vgg')` (train.py:510) on CPU in fp64: VGG16
+    weights re-drawn from a seed (tests/golden/synth.py; torchvision's are not available offline), the five `lin`
+    layers from the vendored lpips/weights/v0.1/vgg.pth.  Stores the distances and the gradient towards `pred`
+    (the student image of train.py:182)."""
+    import synth
+    ref_lpips = _import_ref_lpips()
+    c = synth.LPIPS_TINY
+    loss = ref_lpips.PerceptualLoss(model='net-lin', net='vgg', use_gpu=False)
+    net = loss.model.net.double()
+    vgg = net.net
+    convs = [m for sl in (vgg.slice1, vgg.slice2, vgg.slice3, vgg.slice4, vgg.slice5) for m in sl
+             if isinstance(m, torch.nn.Conv2d)]
+    cw, cb = synth.vgg16_weights(c['seed_weights'])
+    with torch.no_grad():
+        for m, wt, bt in zip(convs, cw, cb):
+            m.weight.copy_(torch.from_numpy(wt))
+            m.bias.copy_(torch.from_numpy(bt))
+    assert not net.training
+    out = {}
+    for k, lin in enumerate((net.lin0, net.lin1, net.lin2, net.lin3, net.lin4)):
+        out[f'lin{k}'] = npy(lin.model[1].weight.reshape(-1))          # vendored (7 KB): stored
+    pred_np, target_np = synth.lpips_images(c['seed_inputs'], c['batch'], c['size'])
+    pred = torch.from_numpy(pred_np).requires_grad_(True)
+    target = torch.from_numpy(target_np)
+    val = loss(pred, target)                                            # lpips/__init__.py:27-41
+    cot = torch.from_numpy(np.random.RandomState(c['seed_inputs'] + 1).standard_normal(tuple(val.shape)))
+    g, = torch.autograd.grad(val, pred, cot)
+    out['val'], out['cot'], out['g_pred'] = npy(val), npy(cot), npy(g)
+    # train.py:179-182 form: kd_lpips_lambda * mean(percept_loss(fake, teacher))
+    val2 = loss(pred, target)
+    g2, = torch.autograd.grad(3.0 * torch.mean(val2), pred)
+    out['kd_lpips'], out['kd_lpips_g'] = npy(3.0 * torch.mean(val2)), npy(g2)
+    np.savez_compressed(os.path.join(HERE, 'lpips_tiny.npz'), **out)
+
+
+def gen_mask_glue():
+    """`Batch_Img_Parsing` and `Get_Masked_Tensor` (Util/content_aware_pruning.py:61-117) run unmodified on CPU, with a
+    stand-in parser that returns seeded class scores (BiSeNet's call contract: `parsing_net(x)[0]` = [N,19,512,512]); the
+    tensor the parser RECEIVES is recorded (it is the preprocessing under test)."""
+    import synth
+    import Util.content_aware_pruning as cap
+    out = {}
+    for tag, size in (('s256', 256), ('s1024', 1024), ('s64', 64)):
+        n = 2
+        rs = np.random.RandomState(910 + size)
+        img = torch.from_numpy((rs.standard_normal((n, 3, size, size)) * 0.8).astype(np.float32)).float()
+        scores = synth.parser_scores(911 + size, n)
+        seen = {}
+
+        class Parser:
+            def __call__(self, x):
+                seen['x'] = x.detach().clone()
+                return (torch.from_numpy(scores),)
+        parsing = cap.Batch_Img_Parsing(img.clone(), Parser(), 'cpu')
+        masked = cap.Get_Masked_Tensor(img.clone(), parsing, 'cpu', mask_grad=True)
+        out[f'{tag}.pre'] = npy(seen['x'][:, :, ::7, ::5]).astype(np.float32)       # subsampled: 6 MB per case otherwise
+        out[f'{tag}.parsing_sum'] = np.array(int(parsing.sum()))
+        mask = (masked != 0).any(1)            # img has no exact zeros: the mask is where the product survived
+        out[f'{tag}.mask'] = np.packbits(npy(mask).astype(np.uint8))
+        out[f'{tag}.masked_sum'] = np.array(float(masked.detach().double().abs().sum()))
+    np.savez_compressed(os.path.join(HERE, 'mask_glue.npz'), **out)
+
+
+def _ref_train_functions(names):
+    """Function definitions of the reference's train.py, executed from its own source text (train.py parses the command
+    line and builds datasets at import, so it cannot be imported): {name: function}, globals = what train.py imports."""
+    import ast
+    src = open(os.path.join(REF, 'train.py')).read()
+    tree = ast.parse(src)
+    import train_hyperparams
+    from Util.content_aware_pruning import Batch_Img_Parsing, Get_Masked_Tensor
+    ns = {'torch': torch, 'F': F, 'np': np, 'train_hyperparams': train_hyperparams, 'device': 'cpu',
+          'Batch_Img_Parsing': Batch_Img_Parsing, 'Get_Masked_Tensor': Get_Masked_Tensor}
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in names:
+            exec(compile(ast.Module(body=[node], type_ignores=[]), os.path.join(REF, 'train.py'), 'exec'), ns)
+    return {n: ns[n] for n in names}
+
+
+def gen_kd_full():
+    """The COMPLETE generator loss of train.py:280-308: non-saturating GAN term + the reference's own `KD_loss`
+    (train.py:145-184, executed from its source text) with its own lpips.PerceptualLoss, Batch_Img_Parsing and
+    Get_Masked_Tensor; the face parser is a stand-in returning seeded class scores (BiSeNet's call contract), the VGG16
+    weights are re-drawn from a seed.  Both kd_modes; every student gradient."""
+    import argparse
+    import synth
+    ref_lpips = _import_ref_lpips()
+    fns = _ref_train_functions(['KD_loss', 'Downsample_Image_256', 'g_nonsaturating_loss'])
+    c = synth.KD_TINY
+    out = {}
+    disc = synth.load_synth(ref_model.Discriminator(c['size']).double(), c['seed_disc'])
+    student = synth.load_synth(ref_model.Generator(c['size'], c['style_dim'], c['n_mlp'],
+                                                   generator_net_shape=c['student']).double(), c['seed_student'])
+    teacher = synth.load_synth(ref_model.Generator(c['size'], c['style_dim'], c['n_mlp'],
+                                                   generator_net_shape=c['teacher']).double(), c['seed_teacher'])
+    for p in list(disc.parameters()) + list(teacher.parameters()):
+        p.requires_grad_(False)              # train.py:287, :507
+    shapes = [(n.shape[2], n.shape[3]) for n in student.make_noise()]
+    z, noise2, rs = synth.latents_and_noise(c['seed_inputs'], c['batch'], c['style_dim'], shapes + shapes, n_latents=2)
+    z = [torch.from_numpy(a) for a in z]
+    s_noise = [torch.from_numpy(a) for a in noise2[:len(shapes)]]
+    t_noise = [torch.from_numpy(a) for a in noise2[len(shapes):]]
+    loss = ref_lpips.PerceptualLoss(model='net-lin', net='vgg', use_gpu=False)
+    net = loss.model.net.double()
+    vgg = net.net
+    convs = [m for sl in (vgg.slice1, vgg.slice2, vgg.slice3, vgg.slice4, vgg.slice5) for m in sl
+             if isinstance(m, torch.nn.Conv2d)]
+    cw, cb = synth.vgg16_weights(synth.KD_FULL['seed_vgg'])
+    with torch.no_grad():
+        for m, wt, bt in zip(convs, cw, cb):
+            m.weight.copy_(torch.from_numpy(wt))
+            m.bias.copy_(torch.from_numpy(bt))
+    scores = torch.from_numpy(synth.parser_scores(synth.KD_FULL['seed_parser'], c['batch']))
+
+    def parsing_net(x):
+        return (scores,)
+
+    def teacher_g(latents, **kw):            # train.py:151 draws fresh noise; the fixture pins it
+        return teacher(latents, noise=t_noise, **kw)
+    for mode in ('Output_Only', 'Intermediate'):
+        args = argparse.Namespace(kd_mode=mode, kd_l1_lambda=3.0, kd_lpips_lambda=3.0, size=c['size'])
+        student.zero_grad()
+        fake_list = student(z, return_rgb_list=True, inject_index=c['inject'], noise=s_noise)           # train.py:291
+        g_loss = fns['g_nonsaturating_loss'](disc(fake_list[-1]))                                      # train.py:293-294
+        l1, lp = fns['KD_loss'](args, teacher_g, z, c['inject'], fake_list[-1], fake_list, loss, parsing_net)
+        (g_loss + l1 + lp).backward()                                                                  # train.py:304-307
+        out[f'{mode}.g_loss'], out[f'{mode}.kd_l1'], out[f'{mode}.kd_lpips'] = npy(g_loss), npy(l1), npy(lp)
+        for n, p in student.named_parameters():
+            out[f'{mode}.grad.{n}'] = npy(p.grad) if p.grad is not None else np.zeros(tuple(p.shape))
+    for k, lin in enumerate((net.lin0, net.lin1, net.lin2, net.lin3, net.lin4)):
+        out[f'lin{k}'] = npy(lin.model[1].weight.reshape(-1))
+    np.savez_compressed(os.path.join(HERE, 'kd_full_tiny.npz'), **out)
+
+
 if __name__ == '__main__':
     which = sys.argv[1:] or ['upfirdn2d', 'fused_act', 'layers', 'generator']
     sys.path.insert(0, HERE)
     from torch.nn import functional as F  # noqa: E402
     table = {'upfirdn2d': gen_upfirdn2d, 'fused_act': gen_fused_act, 'layers': gen_layers, 'generator': gen_generator,
-             'kd_tiny': gen_kd_tiny, 'rng_order': gen_rng_order, 'config3': gen_config3}
+             'kd_tiny': gen_kd_tiny, 'rng_order': gen_rng_order, 'config3': gen_config3, 'lpips': gen_lpips,
+             'mask_glue': gen_mask_glue, 'kd_full': gen_kd_full}
     for w in which:
         table[w]()
     for f in sorted(os.listdir(HERE)):

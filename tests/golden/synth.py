@@ -74,3 +74,38 @@ def ellipse_mask(size: int) -> np.ndarray:
     yy, xx = np.mgrid[0:size, 0:size]
     c = (size - 1) / 2
     return (((yy - c) / (0.42 * size)) ** 2 + ((xx - c) / (0.34 * size)) ** 2) <= 1
+
+
+# ------------------------------------------------------------------ LPIPS-VGG16 / content-mask fixtures
+LPIPS_TINY = dict(size=32, batch=2, seed_weights=51, seed_inputs=52)
+KD_FULL = dict(seed_vgg=53, seed_parser=54)     # on top of KD_TINY: the complete generator loss (LPIPS + parsed mask)
+VGG16_CHANNELS = (64, 64, 128, 128, 256, 256, 256, 512, 512, 512, 512, 512, 512)
+
+
+def vgg16_weights(seed: int):
+    """The 13 convolutions of torchvision's vgg16().features[0:30], He-scaled N(0, 2/(9 I)) weights and N(0, 0.05^2) biases
+    (the pretrained ones cannot be downloaded; activations keep a sane range through 13 layers)."""
+    rs = np.random.RandomState(seed)
+    ws, bs, cin = [], [], 3
+    for cout in VGG16_CHANNELS:
+        ws.append((rs.standard_normal((cout, cin, 3, 3)) * np.sqrt(2.0 / (9 * cin))).astype(np.float32).astype(np.float64))
+        bs.append((rs.standard_normal((cout,)) * 0.05).astype(np.float32).astype(np.float64))
+        cin = cout
+    return ws, bs
+
+
+def lpips_images(seed: int, batch: int, size: int):
+    """A 'student' and a 'teacher' image in [-1, 1]: smooth content plus a perturbation (pred = target + noise)."""
+    rs = np.random.RandomState(seed)
+    target = np.tanh(rs.standard_normal((batch, 3, size, size))).astype(np.float32).astype(np.float64)
+    pred = np.clip(target + 0.3 * rs.standard_normal(target.shape), -1, 1).astype(np.float32).astype(np.float64)
+    return pred, target
+
+
+def parser_scores(seed: int, n: int, size: int = 512, classes: int = 19):
+    """Stand-in face-parser output: smooth random class scores (blobs a few dozen pixels wide, so the mask has
+    structure), float32 [n, classes, size, size]."""
+    rs = np.random.RandomState(seed)
+    coarse = rs.standard_normal((n, classes, size // 32, size // 32)).astype(np.float32)
+    fine = np.repeat(np.repeat(coarse, 32, axis=2), 32, axis=3)
+    return (fine + 0.35 * rs.standard_normal((n, classes, size, size)).astype(np.float32)).astype(np.float32)

@@ -246,3 +246,76 @@ def test_rng_order_golden(golden_dir):
     sd.update({k: T(v) for k, v in synth.synth_state(tmpl, int(g['seed_weights'])).items()})
     noise = [T(g[f'noise{i}']) for i in range(7)]
     close(O.generator_forward(sd, TINY['size'], [T(g['z'])], noise), g['img'])
+
+
+# ------------------------------------------------------------------ rest of the KD loss: LPIPS-VGG16, content-mask glue
+def test_lpips_oracle_matches_reference_lpips(golden_dir):
+    """oracle.lpips_oracle.lpips_vgg against the reference's own lpips.PerceptualLoss (net-lin, vgg) in fp64."""
+    import sys
+    sys.path.insert(0, golden_dir)
+    import synth
+    from oracle import lpips_oracle as L
+    g = np.load(os.path.join(golden_dir, 'lpips_tiny.npz'))
+    c = synth.LPIPS_TINY
+    cw, cb = synth.vgg16_weights(c['seed_weights'])
+    cw, cb = [T(a) for a in cw], [T(a) for a in cb]
+    lins = [T(g[f'lin{k}']) for k in range(5)]
+    pred_np, target_np = synth.lpips_images(c['seed_inputs'], c['batch'], c['size'])
+    pred = T(pred_np).requires_grad_(True)
+    val = L.lpips_vgg(pred, T(target_np), cw, cb, lins)
+    close(val.detach(), g['val'])
+    gp, = torch.autograd.grad(val, pred, T(g['cot']))
+    close(gp, g['g_pred'], 1e-9)
+    val2 = L.lpips_vgg(pred, T(target_np), cw, cb, lins)
+    kd = 3.0 * val2.mean()
+    close(kd.detach(), g['kd_lpips'])
+    g2, = torch.autograd.grad(kd, pred)
+    close(g2, g['kd_lpips_g'], 1e-9)
+
+
+@pytest.mark.parametrize('tag,size', [('s256', 256), ('s1024', 1024), ('s64', 64)])
+def test_mask_glue_oracle_matches_reference(golden_dir, tag, size):
+    """oracle.lpips_oracle.batch_img_preprocess / content_mask against Batch_Img_Parsing / Get_Masked_Tensor run
+    unmodified (Util/content_aware_pruning.py:61-117)."""
+    import sys
+    sys.path.insert(0, golden_dir)
+    import synth
+    from oracle import lpips_oracle as L
+    g = np.load(os.path.join(golden_dir, 'mask_glue.npz'))
+    n = 2
+    rs = np.random.RandomState(910 + size)
+    img = torch.from_numpy((rs.standard_normal((n, 3, size, size)) * 0.8).astype(np.float32))
+    pre = L.batch_img_preprocess(img)
+    close(pre[:, :, ::7, ::5], g[f'{tag}.pre'], 1e-6)
+    scores = torch.from_numpy(synth.parser_scores(911 + size, n))
+    parsing = scores.argmax(1)
+    assert int(parsing.sum()) == int(g[f'{tag}.parsing_sum'])
+    mask = L.content_mask(parsing, size)
+    want = np.unpackbits(g[f'{tag}.mask'])[:n * size * size].reshape(n, size, size)
+    assert np.array_equal(mask.numpy().astype(np.uint8), want)
+    assert 0.05 < want.mean() < 0.999
+    masked = L.get_masked_tensor(img.double(), parsing)
+    assert abs(float(masked.abs().sum()) - float(g[f'{tag}.masked_sum'])) <= 1e-6 * float(g[f'{tag}.masked_sum'])
+
+
+@pytest.mark.parametrize('mode', ['Output_Only', 'Intermediate'])
+def test_kd_step_full_loss_golden(golden_dir, mode):
+    """oracle.kd_step with the parsed content mask and LPIPS against the fixture produced by the reference's own KD_loss
+    text (train.py:145-184) + lpips.PerceptualLoss + Batch_Img_Parsing / Get_Masked_Tensor."""
+    import synth
+    g0 = np.load(os.path.join(golden_dir, 'kd_tiny.npz'))
+    g = np.load(os.path.join(golden_dir, 'kd_full_tiny.npz'))
+    c, dp, sp, tp, z, s_noise, t_noise, _ = _kd_tiny_inputs(g0)
+    cw, cb = synth.vgg16_weights(synth.KD_FULL['seed_vgg'])
+    lp = ([T(a) for a in cw], [T(a) for a in cb], [T(g[f'lin{k}']) for k in range(5)])
+    parsing = torch.from_numpy(synth.parser_scores(synth.KD_FULL['seed_parser'], c['batch'])).argmax(1)
+    loss, grads = O.kd_step(sp, tp, dp, c['size'], z, s_noise, t_noise, c['inject'], kd_mode=mode, parsing=parsing, lpips=lp)
+    close(loss, g[f'{mode}.g_loss'] + g[f'{mode}.kd_l1'] + g[f'{mode}.kd_lpips'])
+    assert float(g[f'{mode}.kd_lpips']) > 1e-3          # the LPIPS term is a real part of the loss in this fixture
+    for n in g0['param_names']:
+        ref = g[f'{mode}.grad.{n}']
+        got = grads[n].numpy() if n in grads else np.zeros_like(ref)
+        if np.abs(ref).max() == 0:
+            assert np.abs(got).max() == 0, n
+        else:
+            close(got, ref, 1e-9)
