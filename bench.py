@@ -6,10 +6,11 @@ StyleGAN2 student, full-size teacher, global batch 16) -- see DESIGN.md "Measure
     python bench.py --impl reference --gpus N --steps K ...       # the reference's OWN code on the host CPU cores
     python bench.py --config kd1024|fid256|saliency256 ...        # BASELINE.json configs[3], [4], [2]
 
-One step = train.py:280-308 restricted to the hot path and its direct consumers: student forward
-(RGB list) + discriminator forward + GAN loss, teacher forward, masked L1 KD loss, backward, gradient
-all-reduce over ranks, fused Adam.  LPIPS-VGG / BiSeNet are third-party networks outside the path
-(their weights are not available offline) and are excluded on both arms.
+One step = train.py:280-308 (BASELINE.json configs[1]): student forward (RGB list) + discriminator forward + GAN loss,
+teacher forward, BiSeNet face parsing of the teacher image at 512px + content mask, masked L1 + LPIPS-VGG16 KD losses,
+backward, gradient all-reduce over ranks, fused Adam.  The pretrained VGG16 / BiSeNet weights are not available offline:
+both networks run with random weights of the same architecture on every arm.  `--loss kdlike` is the workload of rounds
+1-2 (no LPIPS, no parser; constant content mask); the default run reports it as well under "kd_like".
 
 Scaling: the north star shards the minibatch of 16 over the GPUs of one box, so the headline mode is STRONG
 scaling (global batch 16, per-rank 16/N); the weak-scaling figure (16 per GPU) is measured in the same run and
@@ -38,16 +39,21 @@ GLOBAL_BATCH = 16
 REF_STEP = os.path.join(ROOT, 'oracle', 'ref_step.py')
 
 
-def kd_workload(size):
+def kd_workload(size, loss='full'):
     s = STUDENT_SHAPES[size]
+    if loss == 'full':
+        return (f'KD generator step {size}px (train.py:280-308): 70%-pruned student {s[0]}/{s[-1]}ch f+b, full teacher f, '
+                f'discriminator f+dgrad, BiSeNet parsing @512 + content mask, masked L1 + LPIPS-VGG16'
+                f'{" on bilinear-256" if size > 256 else ""} KD losses (random-init VGG16 / BiSeNet weights), '
+                f'grad all-reduce, Adam; global batch {GLOBAL_BATCH}; style mixing inject_index=5')
     return (f'KD-like generator step {size}px: 70%-pruned student {s[0]}/{s[-1]}ch f+b, full teacher f, '
             f'discriminator f+dgrad, masked L1 KD, grad all-reduce, Adam; global batch {GLOBAL_BATCH}; '
             f'style mixing inject_index=5')
 
 
-def kd_config(size, world):
+def kd_config(size, world, loss='full'):
     """`config` of the JSON line -- identical on the product arm and on the reference arm."""
-    return {'workload': kd_workload(size), 'global_batch': GLOBAL_BATCH, 'parallelism': f'dp{world}',
+    return {'workload': kd_workload(size, loss), 'global_batch': GLOBAL_BATCH, 'parallelism': f'dp{world}',
             'l2': 'per-step working set (>=4 GB of activations) exceeds the 126 MB L2; no explicit flush'}
 
 
@@ -107,11 +113,11 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # reference arms: the reference's own code (oracle/_ref, staged by oracle/stage_ref.py) in its own process
 # ------------------------------------------------------------------------------------------------
-def run_ref_step(device, size, batch, steps, warmup, timeout=1500):
+def run_ref_step(device, size, batch, steps, warmup, timeout=1500, loss='full'):
     """oracle/ref_step.py in a subprocess (the reference's `model` / `op` module names collide with the
     drop-in's).  Returns the parsed JSON or {'unavailable': why}."""
     cmd = [sys.executable, REF_STEP, '--device', device, '--size', str(size), '--batch', str(batch),
-           '--steps', str(steps), '--warmup', str(warmup)]
+           '--steps', str(steps), '--warmup', str(warmup), '--loss', loss]
     env = {k: v for k, v in os.environ.items() if k not in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK', 'MASTER_ADDR',
                                                            'MASTER_PORT', 'CAGC_CONV_ALGO')}
     try:
@@ -128,9 +134,11 @@ def run_ref_step(device, size, batch, steps, warmup, timeout=1500):
 def cpu_baseline_from(ref, sample_b, steps, warmup):
     if 'unavailable' in ref:
         return None
+    what = ("its own KD_loss / lpips / BiSeNet / Batch_Img_Parsing / Get_Masked_Tensor, same KD step"
+            if ref.get('loss_kind') == 'full' else 'same KD-like step')
     return {'value': ref['images_per_s'], 'unit': 'images/s', 'cores': ref['cores'], 'kind': 'reference',
             'sample': f"the reference's own model.py + op/ CPU fallbacks (oracle/_ref, unmodified; {ref['import']}), "
-                      f"same KD-like step, bounded sample: batch {sample_b} per step, {warmup} warm-up + {steps} "
+                      f"{what}, bounded sample: batch {sample_b} per step, {warmup} warm-up + {steps} "
                       f"timed steps, torch {ref['torch']} CPU fp32, {ref['cores']} threads, "
                       f"{ref['sec_per_step']:.2f} s/step"}
 
@@ -143,7 +151,7 @@ def run_reference(args):
         return
     sample_b = 2            # >= 2: Util/content_aware_pruning.py:108 squeezes the batch dim at 1
     warm = max(1, min(args.warmup, 2))
-    ref = run_ref_step('cpu', args.size, sample_b, args.steps, warm)
+    ref = run_ref_step('cpu', args.size, sample_b, args.steps, warm, loss=args.loss)
     if 'unavailable' in ref:
         print(json.dumps({'impl': 'reference', 'unavailable': ref['unavailable']}))
         return
@@ -153,7 +161,7 @@ def run_reference(args):
         'unit': 'images/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
-        'config': kd_config(args.size, args.gpus),
+        'config': kd_config(args.size, args.gpus, args.loss),
         'cpu_baseline': cpu_baseline_from(ref, sample_b, args.steps, warm),
         'e2e': {'value': ips, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
@@ -168,6 +176,25 @@ def synthetic_mask(size, device):
     yy, xx = torch.meshgrid(torch.arange(size, device=device), torch.arange(size, device=device), indexing='ij')
     c = (size - 1) / 2
     return ((((yy - c) / (0.42 * size)) ** 2 + ((xx - c) / (0.34 * size)) ** 2) <= 1).float().view(1, 1, size, size)
+
+
+def kd_loss_networks(torch, dev):
+    """LPIPS-VGG16 on the package's own kernels and the BiSeNet-architecture face parser (library convolutions), both
+    with random weights of the reference architectures (torchvision's VGG16 initialiser: kaiming-normal fan-out, zero
+    bias; non-negative lin heads as in lpips/weights/v0.1/vgg.pth).  Returns (percept_loss, parsing_net)."""
+    from b200gan.lpips import PerceptualLossVGG, VGG16_CFG
+    from b200gan.parsing import FaceParser, synthetic_state_dict
+    g = torch.Generator().manual_seed(99)
+    cws, cbs, cin = [], [], 3
+    for c in [c for c in VGG16_CFG if c != 'M']:
+        cws.append(torch.randn(c, cin, 3, 3, generator=g) * (2.0 / (9 * c)) ** 0.5)
+        cbs.append(torch.zeros(c))
+        cin = c
+    lins = [torch.rand(c, generator=g) for c in (64, 128, 256, 512, 512)]
+    percept = PerceptualLossVGG(cws, cbs, lins).to(dev)
+    parser = FaceParser.from_state_dict(synthetic_state_dict(0)).to(dev)
+    torch.backends.cudnn.benchmark = True           # the parser's library convolutions (autotuned during warm-up)
+    return percept, parser
 
 
 class Ctx:
@@ -241,7 +268,10 @@ def bench_kd(args, cx):
     disc = model.Discriminator(size).to(dev)
     for m in (teacher, student, disc):
         cx.broadcast_module(m)                      # identical replicas on every rank
-    kd = KDStep(student, teacher, disc, mask=synthetic_mask(size, dev))
+    full = args.loss == 'full'
+    percept, parser = kd_loss_networks(torch, dev) if full else (None, None)
+    kd = KDStep(student, teacher, disc, percept_loss=percept, parsing_net=parser,
+                mask=None if full else synthetic_mask(size, dev))
 
     def fresh_latents(b):
         return [torch.randn(b, 512, device=dev), torch.randn(b, 512, device=dev)]
@@ -346,6 +376,17 @@ def bench_kd(args, cx):
         other = {'scaling': 'weak' if strong else 'strong', 'per_gpu_batch': B2, 'global_batch': B2 * world,
                  'value': world * B2 * args.steps / (ms2 / 1e3), 'unit': 'images/s', 'ms_per_step': ms2 / args.steps}
 
+    # ---------------- the rounds-1/2 workload ("KD-like": no LPIPS, no parser, constant mask), same modules, same run
+    kd_like = None
+    if full and not args.no_kd_like:
+        kd.percept_loss, kd.parsing_net, kd.mask = None, None, synthetic_mask(size, dev)
+        del kd.graph
+        kd.graph = None
+        ms3, _, _, _, _ = measure(kd, B, args.steps, args.warmup, False)
+        kd_like = {'value': world * B * args.steps / (ms3 / 1e3), 'unit': 'images/s', 'ms_per_step': ms3 / args.steps,
+                   'workload': kd_workload(size, 'kdlike')}
+        kd.percept_loss, kd.parsing_net, kd.mask = percept, parser, None
+
     if rank != 0:
         return
     peaks = load_peaks()
@@ -364,7 +405,7 @@ def bench_kd(args, cx):
                          'avg_launch_us': per * 1e3,
                          'tflops': (r['flops'] / (r['ms'] / 1e3) / 1e12) if r['flops'] and r['ms'] else None,
                          'gbs': (r['bytes'] / (r['ms'] / 1e3) / 1e9) if r['bytes'] and r['ms'] else None}
-    conv_names = [n for n in summ if n.startswith('conv_') or n.startswith('dconv')]
+    conv_names = [n for n in summ if n.startswith('conv_') or n.startswith('dconv') or n.startswith('lpips_conv')]
     dom = max(conv_names, key=lambda n: summ[n]['ms']) if conv_names else None
     roofline = None
     if dom:
@@ -405,18 +446,19 @@ def bench_kd(args, cx):
         hbm['fir_nhwc[largest]'] = {'bound': 'hbm', 'layer': k.split('@')[1], 'achieved': fl[k]['gbs'],
                                     'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': fl[k]['gbs'] / peaks['hbm_gbs'],
                                     'avg_launch_us': fl[k]['avg_launch_us']}
-    cl = {k: v for k, v in layers.items() if (k.startswith('conv_') or k.startswith('dconv')) and v['tflops']}
+    cl = {k: v for k, v in layers.items() if k.startswith(('conv_', 'dconv', 'lpips_conv')) and v['tflops']}
     top_layers = {k: cl[k] for k in sorted(cl, key=lambda k: -cl[k]['avg_launch_us'] * cl[k]['launches_per_step'])[:6]}
 
     cpu, ref_gpu = None, None
     if world == 1 and not args.no_cpu_baseline:
-        ref = run_ref_step('cpu', size, 2, 2, 1, timeout=600)
+        ref = run_ref_step('cpu', size, 2, 2, 1, timeout=600, loss=args.loss)
         cpu = cpu_baseline_from(ref, 2, 2, 1) or {'unavailable': ref.get('unavailable')}
     if world == 1 and not args.no_ref_gpu:
         # the real competitor: the reference CUDA path -- its SIMT op/*.cu compiled for sm_100a +
         # cuDNN grouped convolutions (TF32 allowed, torch's default) -- on this same B200, full batch, CUDA events
         torch.cuda.empty_cache()
-        rg = run_ref_step('cuda', size, GLOBAL_BATCH, 30 if size == 256 else 6, 8 if size == 256 else 2, timeout=900)
+        rg = run_ref_step('cuda', size, GLOBAL_BATCH, 30 if size == 256 else 6, 8 if size == 256 else 2, timeout=900,
+                          loss=args.loss)
         if 'unavailable' in rg:
             ref_gpu = rg
         else:
@@ -424,7 +466,9 @@ def bench_kd(args, cx):
                        'batch': rg['batch'], 'steps': rg['steps'], 'warmup': rg['warmup'], 'tf32': rg['tf32'],
                        'speedup_of_this_repo': value / rg['images_per_s'],
                        'what': "the reference's own model.py + op/*.cu (sm_100a JIT build) + cuDNN on this B200, "
-                               'same KD-like step, eager (no CUDA graph: the reference has none)'}
+                               + ('its own KD_loss / lpips / BiSeNet / mask glue, same KD step'
+                                  if rg.get('loss_kind') == 'full' else 'same KD-like step')
+                               + ', eager (no CUDA graph: the reference has none and its mask glue syncs with the host)'}
 
     gf = GFLOP_PER_IMG[size]
     line = {
@@ -432,7 +476,8 @@ def bench_kd(args, cx):
         'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_total / args.steps,
         'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None,
         'dtype': 'tf32' if cx.tf32 else 'f32', 'data': 'synthetic',
-        'config': kd_config(size, world) if strong else dict(kd_config(size, world), global_batch=B * world),
+        'config': kd_config(size, world, args.loss) if strong
+        else dict(kd_config(size, world, args.loss), global_batch=B * world),
         'config_detail': {'per_gpu_batch': B, 'conv_algo': 'tcgen05-tf32' if cx.tf32 else 'simt-fp32',
                    'launch': ('one CUDA graph per step' if use_graph else 'eager launches') + (', teacher forward on a parallel graph branch' if kd.teacher_stream is not None else ''),
                    'kernel_timing': f'CUDA events around each native launch over {prof_steps} eager steps in this run'},
@@ -446,6 +491,7 @@ def bench_kd(args, cx):
         'reference_gpu': ref_gpu,
         'sustained': sustained,
         ('weak_scaling' if strong else 'strong_scaling'): other,
+        'kd_like': kd_like,
         'generator_slice': {'ms_per_step': slice_ms, 'images_per_s': B / (slice_ms / 1e3),
                             'tflops': B * (3 * gf['student'] + gf['teacher']) / slice_ms,
                             'note': 'student f+b + teacher f only, rank 0'},
@@ -582,6 +628,9 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-ref-gpu', action='store_true')
     ap.add_argument('--no-second-mode', action='store_true')
+    ap.add_argument('--loss', default='full', choices=['full', 'kdlike'],
+                    help='full: train.py:280-308 with parser + LPIPS (configs[1]); kdlike: the rounds-1/2 workload')
+    ap.add_argument('--no-kd-like', action='store_true', help='skip the secondary measurement of the KD-like workload')
     ap.add_argument('--all-layers', action='store_true', help='add every per-layer kernel record to the JSON line')
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel from Python instead of one CUDA graph per step')
     args = ap.parse_args()

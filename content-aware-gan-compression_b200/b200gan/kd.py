@@ -69,23 +69,26 @@ class KDStep:
         main = torch.cuda.current_stream(self.device)
         ready = main.record_event() if self.teacher_stream is not None else None
         fake = self.student(z, return_rgb_list=True, inject_index=inject_index, noise=s_noise)
+        mask = self.mask
         if self.teacher_stream is not None:
             self.teacher_stream.wait_event(ready)
             with torch.cuda.stream(self.teacher_stream), torch.no_grad():
                 real = self.teacher(z, return_rgb_list=True, inject_index=inject_index, noise=t_noise)
                 for r in real:
                     r.record_stream(main)
+                if self.parsing_net is not None:     # the face parser only needs the teacher image: same branch
+                    mask = maskglue.content_mask(real[-1], self.parsing_net)
+                    mask.record_stream(main)
         else:
             with torch.no_grad():
                 real = self.teacher(z, return_rgb_list=True, inject_index=inject_index, noise=t_noise)
+                if self.parsing_net is not None:
+                    mask = maskglue.content_mask(real[-1], self.parsing_net)
         g_loss = F.softplus(-self.disc(fake[-1])).mean()
         if self.teacher_stream is not None:
             main.wait_stream(self.teacher_stream)
         # content-aware adjustment (train.py:154-158): the mask comes from parsing the TEACHER image and multiplies both
         s_img, t_img = fake[-1], real[-1]
-        mask = self.mask
-        if self.parsing_net is not None:
-            mask = maskglue.content_mask(t_img, self.parsing_net)
         if mask is not None:
             s_img, t_img = s_img * mask, t_img * mask
         if self.kd_mode == 'Output_Only':                      # train.py:163-164

@@ -44,9 +44,26 @@ def parsing_mask(logits: torch.Tensor, size: int) -> torch.Tensor:
     return mask
 
 
+def parsing_mask_lowres(scores: torch.Tensor, size: int, parsing_size: int = PARSING_SIZE) -> torch.Tensor:
+    """Low-resolution class scores [N,K,h,w] (before BiSeNet's final align_corners=True upsample to parsing_size) ->
+    content mask [N,1,size,size]; any memory layout."""
+    require_cuda(scores, 'parsing_mask_lowres')
+    n, k, h, w = scores.shape
+    sc = scores.detach()
+    mask = torch.empty((n, 1, size, size), device=scores.device, dtype=torch.float32)
+    sn, sk, sh, sw = sc.stride()
+    with torch.cuda.device(scores.device):
+        check(lib.cagc_parsing_mask_lowres(stream_of(sc), sc.data_ptr(), sn, sk, sh, sw, mask.data_ptr(), n, k, h, w,
+                                           parsing_size, size), 'parsing_mask_lowres')
+    return mask
+
+
 def content_mask(teacher_img: torch.Tensor, parsing_net, parsing_size: int = PARSING_SIZE) -> torch.Tensor:
     """`Batch_Img_Parsing` + the mask half of `Get_Masked_Tensor`: [N,1,S,S]; `parsing_net(x)[0]` are the class scores
-    (BiSeNet's call contract, Util/face_parsing/BiSeNet.py:230-254)."""
+    (BiSeNet's call contract, Util/face_parsing/BiSeNet.py:230-254).  A parser that offers `scores_lowres(x)` (b200gan.
+    parsing.FaceParser) is asked for the scores before its final upsample, which then happens inside the mask kernel."""
     with torch.no_grad():
-        scores = parsing_net(parse_preprocess(teacher_img, parsing_size))[0]
-        return parsing_mask(scores.float(), teacher_img.shape[-1])
+        x = parse_preprocess(teacher_img, parsing_size)
+        if hasattr(parsing_net, 'scores_lowres'):
+            return parsing_mask_lowres(parsing_net.scores_lowres(x).float(), teacher_img.shape[-1], parsing_size)
+        return parsing_mask(parsing_net(x)[0].float(), teacher_img.shape[-1])

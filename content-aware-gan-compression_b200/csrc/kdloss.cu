@@ -97,6 +97,60 @@ __global__ void __launch_bounds__(256) parsing_mask_kernel(const float* __restri
     }
 }
 
+// The same mask from the parser's LOW-RESOLUTION class scores [N,K,h,w] (element strides: any layout): the final
+// F.interpolate(..., (P, P), mode='bilinear', align_corners=True) of BiSeNet.forward (Util/face_parsing/BiSeNet.py:247)
+// is evaluated per needed grid point inside the kernel, so the [N,K,P,P] tensor (318 MB at N = 16) is never written.
+struct LrP {
+    const float* lr;
+    int64_t sn, sk, sh, sw;
+    float* mask;
+    int N, K, h, w, P, S;
+    float inv_scale, ry, rx;      // P/S; (h-1)/(P-1), (w-1)/(P-1)
+};
+
+__device__ __forceinline__ float fg_bit_lowres(const LrP& p, const float* __restrict__ base, int Y, int X) {
+    // align_corners=True source coordinates (ATen area_pixel_compute_source_index): src = dst * (in - 1) / (out - 1)
+    const float fy = p.ry * (float)Y, fx = p.rx * (float)X;
+    const int y0 = (int)fy, x0 = (int)fx;
+    const int y1 = y0 + (y0 < p.h - 1 ? 1 : 0), x1 = x0 + (x0 < p.w - 1 ? 1 : 0);
+    const float ly1 = fy - (float)y0, lx1 = fx - (float)x0;
+    const float ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+    const float* p00 = base + y0 * p.sh + x0 * p.sw;
+    const float* p01 = base + y0 * p.sh + x1 * p.sw;
+    const float* p10 = base + y1 * p.sh + x0 * p.sw;
+    const float* p11 = base + y1 * p.sh + x1 * p.sw;
+    float m = 0.f;
+    int arg = 0;
+    for (int k = 0; k < p.K; ++k) {
+        const int64_t o = k * p.sk;
+        const float v = ly0 * (lx0 * __ldg(p00 + o) + lx1 * __ldg(p01 + o)) + ly1 * (lx0 * __ldg(p10 + o) + lx1 * __ldg(p11 + o));
+        if (k == 0 || v > m) { m = v; arg = k; }
+    }
+    return (arg > 0 && arg != 16) ? 1.f : 0.f;
+}
+
+__global__ void __launch_bounds__(256) parsing_mask_lowres_kernel(const __grid_constant__ LrP p) {
+    const int64_t total = (int64_t)p.N * p.S * p.S;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+        const int x = (int)(i % p.S);
+        const int64_t q = i / p.S;
+        const int y = (int)(q % p.S);
+        const int n = (int)(q / p.S);
+        const Bilerp by = bilerp_index(y, p.inv_scale, p.P), bx = bilerp_index(x, p.inv_scale, p.P);
+        const float* base = p.lr + n * p.sn;
+        const float b00 = fg_bit_lowres(p, base, by.i0, bx.i0);
+        const float b01 = (bx.i1 != bx.i0) ? fg_bit_lowres(p, base, by.i0, bx.i1) : b00;
+        float b10 = b00, b11 = b01;
+        if (by.i1 != by.i0) {
+            b10 = fg_bit_lowres(p, base, by.i1, bx.i0);
+            b11 = (bx.i1 != bx.i0) ? fg_bit_lowres(p, base, by.i1, bx.i1) : b10;
+        }
+        const float top = b00 * (1.f - bx.l1) + b01 * bx.l1;
+        const float bot = b10 * (1.f - bx.l1) + b11 * bx.l1;
+        p.mask[i] = (top * (1.f - by.l1) + bot * by.l1) > 0.5f ? 1.f : 0.f;
+    }
+}
+
 static inline unsigned kd_grid_1d(int64_t work_items, int per_block) {
     int64_t blocks = ceil_div<int64_t>(work_items, per_block);
     const int64_t cap = (int64_t)kNumSMs * 16;
@@ -134,6 +188,22 @@ int cagc_parsing_mask(cagc_stream_t stream_, const float* logits, float* mask, i
     parsing_mask_kernel<<<kd_grid_1d((int64_t)N * S * S, 256), 256, 0, stream>>>(logits, mask, N, K, P, S,
                                                                                  1.f / ((float)S / (float)P));
     return launched("parsing_mask_kernel");
+}
+
+int cagc_parsing_mask_lowres(cagc_stream_t stream_, const float* scores, int64_t sn, int64_t sk, int64_t sh, int64_t sw,
+                             float* mask, int N, int K, int h, int w, int P, int S) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CAGC_REQUIRE(scores && mask, "parsing_mask_lowres: null pointer");
+    CAGC_REQUIRE(N >= 0 && K >= 1 && h >= 1 && w >= 1 && P >= 2 && S >= 1, "parsing_mask_lowres: bad size");
+    if (N == 0) return 0;
+    LrP p;
+    p.lr = scores; p.sn = sn; p.sk = sk; p.sh = sh; p.sw = sw; p.mask = mask;
+    p.N = N; p.K = K; p.h = h; p.w = w; p.P = P; p.S = S;
+    p.inv_scale = 1.f / ((float)S / (float)P);
+    p.ry = (float)(h - 1) / (float)(P - 1);
+    p.rx = (float)(w - 1) / (float)(P - 1);
+    parsing_mask_lowres_kernel<<<kd_grid_1d((int64_t)N * S * S, 256), 256, 0, stream>>>(p);
+    return launched("parsing_mask_lowres_kernel");
 }
 
 }  // extern "C"

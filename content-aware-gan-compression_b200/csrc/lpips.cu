@@ -74,6 +74,86 @@ __global__ void __launch_bounds__(256) rgb_conv3x3_fwd_kernel(const float* __res
     }
 }
 
+// Register-blocked form for 32..256 output channels: one thread = 4 output channels of 8 ADJACENT pixels, so a weight
+// vector is read from shared memory once per 8 pixels and an input value once per 3 taps; the scaled input rows of a
+// segment (3 rows x (segment + 2) pixels x 3 channels, zero outside the image) are staged in shared memory.  The 16 (or
+// 8, 32, 64) threads that share a pixel read the same input address (broadcast) and store 256 contiguous bytes.
+template <int PX>
+__global__ void __launch_bounds__(256) rgb_conv3x3_fwd_tiled_kernel(const float* __restrict__ img, int64_t sb, int64_t sc,
+                                                                    int64_t sh, int64_t sw, const float* __restrict__ w,
+                                                                    const float* __restrict__ bias, float* __restrict__ out,
+                                                                    int B, int H, int W, int cout, int pitch, RgbAffine aff) {
+    extern __shared__ float sw_[];          // [27][pitch] weights, [pitch] bias, [9][PW] input patch
+    const int c4n = pitch >> 2;
+    const int groups = 256 / c4n;           // pixel groups per CTA
+    const int seg = groups * PX;            // pixels per segment
+    const int PW = seg + 2;
+    float* sbias = sw_ + 27 * pitch;
+    float* s_in = sbias + pitch;
+    for (int i = threadIdx.x; i < 27 * pitch; i += 256) {
+        const int r = i / pitch, o = i - r * pitch;
+        const int t = r / 3, c = r - t * 3;
+        sw_[i] = (o < cout) ? __ldg(w + (o * 3 + c) * 9 + t) : 0.f;
+    }
+    for (int i = threadIdx.x; i < pitch; i += 256) sbias[i] = (bias && i < cout) ? __ldg(bias + i) : 0.f;
+    const int c4 = threadIdx.x % c4n, xg = threadIdx.x / c4n;
+    const int nseg = (W + seg - 1) / seg;
+    const int64_t items = (int64_t)B * H * nseg;
+    for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
+        const int sgi = (int)(it % nseg);
+        const int64_t row = it / nseg;
+        const int b = (int)(row / H), y = (int)(row - (int64_t)b * H);
+        const int x0 = sgi * seg;
+        __syncthreads();                    // previous patch fully consumed (and the weights visible on the first pass)
+        for (int i = threadIdx.x; i < 9 * PW; i += 256) {
+            const int r = i / PW, q = i - r * PW;
+            const int c = r / 3, ky = r - c * 3;
+            const int yy = y + ky - 1, xx = x0 + q - 1;
+            float v = 0.f;
+            if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+                const float sft = c == 0 ? aff.shift[0] : (c == 1 ? aff.shift[1] : aff.shift[2]);       // no local-memory copy
+                const float isc = c == 0 ? aff.inv_scale[0] : (c == 1 ? aff.inv_scale[1] : aff.inv_scale[2]);
+                v = (__ldg(img + b * sb + c * sc + yy * sh + xx * sw) - sft) * isc;
+            }
+            s_in[i] = v;
+        }
+        __syncthreads();
+        float4 acc[PX];
+        const float4 b4 = ld4(sbias + c4 * 4);
+#pragma unroll
+        for (int j = 0; j < PX; ++j) acc[j] = b4;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+                float iv[PX + 2];
+#pragma unroll
+                for (int q = 0; q < PX + 2; ++q) iv[q] = s_in[(c * 3 + ky) * PW + xg * PX + q];
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const float4 wv = ld4(sw_ + ((ky * 3 + kx) * 3 + c) * pitch + c4 * 4);
+#pragma unroll
+                    for (int j = 0; j < PX; ++j) {
+                        acc[j].x = fmaf(iv[j + kx], wv.x, acc[j].x);
+                        acc[j].y = fmaf(iv[j + kx], wv.y, acc[j].y);
+                        acc[j].z = fmaf(iv[j + kx], wv.z, acc[j].z);
+                        acc[j].w = fmaf(iv[j + kx], wv.w, acc[j].w);
+                    }
+                }
+            }
+        }
+        float* orow = out + (row * W + x0 + xg * PX) * pitch + c4 * 4;
+#pragma unroll
+        for (int j = 0; j < PX; ++j) {
+            if (x0 + xg * PX + j < W) {
+                float4 o = acc[j];
+                o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+                st4(orow + (int64_t)j * pitch, o);
+            }
+        }
+    }
+}
+
 // g_img[b,c,Y,X] = inv_scale[c] * sum_{ky,kx,o} w[o,c,ky,kx] * gz[b, Y-ky+1, X-kx+1, o]   (gz already carries the ReLU
 // mask of conv1_1).  8 lanes per pixel, 32 pixels per CTA step.
 __global__ void __launch_bounds__(256) rgb_conv3x3_bwd_kernel(const float* __restrict__ gz, const float* __restrict__ w,
@@ -366,6 +446,17 @@ int cagc_rgb_conv3x3_fwd(cagc_stream_t stream_, const float* img, int64_t sb, in
     CAGC_REQUIRE(aligned16(out), "rgb_conv3x3_fwd: output must be 16-byte aligned");
     CAGC_REQUIRE(B >= 0 && H >= 0 && W >= 0, "rgb_conv3x3_fwd: negative size");
     if ((int64_t)B * H * W == 0) return 0;
+    const int c4n = pitch / 4;
+    if (c4n >= 8 && 256 % c4n == 0) {
+        constexpr int PX = 8;
+        const int seg = (256 / c4n) * PX;
+        const size_t smem_t = ((size_t)28 * pitch + 9 * (seg + 2)) * sizeof(float);
+        const int64_t items = (int64_t)B * H * ceil_div(W, seg);
+        const unsigned blocks = (unsigned)std::min<int64_t>(items, (int64_t)kNumSMs * 6);
+        rgb_conv3x3_fwd_tiled_kernel<PX><<<blocks, 256, smem_t, stream>>>(img, sb, sc, sh, sw, w, bias, out, B, H, W, cout,
+                                                                          pitch, make_affine(shift_host, scale_host));
+        return launched("rgb_conv3x3_fwd_tiled_kernel");
+    }
     const size_t smem = (size_t)28 * pitch * sizeof(float);
     dim3 grid((unsigned)std::min(8, ceil_div(W * (pitch / 4), 256)), (unsigned)std::min(B * H, kNumSMs * 8));
     rgb_conv3x3_fwd_kernel<<<grid, 256, smem, stream>>>(img, sb, sc, sh, sw, w, bias, out, B, H, W, cout, pitch,

@@ -37,7 +37,7 @@ typedef void* cagc_stream_t; /* cudaStream_t */
 #define CAGC_E_UNSUPPORTED (-2) /* shape outside what the kernels implement */
 
 /* bump when a signature changes; the Python loader checks it */
-#define CAGC_ABI_VERSION 20
+#define CAGC_ABI_VERSION 21
 
 int cagc_abi_version(void);
 const char* cagc_last_error(void);
@@ -397,6 +397,11 @@ int cagc_lpips_head_bwd(cagc_stream_t stream, const float* fs, const float* ft, 
 int cagc_parse_preprocess(cagc_stream_t stream, const float* img, int64_t sb, int64_t sc, int64_t sh, int64_t sw,
                           float* out, int N, int S, int P);
 int cagc_parsing_mask(cagc_stream_t stream, const float* logits, float* mask, int N, int K, int P, int S);
+/* The same mask from the parser's low-resolution scores [N,K,h,w] (element strides sn, sk, sh, sw): the final
+ * F.interpolate(scores, (P, P), bilinear, align_corners=True) of BiSeNet.forward (Util/face_parsing/BiSeNet.py:247) is
+ * evaluated inside the kernel instead of being materialised. */
+int cagc_parsing_mask_lowres(cagc_stream_t stream, const float* scores, int64_t sn, int64_t sk, int64_t sh, int64_t sw,
+                             float* mask, int N, int K, int h, int w, int P, int S);
 
 #ifdef __cplusplus
 }

@@ -8,9 +8,12 @@ oracle/_ref/ (oracle/stage_ref.py) -- TEST / BASELINE INFRASTRUCTURE ONLY.
 The step is train.py:280-308 composed from the reference's own `model.Generator` / `model.Discriminator`
 (its `op/` kernels, cuDNN grouped convolutions / native CPU fallbacks) exactly as bench.py's product arm composes
 it: student forward with rgb list -> discriminator -> g_nonsaturating_loss (train.py:215-218); teacher forward
-(eval, requires_grad False: train.py:500-503); constant content mask (stand-in for BiSeNet, as on the product
-arm); L1 KD 'Output_Only' (train.py:163-164); generator.zero_grad(); backward; torch.optim.Adam with the
-reference's hyper-parameters (train.py:528-532).  LPIPS / BiSeNet are excluded on both arms.
+(eval, requires_grad False: train.py:500-503); then, with `--loss full` (default), the reference's OWN `KD_loss`
+(train.py:145-184, its function text executed from the staged train.py) with its own `lpips.PerceptualLoss`
+(net-lin VGG16: torchvision architecture, random weights -- the pretrained ones cannot be downloaded -- and the vendored
+lin heads), its own BiSeNet class (random weights: 79999_iter.pth is not staged), `Batch_Img_Parsing` and
+`Get_Masked_Tensor`; with `--loss kdlike` a constant content mask and the L1 term only (rounds 1-2 workload);
+generator.zero_grad(); backward; torch.optim.Adam with the reference's hyper-parameters (train.py:528-532).
 
 Runs in its own process: `model` / `op` here are the REFERENCE's modules (the product's drop-in modules have the
 same names).  Prints one JSON line.
@@ -54,6 +57,45 @@ def import_reference(device):
     return ref_model, how
 
 
+def reference_kd_loss(device_str):
+    """(KD_loss, percept_loss, parsing_net) built from the reference's own code.  train.py parses the command line and
+    builds datasets at import, so its function definitions are executed from the source text instead."""
+    import ast
+    import types
+    import torch
+    import torch.nn.functional as F
+    import numpy as np
+    for name in ('skimage', 'skimage.measure', 'skimage.color', 'skimage.transform', 'IPython'):
+        if name not in sys.modules:                  # lpips/__init__.py:7, networks_basic.py:11-12 (unused by net-lin)
+            try:
+                __import__(name)
+            except Exception:
+                m = types.ModuleType(name)
+                m.__path__ = []
+                sys.modules[name] = m
+    sys.modules['skimage.measure'].__dict__.setdefault('compare_ssim', None)
+    sys.modules['IPython'].__dict__.setdefault('embed', lambda *a, **k: None)
+    import torchvision.models as tvm
+    real_vgg = tvm.vgg16
+    tvm.vgg16 = lambda pretrained=True, **k: real_vgg(weights=None)        # no network: random VGG16
+    import torch.utils.model_zoo as mz
+    mz.load_url = lambda *a, **k: {}                                        # resnet.py:83: random ResNet18
+    import lpips
+    import train_hyperparams
+    from Util.content_aware_pruning import Batch_Img_Parsing, Get_Masked_Tensor
+    from Util.face_parsing.BiSeNet import BiSeNet
+    ns = {'torch': torch, 'F': F, 'np': np, 'train_hyperparams': train_hyperparams, 'device': device_str,
+          'Batch_Img_Parsing': Batch_Img_Parsing, 'Get_Masked_Tensor': Get_Masked_Tensor}
+    path = os.path.join(REF, 'train.py')
+    for node in ast.parse(open(path).read()).body:
+        if isinstance(node, ast.FunctionDef) and node.name in ('KD_loss', 'Downsample_Image_256'):
+            exec(compile(ast.Module(body=[node], type_ignores=[]), path, 'exec'), ns)
+    gpu = device_str != 'cpu'
+    percept = lpips.PerceptualLoss(model='net-lin', net='vgg', use_gpu=gpu, gpu_ids=[0])       # train.py:510
+    parsing_net = BiSeNet(n_classes=19).to(device_str).eval()                                   # content_aware_pruning.py:24-28
+    return ns['KD_loss'], percept, parsing_net
+
+
 def synthetic_mask(size, device):
     import torch
     yy, xx = torch.meshgrid(torch.arange(size, device=device), torch.arange(size, device=device), indexing='ij')
@@ -70,6 +112,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=1)
     ap.add_argument('--threads', type=int, default=0)
     ap.add_argument('--tf32', type=int, default=1, help='cuDNN / cuBLAS TF32 (torch default for convolutions: on)')
+    ap.add_argument('--loss', default='full', choices=['full', 'kdlike'])
     args = ap.parse_args()
 
     import torch
@@ -92,6 +135,10 @@ def main():
     g_optim = torch.optim.Adam(student.parameters(), lr=0.002 * 0.8, betas=(0.0, 0.99 ** 0.8))   # train.py:528-532
     mask = synthetic_mask(size, dev)
     inject = 5
+    full = args.loss == 'full'
+    if full:
+        kd_loss_fn, percept, parsing_net = reference_kd_loss('cuda:0' if args.device == 'cuda' else 'cpu')
+        kd_args = argparse.Namespace(kd_mode='Output_Only', kd_l1_lambda=3.0, kd_lpips_lambda=3.0, size=size)
 
     def step(z):
         for p in student.parameters():
@@ -100,9 +147,13 @@ def main():
             p.requires_grad_(False)                              # train.py:287
         fake_list = student(z, return_rgb_list=True, inject_index=inject)          # train.py:291
         g_loss = F.softplus(-disc(fake_list[-1])).mean()                          # train.py:293-294
-        real = teacher(z, return_rgb_list=True, inject_index=inject)[-1]          # train.py:151-152
-        kd = 3.0 * torch.mean(torch.abs(real * mask - fake_list[-1] * mask))      # train.py:157-164
-        total = g_loss + kd
+        if full:
+            l1, lp = kd_loss_fn(kd_args, teacher, z, inject, fake_list[-1], fake_list, percept, parsing_net)   # train.py:301
+            total = g_loss + l1 + lp                                                # train.py:304
+        else:
+            real = teacher(z, return_rgb_list=True, inject_index=inject)[-1]      # train.py:151-152
+            kd = 3.0 * torch.mean(torch.abs(real * mask - fake_list[-1] * mask))  # train.py:157-164
+            total = g_loss + kd
         student.zero_grad()                                                       # train.py:306
         total.backward()
         g_optim.step()
@@ -134,7 +185,7 @@ def main():
         sec = time.perf_counter() - t0
     out = {'impl': 'reference', 'device': args.device, 'size': size, 'batch': B, 'steps': args.steps,
            'warmup': args.warmup, 'sec_per_step': sec / args.steps, 'images_per_s': B * args.steps / sec,
-           'cores': cores, 'loss': float(loss), 'import': how, 'torch': torch.__version__,
+           'cores': cores, 'loss': float(loss.detach()), 'loss_kind': args.loss, 'import': how, 'torch': torch.__version__,
            'tf32': bool(args.tf32) if args.device == 'cuda' else None,
            'source': 'oracle/_ref (byte-identical copy of the reference, see MANIFEST.json)'}
     if args.device == 'cuda':

@@ -18,7 +18,12 @@ dev = torch.device('cuda')
 teacher = model.Generator(size, 512, 8).to(dev)
 student = model.Generator(size, 512, 8, generator_net_shape=bench.STUDENT_SHAPES[size]).to(dev)
 disc = model.Discriminator(size).to(dev)
-kd = KDStep(student, teacher, disc, mask=bench.synthetic_mask(size, dev))
+if os.environ.get('LOSS', 'full') == 'full':
+    percept, parser = bench.kd_loss_networks(torch, dev)
+    kd = KDStep(student, teacher, disc, percept_loss=percept, parsing_net=parser)
+else:
+    kd = KDStep(student, teacher, disc, mask=bench.synthetic_mask(size, dev))
+kd.teacher_stream = None          # one stream: the launch list is in program order
 z = lambda: [torch.randn(B, 512, device=dev), torch.randn(B, 512, device=dev)]
 for _ in range(3):
     kd.step(z(), 5)

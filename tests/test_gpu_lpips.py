@@ -278,3 +278,31 @@ def test_kd_step_with_lpips_captures_into_a_graph(golden_dir):
         graphed.capture(c['batch'], c['inject'], style_dim=c['style_dim'])
         l_graph = float(graphed.step_graphed(z))
     assert abs(l_eager - l_graph) <= 1e-5 * abs(l_eager), (l_eager, l_graph)
+
+
+def test_face_parser_gpu_forms_agree():
+    """FaceParser on the GPU: the fused cuDNN calls (conv + bias [+ residual] + ReLU) against the plain conv -> add -> relu
+    composition in fp32 without TF32, and the low-resolution mask path (upsample inside the mask kernel) against
+    materialising the 512^2 scores."""
+    from b200gan import maskglue
+    from b200gan.parsing import FaceParser, synthetic_state_dict
+    torch.backends.cudnn.allow_tf32 = False
+    fp = FaceParser.from_state_dict(synthetic_state_dict(7)).cuda()
+    img = torch.tanh(torch.randn(2, 3, 256, 256, generator=torch.Generator().manual_seed(1))).cuda()
+    x = maskglue.parse_preprocess(img)
+    with torch.no_grad():
+        fp.fused = True
+        a = fp(x)[0]
+        lr = fp.scores_lowres(x)
+        fp.fused = False
+        b = fp(x)[0]
+    assert tuple(a.shape) == (2, 19, 512, 512) and tuple(lr.shape) == (2, 19, 64, 64)
+    assert relmax(a, b) <= 1e-4
+    m_full = maskglue.parsing_mask(a, 256)
+    fp.fused = True
+    m_lr = maskglue.content_mask(img, fp)
+    assert tuple(m_lr.shape) == (2, 1, 256, 256)
+    # same arithmetic up to the order of fp32 operations in the upsample: near-ties of two classes may flip single pixels
+    assert float((m_full != m_lr).float().mean()) <= 1e-3
+    assert 0.02 < float(m_lr.mean()) < 0.999
+    torch.backends.cudnn.allow_tf32 = True
