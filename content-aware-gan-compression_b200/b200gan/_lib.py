@@ -17,7 +17,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # CAGC_LIB: another build of the same library (A/B timing of two revisions on one box, scripts/build_rev.sh)
 LIB_PATH = os.environ.get('CAGC_LIB') or os.path.join(os.path.dirname(_HERE), 'lib', 'libcagc_b200.so')
-ABI_VERSION = 21
+ABI_VERSION = 22
 
 _p = C.c_void_p
 _i = C.c_int
@@ -83,7 +83,7 @@ SIGNATURES = {
     'cagc_lpips_head_blocks': (_i, [_i, _i]),
     'cagc_lpips_head_fwd': (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i]),
     'cagc_lpips_head_bwd': (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i]),
-    'cagc_parse_preprocess': (_i, [_p, _p, _l, _l, _l, _l, _p, _i, _i, _i]),
+    'cagc_parse_preprocess': (_i, [_p, _p, _l, _l, _l, _l, _p, _i, _i, _i, _i]),
     'cagc_parsing_mask': (_i, [_p, _p, _p, _i, _i, _i, _i]),
     'cagc_parsing_mask_lowres': (_i, [_p, _p, _l, _l, _l, _l, _p, _i, _i, _i, _i, _i, _i]),
     'cagc_fir_nhwc_mask': (_i, [_p, _p, _p, _p, _p, _f, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i]),

@@ -15,19 +15,21 @@ from ._lib import lib, check, stream_of, require_cuda
 PARSING_SIZE = 512          # Util/content_aware_pruning.py:73,101
 
 
-def parse_preprocess(img: torch.Tensor, parsing_size: int = PARSING_SIZE) -> torch.Tensor:
+def parse_preprocess(img: torch.Tensor, parsing_size: int = PARSING_SIZE, channels_last: bool = False) -> torch.Tensor:
     """[N,3,S,S] generator output in [-1,1] -> the parser's input [N,3,P,P] (no gradient: :84-85 runs under no_grad and
-    the teacher image carries none)."""
+    the teacher image carries none); channels_last: the same tensor in torch.channels_last memory format (what cuDNN's
+    tensor-core convolutions read without a layout copy)."""
     require_cuda(img, 'parse_preprocess')
     n, c, s, s2 = img.shape
     if c != 3 or s != s2:
         raise RuntimeError(f'parse_preprocess: [N,3,S,S] image expected, got {tuple(img.shape)}')
-    out = torch.empty((n, 3, parsing_size, parsing_size), device=img.device, dtype=torch.float32)
+    out = torch.empty((n, 3, parsing_size, parsing_size), device=img.device, dtype=torch.float32,
+                      memory_format=torch.channels_last if channels_last else torch.contiguous_format)
     x = img.detach()
     sb, sc, sh, sw = x.stride()
     with torch.cuda.device(img.device):
-        check(lib.cagc_parse_preprocess(stream_of(x), x.data_ptr(), sb, sc, sh, sw, out.data_ptr(), n, s, parsing_size),
-              'parse_preprocess')
+        check(lib.cagc_parse_preprocess(stream_of(x), x.data_ptr(), sb, sc, sh, sw, out.data_ptr(), n, s, parsing_size,
+                                        int(channels_last)), 'parse_preprocess')
     return out
 
 
@@ -63,7 +65,8 @@ def content_mask(teacher_img: torch.Tensor, parsing_net, parsing_size: int = PAR
     (BiSeNet's call contract, Util/face_parsing/BiSeNet.py:230-254).  A parser that offers `scores_lowres(x)` (b200gan.
     parsing.FaceParser) is asked for the scores before its final upsample, which then happens inside the mask kernel."""
     with torch.no_grad():
-        x = parse_preprocess(teacher_img, parsing_size)
-        if hasattr(parsing_net, 'scores_lowres'):
+        own = hasattr(parsing_net, 'scores_lowres')
+        x = parse_preprocess(teacher_img, parsing_size, channels_last=own)
+        if own:
             return parsing_mask_lowres(parsing_net.scores_lowres(x).float(), teacher_img.shape[-1], parsing_size)
         return parsing_mask(parsing_net(x)[0].float(), teacher_img.shape[-1])

@@ -23,6 +23,11 @@ only prepares the process around it:
   3. optional, for parity tests: `--seed S` seeds torch / numpy / random; `--synthetic-mask` replaces the BiSeNet
      face parser by the centred ellipse used by bench.py and the tests (a random-init generator draws no faces).
 
+  4. the rest of the KD loss (train.py only, `--kd-loss own`, the default): `lpips.PerceptualLoss` objects route CUDA
+     calls of the net-lin VGG16 distance to b200gan.lpips.PerceptualLossVGG (parameters taken from the reference object),
+     and `Batch_Img_Parsing` / `Get_Masked_Tensor` (Util/content_aware_pruning.py:61-117) are replaced by the device-side
+     glue of b200gan.maskglue (same results, no host round trip); `--kd-loss reference` leaves both untouched.
+
 The convolution engine is the package default (`CAGC_CONV_ALGO`, tcgen05 TF32 on sm_100); the saliency pass
 (`Get_Content_Aware_Pruning_Score`) is wrapped in `config.exact_fp32()` unless `--saliency-engine` says otherwise, because
 its product -- the prune mask -- is gated bit-exact (SURVEY.md finding 7).
@@ -235,12 +240,63 @@ def _patch_saliency(synthetic_mask: bool, engine: str):
         cap.Get_Content_Aware_Pruning_Score = scored
 
 
+def _patch_kd_loss():
+    """train.py binds `Batch_Img_Parsing` / `Get_Masked_Tensor` by name at import (train.py:22) and builds
+    `lpips.PerceptualLoss(model='net-lin', net='vgg', ...)` (train.py:510): both are swapped at their source modules."""
+    import torch
+    import Util.content_aware_pruning as cap
+    from b200gan import maskglue
+    from b200gan.lpips import PerceptualLossVGG
+    ref_parsing, ref_masked = cap.Batch_Img_Parsing, cap.Get_Masked_Tensor
+
+    def Batch_Img_Parsing(img_tensor, parsing_net, device):
+        if not img_tensor.is_cuda:
+            return ref_parsing(img_tensor, parsing_net, device)
+        with torch.no_grad():
+            return parsing_net(maskglue.parse_preprocess(img_tensor))[0].argmax(1)       # labels [N,512,512], as :87
+
+    def Get_Masked_Tensor(img_tensor, batch_parsing, device, mask_grad=False):
+        if not img_tensor.is_cuda:
+            return ref_masked(img_tensor, batch_parsing, device, mask_grad)
+        labels = batch_parsing.to(img_tensor.device).float().unsqueeze(1)               # K = 1: the plane holds labels
+        return img_tensor * maskglue.parsing_mask(labels, img_tensor.shape[-1])
+    cap.Batch_Img_Parsing, cap.Get_Masked_Tensor = Batch_Img_Parsing, Get_Masked_Tensor
+
+    import lpips
+    Real = lpips.PerceptualLoss
+    if getattr(Real, '_cagc_swapped', False):
+        return
+    # methods are patched in place: PerceptualLoss.__init__ calls `super(PerceptualLoss, self)` through the module-global
+    # name (lpips/__init__.py:17), so rebinding that name to a subclass would recurse
+    real_init, real_forward = Real.__init__, Real.forward
+
+    def __init__(self, *a, **k):
+        real_init(self, *a, **k)
+        try:
+            own = PerceptualLossVGG.from_reference(self)
+        except (ValueError, AttributeError):
+            own = None                          # alex / squeeze / spatial / L2 variants stay on the reference code
+        object.__setattr__(self, '_cagc_own', own)
+
+    def forward(self, pred, target, normalize=False):
+        own = getattr(self, '_cagc_own', None)
+        if own is not None and pred.is_cuda and pred.dtype == torch.float32 and pred.shape[-1] % 16 == 0 \
+                and pred.shape[-2] % 16 == 0:
+            if own.conv_weights[0].device != pred.device:
+                own.to(pred.device)
+            return own(pred, target, normalize)
+        return real_forward(self, pred, target, normalize)
+    Real.__init__, Real.forward, Real._cagc_swapped = __init__, forward, True
+
+
 def main(argv=None):
     ap = argparse.ArgumentParser(prog='python -m b200gan.run', description=__doc__.split('\n\n')[0])
     ap.add_argument('--seed', type=int, default=None)
     ap.add_argument('--synthetic-mask', action='store_true')
     ap.add_argument('--synthetic-fid-stats', action='store_true')
     ap.add_argument('--saliency-engine', default='fp32', choices=['fp32', 'tf32', '3xtf32', 'default'])
+    ap.add_argument('--kd-loss', default='own', choices=['own', 'reference'],
+                    help="train.py: LPIPS / content-mask glue on this package's kernels (own) or the reference's code")
     ap.add_argument('--cwd', default=None, help='working directory for the script (its relative ./Model paths)')
     ap.add_argument('script')
     ap.add_argument('script_args', nargs=argparse.REMAINDER)
@@ -267,6 +323,8 @@ def main(argv=None):
     name = os.path.basename(script)
     if name in ('prune.py', 'train.py') or args.synthetic_mask:
         _patch_saliency(args.synthetic_mask, args.saliency_engine)
+    if name == 'train.py' and args.kd_loss == 'own':
+        _patch_kd_loss()
     if args.seed is not None:
         import numpy as np
         torch.manual_seed(args.seed)

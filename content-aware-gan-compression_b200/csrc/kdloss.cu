@@ -32,6 +32,7 @@ struct PreP {
     int64_t sb, sc, sh, sw;
     float* out;
     int N, S, P;
+    int64_t on, oc, oh, ow;     // output element strides (NCHW-contiguous or channels-last)
     float inv_scale;
     float mean[3], inv_std[3];
 };
@@ -55,7 +56,7 @@ __global__ void __launch_bounds__(256) parse_preprocess_kernel(const __grid_cons
             const float top = px(by.i0, bx.i0) * (1.f - bx.l1) + px(by.i0, bx.i1) * bx.l1;
             const float bot = px(by.i1, bx.i0) * (1.f - bx.l1) + px(by.i1, bx.i1) * bx.l1;
             const float v = top * (1.f - by.l1) + bot * by.l1;
-            p.out[(((int64_t)n * 3 + c) * p.P + y) * p.P + x] = (v - p.mean[c]) * p.inv_std[c];
+            p.out[n * p.on + c * p.oc + y * p.oh + x * p.ow] = (v - p.mean[c]) * p.inv_std[c];
         }
     }
 }
@@ -63,6 +64,10 @@ __global__ void __launch_bounds__(256) parse_preprocess_kernel(const __grid_cons
 // foreground bit of one parser pixel: argmax over K class maps (first maximum wins, as torch.argmax), then
 // `(label > 0) * (label != 16)` (Util/content_aware_pruning.py:103)
 __device__ __forceinline__ float fg_bit(const float* __restrict__ lg, int64_t plane, int K) {
+    if (K == 1) {                      // a single plane holds the LABELS themselves (Batch_Img_Parsing's return value)
+        const int lab = (int)__ldg(lg);
+        return (lab > 0 && lab != 16) ? 1.f : 0.f;
+    }
     float m = __ldg(lg);
     int arg = 0;
     for (int k = 1; k < K; ++k) {
@@ -166,13 +171,15 @@ using namespace cagc;
 extern "C" {
 
 int cagc_parse_preprocess(cagc_stream_t stream_, const float* img, int64_t sb, int64_t sc, int64_t sh, int64_t sw,
-                          float* out, int N, int S, int P) {
+                          float* out, int N, int S, int P, int channels_last) {
     cudaStream_t stream = (cudaStream_t)stream_;
     CAGC_REQUIRE(img && out, "parse_preprocess: null pointer");
     CAGC_REQUIRE(N >= 0 && S >= 1 && P >= 1, "parse_preprocess: bad size");
     if (N == 0) return 0;
     PreP p;
     p.img = img; p.sb = sb; p.sc = sc; p.sh = sh; p.sw = sw; p.out = out; p.N = N; p.S = S; p.P = P;
+    if (channels_last) { p.on = (int64_t)P * P * 3; p.oc = 1; p.oh = (int64_t)P * 3; p.ow = 3; }
+    else { p.on = (int64_t)3 * P * P; p.oc = (int64_t)P * P; p.oh = P; p.ow = 1; }
     p.inv_scale = 1.f / ((float)P / (float)S);          // F.interpolate uses 1 / scale_factor
     const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
     for (int c = 0; c < 3; ++c) { p.mean[c] = mean[c]; p.inv_std[c] = 1.f / stdv[c]; }

@@ -216,6 +216,87 @@ __global__ void __launch_bounds__(256) rgb_conv3x3_bwd_kernel(const float* __res
     }
 }
 
+// Same result, four adjacent pixels per 8-lane group (W % 4 == 0): per (ky, channel chunk) the six gradient vectors the
+// four pixels touch are loaded once and each weight vector serves four pixels -- 2.3x fewer load/store-unit operations
+// per pixel than the one-pixel form, which that unit (not DRAM) bounded.
+__global__ void __launch_bounds__(256) rgb_conv3x3_bwd4_kernel(const float* __restrict__ gz, const float* __restrict__ w,
+                                                               float* __restrict__ gimg, int B, int H, int W, int cout,
+                                                               int pitch, RgbAffine aff) {
+    extern __shared__ float sw_[];          // [27][pitch]
+    for (int i = threadIdx.x; i < 27 * pitch; i += 256) {
+        const int r = i / pitch, o = i - r * pitch;
+        const int t = r / 3, c = r - t * 3;
+        sw_[i] = (o < cout) ? __ldg(w + (o * 3 + c) * 9 + t) : 0.f;
+    }
+    __syncthreads();
+    const int lane8 = threadIdx.x & 7;
+    const int grp = threadIdx.x >> 3;
+    const int c4n = pitch >> 2;
+    const int W4 = W >> 2;
+    const int64_t HW = (int64_t)H * W;
+    const int64_t nquad = (int64_t)B * H * W4;
+    for (int64_t base = (int64_t)blockIdx.x * 32; base < nquad; base += (int64_t)gridDim.x * 32) {   // warp-uniform
+        const int64_t quad = base + grp;
+        const bool valid = quad < nquad;
+        const int64_t qv = valid ? quad : 0;
+        const int X0 = (int)(qv % W4) * 4;
+        const int64_t by = qv / W4;                    // b * H + Y
+        const int Y = (int)(by % H);
+        const int64_t brow = by - Y;                   // b * H
+        float acc[4][3];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j][0] = acc[j][1] = acc[j][2] = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int yy = Y - ky + 1;
+            if (yy < 0 || yy >= H) continue;
+            const float* grow = gz + (brow + yy) * W * pitch;
+            for (int c4 = lane8; c4 < c4n; c4 += 8) {
+                float4 gv[6];
+#pragma unroll
+                for (int q = 0; q < 6; ++q) {
+                    const int xx = X0 - 1 + q;
+                    gv[q] = (xx >= 0 && xx < W) ? ldg4(grow + (int64_t)xx * pitch + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const float* wp = sw_ + (ky * 3 + kx) * 3 * pitch + c4 * 4;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const float4 wv = ld4(wp + c * pitch);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {       // source pixel of output X0 + j under tap kx: X0 + j - kx + 1
+                            const float4 g4 = gv[j - kx + 2];
+                            acc[j][c] = fmaf(g4.x, wv.x, acc[j][c]);
+                            acc[j][c] = fmaf(g4.y, wv.y, acc[j][c]);
+                            acc[j][c] = fmaf(g4.z, wv.z, acc[j][c]);
+                            acc[j][c] = fmaf(g4.w, wv.w, acc[j][c]);
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                acc[j][c] += __shfl_xor_sync(0xffffffffu, acc[j][c], 4);
+                acc[j][c] += __shfl_xor_sync(0xffffffffu, acc[j][c], 2);
+                acc[j][c] += __shfl_xor_sync(0xffffffffu, acc[j][c], 1);
+            }
+        if (valid && lane8 < 3) {
+            const float is = lane8 == 0 ? aff.inv_scale[0] : (lane8 == 1 ? aff.inv_scale[1] : aff.inv_scale[2]);
+            float4 o;
+            o.x = (lane8 == 0 ? acc[0][0] : (lane8 == 1 ? acc[0][1] : acc[0][2])) * is;
+            o.y = (lane8 == 0 ? acc[1][0] : (lane8 == 1 ? acc[1][1] : acc[1][2])) * is;
+            o.z = (lane8 == 0 ? acc[2][0] : (lane8 == 1 ? acc[2][1] : acc[2][2])) * is;
+            o.w = (lane8 == 0 ? acc[3][0] : (lane8 == 1 ? acc[3][1] : acc[3][2])) * is;
+            const int64_t b = brow / H;
+            st4(gimg + (b * 3 + lane8) * HW + (int64_t)Y * W + X0, o);      // NCHW contiguous image gradient
+        }
+    }
+}
+
 __device__ __forceinline__ float4 max4(float4 a, float4 b) {
     return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
 }
@@ -474,6 +555,11 @@ int cagc_rgb_conv3x3_bwd(cagc_stream_t stream_, const float* gz, const float* w,
     const int64_t npix = (int64_t)B * H * W;
     if (npix == 0) return 0;
     const size_t smem = (size_t)27 * pitch * sizeof(float);
+    if (W % 4 == 0 && aligned16(gimg)) {
+        rgb_conv3x3_bwd4_kernel<<<lp_grid_1d(npix / 4, 32), 256, smem, stream>>>(gz, w, gimg, B, H, W, cout, pitch,
+                                                                                 make_affine(nullptr, scale_host));
+        return launched("rgb_conv3x3_bwd4_kernel");
+    }
     rgb_conv3x3_bwd_kernel<<<lp_grid_1d(npix, 64), 256, smem, stream>>>(gz, w, gimg, B, H, W, cout, pitch,
                                                                         make_affine(nullptr, scale_host));
     return launched("rgb_conv3x3_bwd_kernel");

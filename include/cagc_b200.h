@@ -37,7 +37,7 @@ typedef void* cagc_stream_t; /* cudaStream_t */
 #define CAGC_E_UNSUPPORTED (-2) /* shape outside what the kernels implement */
 
 /* bump when a signature changes; the Python loader checks it */
-#define CAGC_ABI_VERSION 21
+#define CAGC_ABI_VERSION 22
 
 int cagc_abi_version(void);
 const char* cagc_last_error(void);
@@ -388,14 +388,15 @@ int cagc_lpips_head_bwd(cagc_stream_t stream, const float* fs, const float* ft, 
 
 /* ----------------------------------------------------------------------
  * Content-mask glue of the KD loss (reference Util/content_aware_pruning.py:61-117, train.py:154-158).
- *   cagc_parse_preprocess: out[N,3,P,P] (contiguous) = (bilinear(clamp((img + 1) / 2, 0, 1), S -> P) - mean) / std with
+ *   cagc_parse_preprocess: out[N,3,P,P] (contiguous, or stored [N,P,P,3] when channels_last != 0) = (bilinear(clamp((img + 1) / 2, 0, 1), S -> P) - mean) / std with
  *       the ImageNet statistics of Batch_Img_Parsing (:71-82); img [N,3,S,S] through element strides.
  *   cagc_parsing_mask: mask[N,S,S] = bilinear(float(argmax_k logits[N,K,P,P] not in {0, 16}), P -> S) > 0.5
- *       (`Batch_Img_Parsing` :87 + `Get_Masked_Tensor` :103-109, without the host round trip).
+ *       (`Batch_Img_Parsing` :87 + `Get_Masked_Tensor` :103-109, without the host round trip); K == 1: the single plane
+ *       holds the labels themselves (as floats).
  * Bilinear = F.interpolate(align_corners=False, scale_factor = out / in).
  * ---------------------------------------------------------------------- */
 int cagc_parse_preprocess(cagc_stream_t stream, const float* img, int64_t sb, int64_t sc, int64_t sh, int64_t sw,
-                          float* out, int N, int S, int P);
+                          float* out, int N, int S, int P, int channels_last);
 int cagc_parsing_mask(cagc_stream_t stream, const float* logits, float* mask, int N, int K, int P, int S);
 /* The same mask from the parser's low-resolution scores [N,K,h,w] (element strides sn, sk, sh, sw): the final
  * F.interpolate(scores, (P, P), bilinear, align_corners=True) of BiSeNet.forward (Util/face_parsing/BiSeNet.py:247) is
