@@ -32,6 +32,11 @@ from ._lib import lib, check, stream_of, require_cuda, ptr, fir_nhwc, TensorCach
 from . import config
 
 
+import os as _os
+
+_FOLD_MOD = _os.environ.get('CAGC_FOLD_MOD', '1') != '0'      # development knob: modulation folded into per-sample weights
+
+
 def pitch_of(c: int) -> int:
     return (c + 7) // 8 * 8
 
@@ -216,7 +221,15 @@ class _StyledConvFn(Function):
                                      eps), 'demod')
             else:
                 d_p = None
-            if tc:
+            # A layer nobody differentiates (the frozen teacher under no_grad; sampling) does not need the modulated
+            # activation as a weight-gradient operand: where the halo-tile kernel takes the shape, the modulation is
+            # folded into per-sample weight slabs (B x k^2 small slabs) and the activation is read as it is.
+            psw_bytes = 0
+            if tc and not upsample and _FOLD_MOD and xb.numel() and not any(ctx.needs_input_grad):
+                psw_bytes = int(lib.cagc_conv_same_psw_bytes(b, h, w, pin, pout, k))
+            if tc and psw_bytes:
+                x_in, s_arg, falgo = None, None, config.ALGO_TCGEN05_TF32
+            elif tc:
                 # tensor-pipe path: operands come straight from TMA, so modulation is a tensor pass
                 x_in = torch.empty_like(xb)
                 if xb.numel():
@@ -240,7 +253,16 @@ class _StyledConvFn(Function):
                 nstride, nw = 0, None
             if not upsample:
                 out = torch.empty((b, h, w, pout), device=dev, dtype=torch.float32)
-                if out.numel():
+                if out.numel() and psw_bytes:
+                    w_ps = torch.empty(psw_bytes // 4, device=dev, dtype=torch.float32)
+                    _timed(f'conv_same[algo{falgo}]', 2.0 * b * h * w * cin * cout * k * k, 4.0 * b * h * w * (cin + cout),
+                           lambda: check(lib.cagc_conv_same_psw(st, xb.data_ptr(), w_fwd.data_ptr(), s_p.data_ptr(),
+                                                                ptr(d_p), ptr(noise), ptr(nw), ptr(bias_p), out.data_ptr(),
+                                                                b, h, w, pin, pout, cout, k, nstride, int(act),
+                                                                w_ps.data_ptr(), psw_bytes),
+                                         'conv_same_psw'), shape=f'{cin}->{cout}x{h}x{w}')
+                    del w_ps
+                elif out.numel():
                     flops = 2.0 * b * h * w * cin * cout * k * k          # Util/Calculators.py convention x2
                     ws, ws_bytes = conv_workspace(b, h, w, pout, dev) if tc else (None, 0)
                     _timed(f'conv_same[algo{falgo}]', flops, 4.0 * b * h * w * (cin + cout),

@@ -28,6 +28,8 @@ struct ConvP {
     int out_valid;
     int Hout, Wout, out_stride, out_oy, out_ox;
     int64_t noise_bstride;
+    int w_bslabs;            // > 0: the weights are PER-SAMPLE slab sets (modulation folded in), sample b starts at slab
+                             // b * w_bslabs; 0: one set shared by the batch
     int act;                 // 0: none, 1: leaky ReLU (slope 0.2) * act_gain
     float act_gain;          // sqrt2 unless stated (0 is read as sqrt2)
     int ntaps;
@@ -38,6 +40,8 @@ struct ConvP {
 
 // tcgen05 / TMA implicit-GEMM path (conv_tc.cu)
 int cagc_tc_conv(cudaStream_t stream, const cagc::ConvP& p, const char* what);
+// 1 when cagc_tc_conv would run this shape on the halo-tile kernel (the only one that takes per-sample weight slabs)
+int cagc_tc_conv_takes_sample_weights(const cagc::ConvP& p);
 // several phases (output parities of the transposed convolution) in one persistent launch; 1 = handled (*rc)
 int cagc_tc_conv_multi(cudaStream_t stream, const cagc::ConvP* phases, int nphase, const char* what, int* rc);
 int cagc_tc_conv_multi_splitk(cudaStream_t stream, const cagc::ConvP* phases, int nphase, float* workspace,

@@ -838,6 +838,7 @@ struct HaloParams {
     int B, Ho, Wo;                  // iteration domain (output pixels of this launch)
     int TW, R, Wt, rows_box;        // tile width / rows, raster pitch, box rows (R + dyspan)
     int dx_min, dy_min;
+    int w_bslabs;                   // per-sample weight slab sets: sample b reads slab tap_slab + b * w_bslabs (0: shared)
     int strips, ytiles;             // tiles per sample
     int mt;                         // 128-row M sub-tiles per tile: ceil(R*Wt / 128) (raster mode) or R (row mode)
     int row_mode;                   // 1: sub-tile j = output row j of the tile (TW <= 128 pixels, no halo columns in M)
@@ -938,7 +939,8 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     mbar_wait(bempty(s), ph ^ 1u);
                     if (elect_one()) {
                         mbar_expect_tx(bfull(s), p.b_bytes);
-                        tma_load_3d(b_base + (uint32_t)s * p.b_bytes, &map_b, bfull(s), kc * kChunkK, n0, p.tap_slab[tap]);
+                        tma_load_3d(b_base + (uint32_t)s * p.b_bytes, &map_b, bfull(s), kc * kChunkK, n0,
+                                    p.tap_slab[tap] + b * p.w_bslabs);
                     }
                     __syncwarp();
                     if (++s == SB) { s = 0; ph ^= 1u; }
@@ -1080,6 +1082,28 @@ __global__ void __launch_bounds__(256) modulate_kernel(const float* __restrict__
         st4(os + 4 * (int64_t)i, make_float4(__uint_as_float(r0), __uint_as_float(r1), __uint_as_float(r2), __uint_as_float(r3)));
         c4 += step_c;
         if (c4 >= c4n) c4 -= c4n;
+    }
+}
+
+// Per-sample weight slabs: out[b][row][i] = tf32(w[row][i] * s[b][i]) for the K-major slab rows [taps * n_rows][in_pitch]
+// of the tensor-pipe forward operand -- the modulation of model.py:248-250 folded into the B operand instead of a pass
+// over the activation (a frozen layer without gradients: the teacher's 128^2 / 256^2 layers move 16 x 0.6 .. 1.2 MB of
+// weights instead of 0.5 .. 1.1 GB of activations).
+__global__ void __launch_bounds__(256) modulate_weights_kernel(const float* __restrict__ w, const float* __restrict__ s,
+                                                               float* __restrict__ out, int per_sample4, int c4n) {
+    const int b = blockIdx.y;
+    const float* sb = s + (int64_t)b * c4n * 4;
+    float* os = out + (int64_t)b * per_sample4 * 4;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < per_sample4; i += gridDim.x * 256) {
+        float4 v = ldg4(w + 4 * (int64_t)i);
+        const float4 sv = ldg4(sb + (i % c4n) * 4);
+        v.x *= sv.x; v.y *= sv.y; v.z *= sv.z; v.w *= sv.w;
+        uint32_t r0, r1, r2, r3;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r0) : "f"(v.x));
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r1) : "f"(v.y));
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r2) : "f"(v.z));
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r3) : "f"(v.w));
+        st4(os + 4 * (int64_t)i, make_float4(__uint_as_float(r0), __uint_as_float(r1), __uint_as_float(r2), __uint_as_float(r3)));
     }
 }
 
@@ -1994,7 +2018,8 @@ static int next_pow2(int v) {
 using namespace cagc;
 
 // Halo-tile launch (see conv_tc_halo_kernel).  Returns 1 when it took the call (result in *rc).
-static int try_halo_conv(cudaStream_t stream, const ConvP& c, const char* what, cagc::tc::EncodeTiledFn encode, int* rc) {
+static int try_halo_conv(cudaStream_t stream, const ConvP& c, const char* what, cagc::tc::EncodeTiledFn encode, int* rc,
+                         bool dry_run = false) {
     using namespace cagc::tc;
     static const int halo_env = [] { const char* e = getenv("CAGC_TC_HALO"); return e ? atoi(e) : 1; }();
     if (!halo_env || c.in_stride != 1 || c.ntaps < 2 || c.B > 65535) return 0;
@@ -2085,6 +2110,8 @@ static int try_halo_conv(cudaStream_t stream, const ConvP& c, const char* what, 
     const int64_t left = smem_budget - 1024 - 2 * (int64_t)p.a_stride;
     p.b_stages = (int)std::min<int64_t>(kHaloMaxB, left / p.b_bytes);
     if (p.b_stages < 2) return 0;
+    if (dry_run) return 1;          // eligibility only (cagc_tc_conv_takes_sample_weights)
+    p.w_bslabs = c.w_bslabs;
     p.out_scale = c.out_scale; p.noise = c.noise; p.noise_w = c.noise_w; p.bias = c.bias; p.out = c.out;
     p.residual = c.residual; p.act_gain = (c.act_gain != 0.f) ? c.act_gain : kSqrt2;
     p.B = c.B; p.Ho = c.Ho; p.Wo = c.Wo;
@@ -2112,7 +2139,8 @@ static int try_halo_conv(cudaStream_t stream, const ConvP& c, const char* what, 
         if (r != CUDA_SUCCESS) { *rc = fail(CAGC_E_INVALID, "%s: cuTensorMapEncodeTiled(A, halo) failed with %d", what, (int)r); return 1; }
     }
     {
-        cuuint64_t dims[3] = {(cuuint64_t)c.in_pitch, (cuuint64_t)p.n_rows, (cuuint64_t)(max_slab + 1)};
+        const int nslabs = c.w_bslabs > 0 ? c.w_bslabs * c.B : max_slab + 1;
+        cuuint64_t dims[3] = {(cuuint64_t)c.in_pitch, (cuuint64_t)p.n_rows, (cuuint64_t)nslabs};
         cuuint64_t strides[2] = {(cuuint64_t)c.in_pitch * 4, (cuuint64_t)p.n_rows * c.in_pitch * 4};
         cuuint32_t box[3] = {(cuuint32_t)kChunkK, (cuuint32_t)p.n_tile, 1};
         cuuint32_t es[3] = {1, 1, 1};
@@ -2149,6 +2177,8 @@ int cagc_tc_conv(cudaStream_t stream, const ConvP& c, const char* what) {
     {
         int rc = 0;
         if (try_halo_conv(stream, c, what, encode, &rc)) return rc;
+        if (c.w_bslabs > 0)
+            return fail(CAGC_E_UNSUPPORTED, "%s: per-sample weight slabs need the halo-tile kernel, which does not take this shape", what);
     }
     TcParams p{};
     p.out_scale = c.out_scale; p.noise = c.noise; p.noise_w = c.noise_w; p.bias = c.bias; p.out = c.out;
@@ -2858,4 +2888,54 @@ int cagc_modulate(cagc_stream_t stream_, const float* x, const float* s, float* 
     return launched("modulate_kernel");
 }
 
+static void same_conv_params(ConvP& p, int B, int H, int W, int in_pitch, int out_pitch, int out_valid, int ksize) {
+    p.B = B; p.Hin = H; p.Win = W; p.in_pitch = in_pitch; p.Ho = H; p.Wo = W; p.in_stride = 1;
+    p.n_cols = out_pitch; p.out_valid = out_valid; p.Hout = H; p.Wout = W; p.out_stride = 1; p.out_oy = 0; p.out_ox = 0;
+    p.ntaps = ksize * ksize;
+    for (int ky = 0; ky < ksize; ++ky)
+        for (int kx = 0; kx < ksize; ++kx) p.taps[ky * ksize + kx] = Tap{ky - ksize / 2, kx - ksize / 2, ky * ksize + kx};
+}
+
+int64_t cagc_conv_same_psw_bytes(int B, int H, int W, int in_pitch, int out_pitch, int ksize) {
+    if (B <= 0 || H <= 0 || W <= 0 || in_pitch <= 0 || out_pitch <= 0 || in_pitch % 8 || out_pitch % 8 || ksize < 1 ||
+        ksize % 2 == 0 || ksize * ksize > kMaxTaps)
+        return 0;
+    ConvP p{};
+    same_conv_params(p, B, H, W, in_pitch, out_pitch, out_pitch, ksize);
+    p.w_bslabs = ksize * ksize;
+    if (!cagc_tc_conv_takes_sample_weights(p)) return 0;
+    return (int64_t)B * ksize * ksize * ((out_pitch + 15) & ~15) * in_pitch * 4;
+}
+
+int cagc_conv_same_psw(cagc_stream_t stream_, const float* in, const float* w_slabs, const float* in_scale,
+                       const float* out_scale, const float* noise, const float* noise_w, const float* bias, float* out,
+                       int B, int H, int W, int in_pitch, int out_pitch, int out_valid, int ksize, int64_t noise_bstride,
+                       int act, float* w_ps, int64_t w_ps_bytes) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CAGC_REQUIRE(in && w_slabs && in_scale && out && w_ps, "conv_same_psw: null pointer");
+    CAGC_REQUIRE(!noise || noise_w, "conv_same_psw: noise without noise weight");
+    CAGC_REQUIRE(aligned16(in) && aligned16(w_slabs) && aligned16(out) && aligned16(w_ps) && aligned16(in_scale),
+                 "conv_same_psw: pointers must be 16-byte aligned");
+    const int64_t need = cagc_conv_same_psw_bytes(B, H, W, in_pitch, out_pitch, ksize);
+    if (need == 0) return fail(CAGC_E_UNSUPPORTED, "conv_same_psw: shape not taken by the per-sample-weight path");
+    CAGC_REQUIRE(w_ps_bytes >= need, "conv_same_psw: weight workspace too small (%lld < %lld bytes)", (long long)w_ps_bytes,
+                 (long long)need);
+    const int64_t per4 = (int64_t)ksize * ksize * ((out_pitch + 15) & ~15) * in_pitch / 4;
+    CAGC_REQUIRE(per4 < (1LL << 30) && B <= 65535, "conv_same_psw: tensor too large");
+    int64_t bx = std::min<int64_t>(ceil_div<int64_t>(per4, 256), std::max<int64_t>(1, (int64_t)kNumSMs * 8 / B));
+    cagc::tc::modulate_weights_kernel<<<dim3((unsigned)bx, (unsigned)B), 256, 0, stream>>>(w_slabs, in_scale, w_ps, (int)per4,
+                                                                                       in_pitch / 4);
+    CAGC_TRY(launched("modulate_weights_kernel"));
+    ConvP p{};
+    same_conv_params(p, B, H, W, in_pitch, out_pitch, out_valid, ksize);
+    p.in = in; p.w = w_ps; p.out_scale = out_scale; p.noise = noise; p.noise_w = noise_w; p.bias = bias; p.out = out;
+    p.noise_bstride = noise_bstride; p.act = act; p.w_bslabs = ksize * ksize;
+    return cagc_tc_conv(stream, p, "conv_same_psw[tc]");
+}
+
 }  // extern "C"
+
+int cagc_tc_conv_takes_sample_weights(const cagc::ConvP& c) {
+    int rc = 0;
+    return try_halo_conv(nullptr, c, "conv", nullptr, &rc, true);
+}

@@ -37,7 +37,7 @@ typedef void* cagc_stream_t; /* cudaStream_t */
 #define CAGC_E_UNSUPPORTED (-2) /* shape outside what the kernels implement */
 
 /* bump when a signature changes; the Python loader checks it */
-#define CAGC_ABI_VERSION 22
+#define CAGC_ABI_VERSION 23
 
 int cagc_abi_version(void);
 const char* cagc_last_error(void);
@@ -333,6 +333,18 @@ int cagc_conv_same_ws(cagc_stream_t stream, const float* in, const float* w_slab
                       const float* out_scale, const float* noise, const float* noise_w, const float* bias, float* out,
                       int B, int H, int W, int in_pitch, int out_pitch, int out_valid, int ksize, int64_t noise_bstride,
                       int act, int algo, float* workspace, int64_t workspace_bytes);
+/* Same-resolution modulated convolution with the modulation folded into PER-SAMPLE weight slabs instead of a pass over
+ * the activation (reference model.py:248-257 formulates it exactly so; here the per-sample set is B x k^2 K-major TF32
+ * slabs written by one small kernel, and the implicit-GEMM kernel picks slab b * k^2 + tap for the tiles of sample b):
+ * out = act(out_scale * conv(in, (w * in_scale[b])) + noise + bias).  Forward only (a layer that needs its weight
+ * gradient keeps the modulated activation, which is the operand of that gradient).  tcgen05 engine only;
+ * cagc_conv_same_psw_bytes: size of the w_ps scratch, 0 when the shape is not taken (the caller then modulates the
+ * activation: cagc_modulate + cagc_conv_same_ws). */
+int64_t cagc_conv_same_psw_bytes(int B, int H, int W, int in_pitch, int out_pitch, int ksize);
+int cagc_conv_same_psw(cagc_stream_t stream, const float* in, const float* w_slabs, const float* in_scale,
+                       const float* out_scale, const float* noise, const float* noise_w, const float* bias, float* out,
+                       int B, int H, int W, int in_pitch, int out_pitch, int out_valid, int ksize, int64_t noise_bstride,
+                       int act, float* w_ps, int64_t w_ps_bytes);
 int cagc_conv_up_dgrad_ws(cagc_stream_t stream, const float* g_t, const float* w_slabs, float* g_in, int B, int H, int W,
                           int g_pitch, int in_pitch, int ksize, int algo, float* workspace, int64_t workspace_bytes);
 /* cagc_conv_up with a workspace sized for the TRANSPOSED output (cagc_conv_workspace_bytes(B, 2H+k-2, 2W+k-2, out_pitch)):

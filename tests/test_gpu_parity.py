@@ -640,3 +640,41 @@ def test_upfirdn2d_channels_last_and_discriminator(mods):
             assert l2 <= 2e-2, f'discriminator dgrad channels_last={cl}: L2 {l2:.3e}'
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+@pytest.mark.parametrize('cin,cout,res,batch', [(128, 128, 128, 3), (256, 256, 128, 2), (39, 39, 64, 3), (77, 77, 128, 2)])
+def test_modulation_folded_into_per_sample_weights(cin, cout, res, batch):
+    """A StyledConv nobody differentiates (the teacher under no_grad) folds the modulation into per-sample weight slabs
+    (cagc_conv_same_psw) where the halo-tile kernel takes the shape: same result as modulating the activation first, up
+    to where the TF32 rounding falls; distinct styles per sample (the slab of sample b must meet the tiles of sample b)."""
+    import model
+    from b200gan import config, modconv
+    from b200gan._lib import lib
+    from b200gan.modconv import pitch_of
+    assert lib.cagc_conv_same_psw_bytes(batch, res, res, pitch_of(cin), pitch_of(cout), 3) > 0, 'shape not taken: test is moot'
+    torch.manual_seed(cin + res)
+    m = model.StyledConv(cin, cout, 3, 512).cuda()
+    with torch.no_grad():
+        m.noise.weight.fill_(0.3)
+        m.activate.bias.normal_(0, 0.3)
+    x = torch.randn(batch, cin, res, res, device='cuda')
+    w = torch.randn(batch, 512, device='cuda') * 2
+    noise = torch.randn(batch, 1, res, res, device='cuda')
+    with config.use_algo(config.ALGO_TCGEN05_TF32), torch.no_grad():
+        assert modconv._FOLD_MOD
+        folded = m(x, w, noise=noise)
+        modconv._FOLD_MOD = False
+        try:
+            plain = m(x, w, noise=noise)
+        finally:
+            modconv._FOLD_MOD = True
+    with config.exact_fp32(), torch.no_grad():
+        exact = m(x, w, noise=noise)
+    scale = float(exact.abs().max())
+    assert float((plain - exact).abs().max()) <= 5e-3 * scale
+    assert float((folded - exact).abs().max()) <= 5e-3 * scale
+    # with gradients enabled the fused path keeps the modulated activation (operand of the weight gradient)
+    with config.use_algo(config.ALGO_TCGEN05_TF32):
+        out = m(x.requires_grad_(True), w, noise=noise)
+        out.sum().backward()
+    assert torch.isfinite(x.grad).all() and m.conv.weight.grad is not None
