@@ -578,7 +578,6 @@ def bench_saliency(args, cx):
     autograd graph, sparse +-1 cotangent, backward, per-channel scores).  One step = one batch of 8.  Reports both
     engines: exact-fp32 SIMT and the fp32-accurate tensor-pipe split (3xTF32) when available."""
     torch, config = cx.torch, cx.config
-    import numpy as np
     import model
     from b200gan import saliency as S
     dev, rank, world = cx.dev, cx.rank, cx.world

@@ -32,7 +32,7 @@ from torch.autograd.function import once_differentiable
 from ._lib import lib, check, stream_of, require_cuda, conv_workspace, ptr
 from . import config
 from .dconv import _prep, _empty
-from .modconv import nhwc_view, _timed
+from .modconv import _timed
 
 # torchvision.models.vgg16().features[0:30]: output channels per conv, 'M' = MaxPool2d(2, 2) (pretrained_networks.py:100-114)
 VGG16_CFG = (64, 64, 'M', 128, 128, 'M', 256, 256, 256, 'M', 512, 512, 512, 'M', 512, 512, 512)

@@ -61,7 +61,6 @@ def test_rgb_conv3x3_fwd_bwd(h, w, cout):
     wt = torch.randn(cout, 3, 3, 3, generator=g, dtype=torch.float64) * 0.3
     bias = torch.randn(cout, generator=g, dtype=torch.float64) * 0.2
     shift, scale = (-.030, -.088, -.188), (.458, .448, .450)
-    xs = ((img - torch.tensor(shift).view(1, 3, 1, 1)) / torch.tensor(scale).view(1, 3, 1, 1)).requires_grad_(True)
     img_leaf = img.clone().requires_grad_(True)
     pre = F.conv2d((img_leaf - torch.tensor(shift).view(1, 3, 1, 1)) / torch.tensor(scale).view(1, 3, 1, 1), wt, bias, padding=1)
     ref = F.relu(pre)
