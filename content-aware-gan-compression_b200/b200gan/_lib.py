@@ -17,7 +17,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # CAGC_LIB: another build of the same library (A/B timing of two revisions on one box, scripts/build_rev.sh)
 LIB_PATH = os.environ.get('CAGC_LIB') or os.path.join(os.path.dirname(_HERE), 'lib', 'libcagc_b200.so')
-ABI_VERSION = 23
+ABI_VERSION = 24
 
 _p = C.c_void_p
 _i = C.c_int
@@ -71,6 +71,7 @@ SIGNATURES = {
     'cagc_conv_same_psw': (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _l, _i, _p, _l]),
     'cagc_conv_up_dgrad_ws': (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _l]),
     'cagc_conv2d_ws': (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _p, _l]),
+    'cagc_conv2d_mask_ws': (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _l]),
     'cagc_linear_fwd': (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _f, _f, _i, _f, _f]),
     'cagc_linear_bwd': (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i]),
     'cagc_conv2d': (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i]),

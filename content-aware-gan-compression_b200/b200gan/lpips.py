@@ -13,8 +13,10 @@ Here the whole distance is one autograd node on NHWC-p buffers:
     forward   conv1_1: cagc_rgb_conv3x3_fwd (scaling layer on the operand load, bias + ReLU on the store)
               12 x cagc_conv2d_ws with a ReLU epilogue (tcgen05 TF32 implicit GEMM, or the exact-fp32 engine)
               4 x cagc_maxpool2_nhwc, 5 x cagc_lpips_head_fwd
-    backward  5 x cagc_lpips_head_bwd; per layer ONE masking pass (cagc_relu_pool_bwd: max-pool backward + tap gradient
-              + ReLU mask) and ONE data-gradient convolution; conv1_1: cagc_rgb_conv3x3_bwd straight to the image gradient
+    backward  5 x cagc_lpips_head_bwd; per layer ONE data-gradient convolution; the ReLU mask of a conv -> ReLU -> conv chain
+              is that convolution's epilogue (cagc_conv2d_mask_ws), tapped / pooled layers take ONE masking pass
+              (cagc_relu_pool_bwd: max-pool backward + tap gradient + ReLU mask); conv1_1: cagc_rgb_conv3x3_bwd straight
+              to the image gradient
 
 The dropout in front of every `lin` layer is the identity: DistModel.initialize puts the net in eval mode
 (lpips/dist_model.py:98-99).  No weight gradient exists on this path (requires_grad=False everywhere in the reference).
@@ -22,6 +24,7 @@ The dropout in front of every `lin` layer is the identity: DistModel.initialize 
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List, Sequence
 
 import torch
@@ -40,6 +43,10 @@ TAPS = (1, 3, 6, 9, 12)                 # conv indices whose ReLU output is tapp
 POOL_BEFORE = (2, 4, 7, 10)             # conv indices whose input went through a max-pool
 SHIFT = (-.030, -.088, -.188)           # ScalingLayer, networks_basic.py:94-101
 SCALE = (.458, .448, .450)
+
+
+# development knob: ReLU masks of the conv -> ReLU -> conv chains as data-gradient epilogues (0: one masking pass per layer)
+_MASK_EPILOGUE = os.environ.get('CAGC_LPIPS_MASK_EPILOGUE', '1') != '0'
 
 
 def _f3(vals):
@@ -106,34 +113,42 @@ class _LpipsFn(Function):
         gv = gval.reshape(n).contiguous()
         with torch.cuda.device(dev):
             st = stream_of(gval)
-            g = None                         # gradient w.r.t. the OUTPUT of conv i (student half), before its ReLU mask
+            g = None        # gradient w.r.t. the OUTPUT of conv i (student half), before its ReLU mask, or ...
+            gz = None       # ... the masked gradient itself, when the data-gradient convolution above applied the mask
             for i in range(12, 0, -1):
                 a = acts[i]
                 _, hh, ww, cout = a.shape
                 cin = ws[i].shape[1]
-                gfeat = None
-                if i in TAPS:
-                    kk = TAPS.index(i)
-                    gfeat = _empty(n, hh, ww, cout, dev)
-                    check(lib.cagc_lpips_head_bwd(st, a.data_ptr(), a[n:].data_ptr(), mod.lin_weights[kk].data_ptr(),
-                                                  gv.data_ptr(), gfeat.data_ptr(), n, hh * ww, cout), 'lpips.head^T')
-                gz = _empty(n, hh, ww, cout, dev)
-                if i + 1 in POOL_BEFORE:     # the output also feeds a max-pool: g lives on the pooled grid
-                    check(lib.cagc_relu_pool_bwd(st, a.data_ptr(), g.data_ptr(), ptr(gfeat), gz.data_ptr(), n, hh, ww,
-                                                 cout), 'lpips.relu_pool^T')
-                else:
-                    src = gfeat if i == 12 else g
-                    check(lib.cagc_relu_pool_bwd(st, a.data_ptr(), None, src.data_ptr(), gz.data_ptr(), n, hh, ww, cout),
-                          'lpips.relu^T')
-                del gfeat, g
+                if gz is None:
+                    gfeat = None
+                    if i in TAPS:
+                        kk = TAPS.index(i)
+                        gfeat = _empty(n, hh, ww, cout, dev)
+                        check(lib.cagc_lpips_head_bwd(st, a.data_ptr(), a[n:].data_ptr(), mod.lin_weights[kk].data_ptr(),
+                                                      gv.data_ptr(), gfeat.data_ptr(), n, hh * ww, cout), 'lpips.head^T')
+                    gz = _empty(n, hh, ww, cout, dev)
+                    if i + 1 in POOL_BEFORE:     # the output also feeds a max-pool: g lives on the pooled grid
+                        check(lib.cagc_relu_pool_bwd(st, a.data_ptr(), g.data_ptr(), ptr(gfeat), gz.data_ptr(), n, hh, ww,
+                                                     cout), 'lpips.relu_pool^T')
+                    else:
+                        src = gfeat if i == 12 else g
+                        check(lib.cagc_relu_pool_bwd(st, a.data_ptr(), None, src.data_ptr(), gz.data_ptr(), n, hh, ww, cout),
+                              'lpips.relu^T')
+                    del gfeat
+                g = None
                 p, _, tcd = _prep(ws[i], bs[i], 1.0, False, algo)
-                g = _empty(n, hh, ww, cin, dev)
-                _vconv(st, gz, p.w_dgrad, None, g, n, hh, ww, cout, cin, False, tcd, f'lpips.conv{i}^T')
-                del gz
+                out = _empty(n, hh, ww, cin, dev)
+                # the activation below feeds this convolution only (no tap, no pool in between): its ReLU mask is applied
+                # in the epilogue of the data-gradient convolution, which then hands the next layer its masked gradient
+                plain_below = _MASK_EPILOGUE and (i - 1) not in TAPS and i not in POOL_BEFORE
+                _vconv(st, gz, p.w_dgrad, None, out, n, hh, ww, cout, cin, False, tcd, f'lpips.conv{i}^T',
+                       mask_ref=acts[i - 1] if plain_below else None)
+                gz, g = (out, None) if plain_below else (None, out)
             a = acts[0]
             _, h, w, c0 = a.shape
-            gz = _empty(n, h, w, c0, dev)
-            check(lib.cagc_relu_pool_bwd(st, a.data_ptr(), None, g.data_ptr(), gz.data_ptr(), n, h, w, c0), 'lpips.relu^T')
+            if gz is None:
+                gz = _empty(n, h, w, c0, dev)
+                check(lib.cagc_relu_pool_bwd(st, a.data_ptr(), None, g.data_ptr(), gz.data_ptr(), n, h, w, c0), 'lpips.relu^T')
             gimg = torch.empty((n, 3, h, w), device=dev, dtype=torch.float32)
             _timed('lpips_rgb_conv', 2.0 * n * h * w * 27 * c0, 4.0 * n * h * w * (3 + c0),
                    lambda: check(lib.cagc_rgb_conv3x3_bwd(st, gz.data_ptr(), ws[0].data_ptr(), mod._scale, gimg.data_ptr(),
@@ -141,13 +156,18 @@ class _LpipsFn(Function):
         return gimg, None, None, None
 
 
-def _vconv(st, x_buf, slab, bias_p, out, b, h, w, pin, pout, relu, tc, name):
+def _vconv(st, x_buf, slab, bias_p, out, b, h, w, pin, pout, relu, tc, name, mask_ref=None):
     algo = config.ALGO_TCGEN05_TF32 if tc else config.ALGO_SIMT_FP32
     wsb, ws_bytes = conv_workspace(b, h, w, pout, out.device) if tc else (None, 0)
-    _timed(f'lpips_conv[algo{algo}]', 2.0 * b * h * w * pin * pout * 9, 4.0 * b * h * w * (pin + pout),
-           lambda: check(lib.cagc_conv2d_ws(st, x_buf.data_ptr(), slab.data_ptr(), ptr(bias_p), None, out.data_ptr(),
-                                            b, h, w, pin, pout, pout, 3, 0, int(relu), -1.0 if relu else 1.0, algo,
-                                            ptr(wsb), ws_bytes), name),
+    if mask_ref is not None:       # data gradient with the ReLU mask of the activation it flows into (first b images)
+        launch = lambda: check(lib.cagc_conv2d_mask_ws(st, x_buf.data_ptr(), slab.data_ptr(), mask_ref.data_ptr(),
+                                                       out.data_ptr(), b, h, w, pin, pout, pout, 3, algo, ptr(wsb), ws_bytes),
+                               name)
+    else:
+        launch = lambda: check(lib.cagc_conv2d_ws(st, x_buf.data_ptr(), slab.data_ptr(), ptr(bias_p), None, out.data_ptr(),
+                                                  b, h, w, pin, pout, pout, 3, 0, int(relu), -1.0 if relu else 1.0, algo,
+                                                  ptr(wsb), ws_bytes), name)
+    _timed(f'lpips_conv[algo{algo}]', 2.0 * b * h * w * pin * pout * 9, 4.0 * b * h * w * (pin + pout), launch,
            shape=f'{pin}->{pout}x{h}x{w}')
 
 

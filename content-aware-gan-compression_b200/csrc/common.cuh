@@ -68,6 +68,9 @@ __host__ __device__ inline T ceil_div(T a, T b) { return (a + b - 1) / b; }
 constexpr float kSqrt2 = 1.41421356237309504880f;
 constexpr float kLreluSlope = 0.2f;
 constexpr int kNumSMs = 148;  // B200
+// ConvP::act of the convolution epilogues: none / leaky ReLU (or ReLU, act_gain < 0) / "the residual pointer is a ReLU
+// mask reference": out = acc * (ref > 0), the backward of a ReLU fused into the data-gradient convolution that feeds it
+constexpr int kActNone = 0, kActLrelu = 1, kActMaskRef = 3;
 
 __device__ __forceinline__ float lrelu_sqrt2(float v) { return (v > 0.f ? v : v * kLreluSlope) * kSqrt2; }
 // leaky ReLU with an explicit output gain (sqrt2 for StyleGAN2's scaled activation; 1 where a following 1/sqrt2 is folded in)

@@ -134,14 +134,19 @@ __global__ void __launch_bounds__(256, 2) conv_simt_kernel(const ConvP p) {
         }
         v[0] += bias4.x; v[1] += bias4.y; v[2] += bias4.z; v[3] += bias4.w;
         const int64_t off = (((int64_t)b * p.Hout + yy) * p.Wout + xx) * p.n_cols + n;
-        if (p.act) {
+        if (p.act == kActLrelu) {
             const float gain = (p.act_gain != 0.f) ? p.act_gain : kSqrt2;
 #pragma unroll
             for (int j = 0; j < 4; ++j) v[j] = lrelu_gain(v[j], gain);
         }
         if (p.residual) {
             const float4 r4 = ldg4(p.residual + off);
-            v[0] += r4.x; v[1] += r4.y; v[2] += r4.z; v[3] += r4.w;
+            if (p.act == kActMaskRef) {
+                v[0] = r4.x > 0.f ? v[0] : 0.f; v[1] = r4.y > 0.f ? v[1] : 0.f;
+                v[2] = r4.z > 0.f ? v[2] : 0.f; v[3] = r4.w > 0.f ? v[3] : 0.f;
+            } else {
+                v[0] += r4.x; v[1] += r4.y; v[2] += r4.z; v[3] += r4.w;
+            }
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j)
@@ -323,7 +328,7 @@ int cagc_conv_same_ws(cagc_stream_t stream_, const float* in, const float* w_sla
     p.bias = bias; p.out = out; p.workspace = workspace; p.workspace_bytes = workspace_bytes;
     p.B = B; p.Hin = H; p.Win = W; p.in_pitch = in_pitch; p.Ho = H; p.Wo = W; p.in_stride = 1;
     p.n_cols = out_pitch; p.out_valid = out_valid; p.Hout = H; p.Wout = W; p.out_stride = 1; p.out_oy = 0; p.out_ox = 0;
-    p.noise_bstride = noise_bstride; p.act = act; p.ntaps = ksize * ksize;
+    p.noise_bstride = noise_bstride; p.act = act ? kActLrelu : kActNone; p.ntaps = ksize * ksize;
     for (int ky = 0; ky < ksize; ++ky)
         for (int kx = 0; kx < ksize; ++kx) p.taps[ky * ksize + kx] = Tap{ky - ksize / 2, kx - ksize / 2, ky * ksize + kx};
     if (algo == 1) return cagc_tc_conv(stream, p, "conv_same[tc]");

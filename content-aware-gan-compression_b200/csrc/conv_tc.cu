@@ -243,11 +243,18 @@ __device__ __forceinline__ void epi_chunk(const EpiArgs& e, float* st, uint32_t 
         }
         if (e.has_noise) { o[0] += nzs[i]; o[1] += nzs[i]; o[2] += nzs[i]; o[3] += nzs[i]; }
         if (e.bias) { o[0] += b4.x; o[1] += b4.y; o[2] += b4.z; o[3] += b4.w; }
-        if (e.act) {
+        if (e.act == kActLrelu) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) o[j] = lrelu_gain(o[j], e.act_gain);
         }
-        if (e.residual) { o[0] += rs[i].x; o[1] += rs[i].y; o[2] += rs[i].z; o[3] += rs[i].w; }
+        if (e.residual) {
+            if (e.act == kActMaskRef) {
+                o[0] = rs[i].x > 0.f ? o[0] : 0.f; o[1] = rs[i].y > 0.f ? o[1] : 0.f;
+                o[2] = rs[i].z > 0.f ? o[2] : 0.f; o[3] = rs[i].w > 0.f ? o[3] : 0.f;
+            } else {
+                o[0] += rs[i].x; o[1] += rs[i].y; o[2] += rs[i].z; o[3] += rs[i].w;
+            }
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j)
             if (cn + j >= e.out_valid) o[j] = 0.f;
@@ -283,13 +290,18 @@ __device__ __forceinline__ void epi_rows_direct(const EpiArgs& e, uint32_t taddr
                 const float4 b4 = ldg4(e.bias + n);
                 o[0] += b4.x; o[1] += b4.y; o[2] += b4.z; o[3] += b4.w;
             }
-            if (e.act) {
+            if (e.act == kActLrelu) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) o[j] = lrelu_gain(o[j], e.act_gain);
             }
             if (res) {
                 const float4 r4 = ldg4(res + n);
-                o[0] += r4.x; o[1] += r4.y; o[2] += r4.z; o[3] += r4.w;
+                if (e.act == kActMaskRef) {
+                    o[0] = r4.x > 0.f ? o[0] : 0.f; o[1] = r4.y > 0.f ? o[1] : 0.f;
+                    o[2] = r4.z > 0.f ? o[2] : 0.f; o[3] = r4.w > 0.f ? o[3] : 0.f;
+                } else {
+                    o[0] += r4.x; o[1] += r4.y; o[2] += r4.z; o[3] += r4.w;
+                }
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j)
@@ -1991,13 +2003,18 @@ __global__ void __launch_bounds__(256) splitk_epilogue_kernel(const __grid_const
             const float4 b4 = ldg4(p.bias + n);
             o[0] += b4.x; o[1] += b4.y; o[2] += b4.z; o[3] += b4.w;
         }
-        if (p.act) {
+        if (p.act == kActLrelu) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) o[j] = lrelu_gain(o[j], p.act_gain);
         }
         if (p.residual) {
             const float4 r4 = ldg4(p.residual + i * 4);
-            o[0] += r4.x; o[1] += r4.y; o[2] += r4.z; o[3] += r4.w;
+            if (p.act == kActMaskRef) {
+                o[0] = r4.x > 0.f ? o[0] : 0.f; o[1] = r4.y > 0.f ? o[1] : 0.f;
+                o[2] = r4.z > 0.f ? o[2] : 0.f; o[3] = r4.w > 0.f ? o[3] : 0.f;
+            } else {
+                o[0] += r4.x; o[1] += r4.y; o[2] += r4.z; o[3] += r4.w;
+            }
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j)
@@ -2929,7 +2946,7 @@ int cagc_conv_same_psw(cagc_stream_t stream_, const float* in, const float* w_sl
     ConvP p{};
     same_conv_params(p, B, H, W, in_pitch, out_pitch, out_valid, ksize);
     p.in = in; p.w = w_ps; p.out_scale = out_scale; p.noise = noise; p.noise_w = noise_w; p.bias = bias; p.out = out;
-    p.noise_bstride = noise_bstride; p.act = act; p.w_bslabs = ksize * ksize;
+    p.noise_bstride = noise_bstride; p.act = act ? kActLrelu : kActNone; p.w_bslabs = ksize * ksize;
     return cagc_tc_conv(stream, p, "conv_same_psw[tc]");
 }
 

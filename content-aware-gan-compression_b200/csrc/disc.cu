@@ -274,9 +274,30 @@ int cagc_conv2d(cagc_stream_t stream, const float* in, const float* w_slabs, con
                           act, act_gain, algo, nullptr, 0);
 }
 
+static int conv2d_impl(cagc_stream_t stream_, const float* in, const float* w_slabs, const float* bias, const float* residual,
+                       float* out, int B, int Hin, int Win, int in_pitch, int out_pitch, int out_valid, int ksize, int mode,
+                       int act, float act_gain, int algo, float* workspace, int64_t workspace_bytes);
+
 int cagc_conv2d_ws(cagc_stream_t stream_, const float* in, const float* w_slabs, const float* bias, const float* residual,
                    float* out, int B, int Hin, int Win, int in_pitch, int out_pitch, int out_valid, int ksize, int mode,
                    int act, float act_gain, int algo, float* workspace, int64_t workspace_bytes) {
+    return conv2d_impl(stream_, in, w_slabs, bias, residual, out, B, Hin, Win, in_pitch, out_pitch, out_valid, ksize, mode,
+                       act ? kActLrelu : kActNone, act_gain, algo, workspace, workspace_bytes);
+}
+
+// out = conv(in, W) * (mask_ref > 0): a same-size data-gradient convolution with the backward of the ReLU that produced
+// its input activation (mask_ref, layout of out) applied in the epilogue
+int cagc_conv2d_mask_ws(cagc_stream_t stream_, const float* in, const float* w_slabs, const float* mask_ref, float* out,
+                        int B, int Hin, int Win, int in_pitch, int out_pitch, int out_valid, int ksize, int algo,
+                        float* workspace, int64_t workspace_bytes) {
+    CAGC_REQUIRE(mask_ref, "conv2d_mask: null mask reference");
+    return conv2d_impl(stream_, in, w_slabs, nullptr, mask_ref, out, B, Hin, Win, in_pitch, out_pitch, out_valid, ksize, 0,
+                       kActMaskRef, 1.f, algo, workspace, workspace_bytes);
+}
+
+static int conv2d_impl(cagc_stream_t stream_, const float* in, const float* w_slabs, const float* bias, const float* residual,
+                       float* out, int B, int Hin, int Win, int in_pitch, int out_pitch, int out_valid, int ksize, int mode,
+                       int act, float act_gain, int algo, float* workspace, int64_t workspace_bytes) {
     cudaStream_t stream = (cudaStream_t)stream_;
     CAGC_REQUIRE(in && w_slabs && out, "conv2d: null pointer");
     CAGC_REQUIRE(B >= 0 && Hin >= 0 && Win >= 0, "conv2d: negative size");
@@ -293,7 +314,7 @@ int cagc_conv2d_ws(cagc_stream_t stream_, const float* in, const float* w_slabs,
     p.workspace = workspace; p.workspace_bytes = workspace_bytes;
     p.B = B; p.Hin = Hin; p.Win = Win; p.in_pitch = in_pitch;
     p.n_cols = out_pitch; p.out_valid = out_valid; p.out_stride = 1; p.out_oy = 0; p.out_ox = 0;
-    p.act = act ? 1 : 0; p.act_gain = act_gain; p.ntaps = ksize * ksize;
+    p.act = act; p.act_gain = act_gain; p.ntaps = ksize * ksize;
     if (mode == 0) {
         p.Ho = Hin; p.Wo = Win; p.in_stride = 1;
         for (int ky = 0; ky < ksize; ++ky)

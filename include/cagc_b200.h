@@ -37,7 +37,7 @@ typedef void* cagc_stream_t; /* cudaStream_t */
 #define CAGC_E_UNSUPPORTED (-2) /* shape outside what the kernels implement */
 
 /* bump when a signature changes; the Python loader checks it */
-#define CAGC_ABI_VERSION 23
+#define CAGC_ABI_VERSION 24
 
 int cagc_abi_version(void);
 const char* cagc_last_error(void);
@@ -355,6 +355,13 @@ int cagc_conv_up_ws(cagc_stream_t stream, const float* in, const float* w_slabs,
 int cagc_conv2d_ws(cagc_stream_t stream, const float* in, const float* w_slabs, const float* bias, const float* residual,
                    float* out, int B, int Hin, int Win, int in_pitch, int out_pitch, int out_valid, int ksize, int mode,
                    int act, float act_gain, int algo, float* workspace, int64_t workspace_bytes);
+/* out = conv(in, W) * (mask_ref > 0), stride 1, same size: a data-gradient convolution (flipped / transposed slabs) with
+ * the backward of the ReLU that produced its input activation fused into the epilogue (VGG16 of the LPIPS loss:
+ * conv -> ReLU -> conv chains, lpips/pretrained_networks.py:100-114; replaces a threshold_backward pass per layer).
+ * mask_ref: the forward activation, layout of out. */
+int cagc_conv2d_mask_ws(cagc_stream_t stream, const float* in, const float* w_slabs, const float* mask_ref, float* out,
+                        int B, int Hin, int Win, int in_pitch, int out_pitch, int out_valid, int ksize, int algo,
+                        float* workspace, int64_t workspace_bytes);
 
 /* ----------------------------------------------------------------------
  * EqualLinear (reference model.py:137-166: F.linear(x, W * scale) + fused_leaky_relu(bias * lr_mul)) as one launch:
