@@ -197,7 +197,16 @@ class PerceptualLossVGG(nn.Module):
         for kk, i in enumerate(TAPS):
             if self.lin_weights[kk].numel() != chans[i]:
                 raise ValueError(f'PerceptualLossVGG: lin{kk} has {self.lin_weights[kk].numel()} weights, expected {chans[i]}')
-        self._shift, self._scale = _f3(shift), _f3(scale)
+        self.shift, self.scale = tuple(float(v) for v in shift), tuple(float(v) for v in scale)
+
+    # host-side float[3] arguments of the conv1_1 kernels (built per call: ctypes arrays do not pickle)
+    @property
+    def _shift(self):
+        return _f3(self.shift)
+
+    @property
+    def _scale(self):
+        return _f3(self.scale)
 
     @classmethod
     def from_reference(cls, percept_loss) -> 'PerceptualLossVGG':
